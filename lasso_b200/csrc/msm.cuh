@@ -1,0 +1,32 @@
+// lasso_b200 — launcher interface of the MSM kernels (msm_kernels.cu).
+#pragma once
+#include "common.cuh"
+
+namespace lb {
+
+static constexpr int kMsmWindowBits = 8;
+static constexpr int kMsmFullWindows = 32;  // 253-bit scalars + signed-digit headroom
+
+// T[w][j] = 2^(8w) * G_j in affine-niels form, w < nwindows, rows `stride` points apart
+void launch_build_table(const fq_t* bases_ark, size_t n, pt_niels* T, size_t stride, int nwindows, cudaStream_t st);
+// Montgomery -> canonical integers, atomicMax of the bit length into *d_max_bits
+void launch_canonicalize(const fr_t* in, fr_t* out, size_t n, unsigned* d_max_bits, cudaStream_t st);
+size_t msm_partials_count(int nrows, int ncols, int nw);
+// nrows independent MSMs over the same ncols bases.
+//   scalars: scalar_limbs == 1 -> u32 integers; == 8 -> canonical 256-bit integers (8 x u32)
+//   row r uses scalars[r*row_stride .. +ncols); nw = number of 8-bit windows to process
+//   (must cover max_bits + 2; <= 5 for u32, <= 32 for 256-bit)
+//   shifted != 0: `table` holds nw window tables (fixed-base); else only window 0 (variable-base)
+// Outputs (either may be null): out_ext = nrows x (x,y,t,z) arkworks Montgomery limbs with z = 1;
+// out_comp = nrows x 32 bytes ark-serialize compressed.
+void launch_msm_rows(const pt_niels* table, size_t table_stride, int shifted, const void* scalars, int scalar_limbs,
+                     size_t row_stride, int nrows, int ncols, int nw, pt_ext* partials, fq_t* out_ext,
+                     uint32_t* out_comp, cudaStream_t st);
+void launch_combine_points(const fq_t* in_ext, int n, fq_t* out_ext, uint32_t* out_comp, cudaStream_t st);
+
+inline int msm_windows_for_bits(unsigned max_bits) {
+  int nw = (int)((max_bits + 2 + kMsmWindowBits - 1) / kMsmWindowBits);
+  return nw < 1 ? 1 : nw;
+}
+
+}  // namespace lb

@@ -1,0 +1,407 @@
+// lasso_b200 — K6: Pippenger bucket MSM over curve25519 on sm_100a, row-batched with shared
+// bases.  Replaces src/msm/mod.rs:91-164 (msm_bigint_wnaf) and its callers
+// src/poly/commitments.rs:84-93 (batch_commit) / src/poly/dense_mlpoly.rs:109-128 (commit_inner:
+// L_size independent row MSMs over the same R_size generators).
+//
+// Shape of the work (SURVEY §7 "MSM shape"): thousands of independent rows of 2^9..2^14 terms over
+// the SAME generators, mostly tiny scalars — not one giant MSM.  So:
+//   * fixed window c = 8 with signed digits d in [-128, 127] via the offset trick
+//     (s + 0x80..80, then byte w minus 128): digits are independent per window, no carry chain;
+//   * the generators are expanded once into a table T[w][j] = 2^(8w) G_j in affine-niels form
+//     (96 B/point), so every window of a row lands in ONE bucket set and no doublings are needed;
+//   * one CTA per (window, row, column-chunk): counting sort of the chunk's digits in shared memory,
+//     then every thread adds an equal-sized contiguous slice of the sorted list (robust against
+//     skewed digits, e.g. 0/1-valued LT tables), bucket partials are stitched, and the weighted
+//     bucket sum  sum_b b*B_b  is a suffix scan + tree reduction over the 128 buckets;
+//   * a finish kernel adds the per-(window, chunk) partials of a row, normalises (one Fq inversion
+//     per row) and emits arkworks-layout points + compressed bytes.
+// For bases without a precomputed table (variable-base lasso_msm) the same kernels run with the
+// single window-0 table and the finish kernel does the 8-doubling Horner combination instead.
+// Integer-ALU bound (7 Fq muls per bucket add), not HBM bound: reported as point-adds/s.
+#include "kernels.cuh"
+#include "msm.cuh"
+
+namespace lb {
+
+static constexpr int MSM_T = 128;        // threads per CTA = number of buckets
+static constexpr int MSM_NB = 128;       // buckets 1..128 (|d|)
+static constexpr int MSM_CHUNK = 8192;   // max columns per CTA
+
+// ---------------------------------------------------------------- shared-memory point storage (SoA)
+// element (coord c, limb l) of point idx lives at base[(c*8 + l) * n + idx] -> conflict-free
+__device__ __forceinline__ void sm_store_pt(uint32_t* base, int n, int idx, const pt_ext& p) {
+#pragma unroll
+  for (int l = 0; l < 8; l++) {
+    base[(0 * 8 + l) * n + idx] = p.X.v[l];
+    base[(1 * 8 + l) * n + idx] = p.Y.v[l];
+    base[(2 * 8 + l) * n + idx] = p.Z.v[l];
+    base[(3 * 8 + l) * n + idx] = p.T.v[l];
+  }
+}
+__device__ __forceinline__ pt_ext sm_load_pt(const uint32_t* base, int n, int idx) {
+  pt_ext p;
+#pragma unroll
+  for (int l = 0; l < 8; l++) {
+    p.X.v[l] = base[(0 * 8 + l) * n + idx];
+    p.Y.v[l] = base[(1 * 8 + l) * n + idx];
+    p.Z.v[l] = base[(2 * 8 + l) * n + idx];
+    p.T.v[l] = base[(3 * 8 + l) * n + idx];
+  }
+  return p;
+}
+__device__ __forceinline__ pt_niels ld_niels(const pt_niels* p) {
+  pt_niels n;
+  n.yplusx = ld_fq(&p->yplusx);
+  n.yminusx = ld_fq(&p->yminusx);
+  n.t2d = ld_fq(&p->t2d);
+  return n;
+}
+__device__ __forceinline__ void st_niels(pt_niels* p, const pt_niels& n) {
+  st_fq(&p->yplusx, n.yplusx);
+  st_fq(&p->yminusx, n.yminusx);
+  st_fq(&p->t2d, n.t2d);
+}
+
+// ---------------------------------------------------------------- generator tables
+__global__ void __launch_bounds__(128) table_first_kernel(const fq_t* bases_ark /*n x (x,y)*/, size_t n, pt_niels* T) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  st_niels(T + j, niels_from_ark_affine(ld_fq(bases_ark + 2 * j), ld_fq(bases_ark + 2 * j + 1)));
+}
+// T[w][j] = 2^8 * T[w-1][j], renormalised to affine-niels
+__global__ void __launch_bounds__(128) table_next_kernel(pt_niels* T, size_t n, size_t stride, int w) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  pt_ext p = pt_from_niels(ld_niels(T + (size_t)(w - 1) * stride + j));
+#pragma unroll 1
+  for (int k = 0; k < 8; k++) p = pt_dbl(p);
+  fq_t zi = fq_inv(p.Z);
+  st_niels(T + (size_t)w * stride + j, niels_from_affine(fq_mul(p.X, zi), fq_mul(p.Y, zi)));
+}
+void launch_build_table(const fq_t* bases_ark, size_t n, pt_niels* T, size_t stride, int nwindows, cudaStream_t st) {
+  unsigned blocks = (unsigned)((n + 127) / 128);
+  table_first_kernel<<<blocks, 128, 0, st>>>(bases_ark, n, T);
+  for (int w = 1; w < nwindows; w++) table_next_kernel<<<blocks, 128, 0, st>>>(T, n, stride, w);
+}
+
+// ---------------------------------------------------------------- scalars
+// Montgomery Fr -> canonical integer (into_bigint, msm/mod.rs:23-25) + max bit length of the batch
+__global__ void __launch_bounds__(256) canonicalize_kernel(const fr_t* in, fr_t* out, size_t n, unsigned* max_bits) {
+  unsigned mb = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    fr_t c = fr_to_canonical(ld_fr(in + i));
+    st_fr(out + i, c);
+    unsigned b = 0;
+#pragma unroll
+    for (int l = 0; l < 8; l++)
+      if (c.v[l]) b = 32 * l + (32 - __clz(c.v[l]));
+    mb = b > mb ? b : mb;
+  }
+  mb = __reduce_max_sync(0xffffffffu, mb);
+  if ((threadIdx.x & 31) == 0 && mb) atomicMax(max_bits, mb);
+}
+void launch_canonicalize(const fr_t* in, fr_t* out, size_t n, unsigned* d_max_bits, cudaStream_t st) {
+  size_t b = (n + 255) / 256;
+  if (b > (size_t)kNumSMs * 8) b = kNumSMs * 8;
+  if (b == 0) return;
+  canonicalize_kernel<<<(unsigned)b, 256, 0, st>>>(in, out, n, d_max_bits);
+}
+
+// signed digit of window w (c = 8): byte w of (s + 0x80..80) minus 128
+template <int SL>
+__device__ __forceinline__ int msm_digit(const uint32_t* s, int w);
+template <>
+__device__ __forceinline__ int msm_digit<1>(const uint32_t* s, int w) {
+  uint64_t v = (uint64_t)s[0] + 0x8080808080ull;
+  return (int)((v >> (8 * w)) & 0xff) - 128;
+}
+template <>
+__device__ __forceinline__ int msm_digit<8>(const uint32_t* s, int w) {
+  // add 0x80808080 to every limb with carry, only as far as limb w/4
+  uint32_t carry = 0, limb = 0;
+  int top = w >> 2;
+#pragma unroll
+  for (int l = 0; l < 8; l++) {
+    if (l <= top) {
+      uint64_t t = (uint64_t)s[l] + 0x80808080u + carry;
+      limb = (uint32_t)t;
+      carry = (uint32_t)(t >> 32);
+    }
+  }
+  return (int)((limb >> (8 * (w & 3))) & 0xff) - 128;
+}
+
+// ---------------------------------------------------------------- the bucket kernel
+struct MsmSmem {
+  int cnt[MSM_NB + 2];
+  int off[MSM_NB + 2];
+  int cur[MSM_NB + 2];
+  int pf_b[MSM_T], pl_b[MSM_T];
+  uint16_t list[MSM_CHUNK];
+  uint32_t bucket[32 * (MSM_NB + 1)];  // SoA, index 0 unused (digit 0)
+  uint32_t pfirst[32 * MSM_T];
+  uint32_t plast[32 * MSM_T];
+};
+
+template <int SL>
+__global__ void __launch_bounds__(MSM_T)
+    msm_bucket_kernel(const pt_niels* table, size_t table_stride, int shifted, const uint32_t* scalars,
+                      size_t row_stride /*in scalars*/, int ncols, int chunk_cols, pt_ext* partials) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MsmSmem& sm = *reinterpret_cast<MsmSmem*>(smem_raw);
+  const int w = blockIdx.x, row = blockIdx.y, chunk = blockIdx.z, tid = threadIdx.x;
+  const int c_begin = chunk * chunk_cols;
+  const int c_end = min(ncols, c_begin + chunk_cols);
+  const pt_niels* tw = shifted ? table + (size_t)w * table_stride : table;
+  const uint32_t* srow = scalars + ((size_t)row * row_stride) * SL;
+
+  for (int b = tid; b < MSM_NB + 2; b += MSM_T) sm.cnt[b] = 0;
+  sm.pf_b[tid] = 0;
+  sm.pl_b[tid] = 0;
+  __syncthreads();
+  // pass 1: histogram of |digit|
+  for (int c = c_begin + tid; c < c_end; c += MSM_T) {
+    uint32_t s[SL];
+#pragma unroll
+    for (int l = 0; l < SL; l++) s[l] = srow[(size_t)c * SL + l];
+    int d = msm_digit<SL>(s, w);
+    if (d) atomicAdd(&sm.cnt[d < 0 ? -d : d], 1);
+  }
+  __syncthreads();
+  // exclusive scan over buckets 1..128 (one warp, 4 buckets per lane)
+  if (tid < 32) {
+    int v[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      v[k] = sm.cnt[1 + tid * 4 + k];
+      sum += v[k];
+    }
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (tid >= d) incl += t;
+    }
+    int run = incl - sum;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      sm.off[1 + tid * 4 + k] = run;
+      sm.cur[1 + tid * 4 + k] = run;
+      run += v[k];
+    }
+    if (tid == 31) sm.off[MSM_NB + 1] = run;
+  }
+  // every bucket starts as the identity
+  sm_store_pt(sm.bucket, MSM_NB + 1, tid + 1, pt_identity());
+  __syncthreads();
+  const int N = sm.off[MSM_NB + 1];
+  if (N == 0) {
+    if (tid == 0) partials[((size_t)row * gridDim.x + w) * gridDim.z + chunk] = pt_identity();
+    return;
+  }
+  // pass 2: scatter (column-in-chunk | sign) into the sorted list
+  for (int c = c_begin + tid; c < c_end; c += MSM_T) {
+    uint32_t s[SL];
+#pragma unroll
+    for (int l = 0; l < SL; l++) s[l] = srow[(size_t)c * SL + l];
+    int d = msm_digit<SL>(s, w);
+    if (d) {
+      int pos = atomicAdd(&sm.cur[d < 0 ? -d : d], 1);
+      sm.list[pos] = (uint16_t)((c - c_begin) | (d < 0 ? 0x8000 : 0));
+    }
+  }
+  __syncthreads();
+  // accumulate: thread t owns the contiguous slice [lo, hi) of the sorted list
+  {
+    const int lo = (int)(((long long)tid * N) / MSM_T), hi = (int)(((long long)(tid + 1) * N) / MSM_T);
+    if (lo < hi) {
+      // bucket containing position lo: largest b with off[b] <= lo
+      int b = 1;
+      {
+        int l = 1, r = MSM_NB;
+        while (l < r) {
+          int m = (l + r + 1) >> 1;
+          if (sm.off[m] <= lo) l = m; else r = m - 1;
+        }
+        b = l;
+      }
+      int pos = lo;
+      while (pos < hi) {
+        while (sm.off[b + 1] <= pos) b++;  // skip exhausted / empty buckets
+        const int bend = sm.off[b + 1];
+        const int run_end = bend < hi ? bend : hi;
+        pt_ext acc = pt_identity();
+        for (int p = pos; p < run_end; p++) {
+          uint16_t e = sm.list[p];
+          pt_niels nn = ld_niels(tw + c_begin + (e & 0x7fff));
+          acc = (e & 0x8000) ? pt_msub(acc, nn) : pt_madd(acc, nn);
+        }
+        const bool complete = (pos == sm.off[b]) && (run_end == bend);
+        if (complete) {
+          sm_store_pt(sm.bucket, MSM_NB + 1, b, acc);
+        } else if (pos == lo) {
+          sm_store_pt(sm.pfirst, MSM_T, tid, acc);
+          sm.pf_b[tid] = b;
+        } else {
+          sm_store_pt(sm.plast, MSM_T, tid, acc);
+          sm.pl_b[tid] = b;
+        }
+        pos = run_end;
+      }
+    }
+  }
+  __syncthreads();
+  // stitch partial runs into their buckets: thread t owns bucket t+1
+  {
+    const int b = tid + 1;
+    pt_ext acc = sm_load_pt(sm.bucket, MSM_NB + 1, b);
+    bool touched = false;
+    for (int t = 0; t < MSM_T; t++) {
+      if (sm.pf_b[t] == b) {
+        acc = pt_add(acc, sm_load_pt(sm.pfirst, MSM_T, t));
+        touched = true;
+      }
+      if (sm.pl_b[t] == b) {
+        acc = pt_add(acc, sm_load_pt(sm.plast, MSM_T, t));
+        touched = true;
+      }
+    }
+    if (touched) sm_store_pt(sm.bucket, MSM_NB + 1, b, acc);
+  }
+  __syncthreads();
+  // weighted sum  sum_b b * B_b = sum_{k>=1} (sum_{b>=k} B_b): suffix scan, then tree reduction.
+  // Reuse pfirst as the ping-pong buffer.
+  {
+    const int b = tid + 1;
+    pt_ext mine = sm_load_pt(sm.bucket, MSM_NB + 1, b);
+    uint32_t* bufA = sm.bucket;  // stride MSM_NB+1, index b
+    uint32_t* bufB = sm.pfirst;  // stride MSM_T, index tid
+    bool inA = true;
+    for (int d = 1; d < MSM_NB; d <<= 1) {
+      pt_ext other;
+      bool has = (tid + d) < MSM_NB;
+      if (has) other = inA ? sm_load_pt(bufA, MSM_NB + 1, b + d) : sm_load_pt(bufB, MSM_T, tid + d);
+      if (has) mine = pt_add(mine, other);
+      if (inA) sm_store_pt(bufB, MSM_T, tid, mine); else sm_store_pt(bufA, MSM_NB + 1, b, mine);
+      inA = !inA;
+      __syncthreads();
+    }
+    // `mine` = suffix sum S_b; now sum all S_b
+    for (int d = MSM_NB / 2; d >= 1; d >>= 1) {
+      pt_ext other;
+      bool act = tid < d;
+      if (act) other = inA ? sm_load_pt(bufA, MSM_NB + 1, b + d) : sm_load_pt(bufB, MSM_T, tid + d);
+      if (act) mine = pt_add(mine, other);
+      if (inA) sm_store_pt(bufB, MSM_T, tid, mine); else sm_store_pt(bufA, MSM_NB + 1, b, mine);
+      inA = !inA;
+      __syncthreads();
+    }
+    if (tid == 0) partials[((size_t)row * gridDim.x + w) * gridDim.z + chunk] = mine;
+  }
+}
+
+// ---------------------------------------------------------------- finish: combine, normalise, emit
+// out_ext: per row 4 x Fq arkworks Montgomery limbs (x, y, t, z=1) or null; out_comp: 32 B/row or null.
+__global__ void __launch_bounds__(64)
+    msm_finish_kernel(const pt_ext* partials, int nrows, int nw, int nchunks, int shifted, fq_t* out_ext,
+                      uint32_t* out_comp) {
+  int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= nrows) return;
+  const pt_ext* p = partials + (size_t)row * nw * nchunks;
+  pt_ext acc = pt_identity();
+  if (shifted) {
+    for (int i = 0; i < nw * nchunks; i++) acc = pt_add(acc, p[i]);
+  } else {
+    // msm/mod.rs:150-163: total = sum_w 2^(8w) W_w, high to low with 8 doublings per window
+    for (int w = nw - 1; w >= 0; w--) {
+      if (w != nw - 1)
+        for (int k = 0; k < 8; k++) acc = pt_dbl(acc);
+      for (int c = 0; c < nchunks; c++) acc = pt_add(acc, p[(size_t)w * nchunks + c]);
+    }
+  }
+  fq_t x, y;
+  pt_to_affine_canonical(acc, x, y);
+  if (out_comp) {
+    uint32_t c[8];
+    pt_compress_canonical(x, y, c);
+#pragma unroll
+    for (int l = 0; l < 8; l++) out_comp[(size_t)row * 8 + l] = c[l];
+  }
+  if (out_ext) {
+    fq_t one = fq_one();
+    out_ext[(size_t)row * 4 + 0] = fq_to_ark(x);
+    out_ext[(size_t)row * 4 + 1] = fq_to_ark(y);
+    out_ext[(size_t)row * 4 + 2] = fq_to_ark(fq_mul(x, y));
+    out_ext[(size_t)row * 4 + 3] = fq_to_ark(one);
+  }
+}
+
+size_t msm_partials_count(int nrows, int ncols, int nw) {
+  int chunk_cols = ncols < MSM_CHUNK ? ncols : MSM_CHUNK;
+  int nchunks = (ncols + chunk_cols - 1) / chunk_cols;
+  return (size_t)nrows * nw * nchunks;
+}
+
+void launch_msm_rows(const pt_niels* table, size_t table_stride, int shifted, const void* scalars, int scalar_limbs,
+                     size_t row_stride, int nrows, int ncols, int nw, pt_ext* partials, fq_t* out_ext,
+                     uint32_t* out_comp, cudaStream_t st) {
+  if (nrows <= 0) return;
+  if (nw < 1) nw = 1;
+  int chunk_cols = ncols < MSM_CHUNK ? ncols : MSM_CHUNK;
+  if (chunk_cols < 1) chunk_cols = 1;
+  int nchunks = (ncols + chunk_cols - 1) / chunk_cols;
+  if (nchunks < 1) nchunks = 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LB_CUDA_CHECK(cudaFuncSetAttribute(msm_bucket_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MsmSmem)));
+    LB_CUDA_CHECK(cudaFuncSetAttribute(msm_bucket_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MsmSmem)));
+    attr_set = true;
+  }
+  // gridDim.y is limited to 65535 rows per launch
+  for (int r0 = 0; r0 < nrows; r0 += 65535) {
+    int nr = nrows - r0 < 65535 ? nrows - r0 : 65535;
+    dim3 grid(nw, nr, nchunks);
+    pt_ext* part = partials + (size_t)r0 * nw * nchunks;
+    if (scalar_limbs == 1)
+      msm_bucket_kernel<1><<<grid, MSM_T, sizeof(MsmSmem), st>>>(
+          table, table_stride, shifted, (const uint32_t*)scalars + (size_t)r0 * row_stride, row_stride, ncols,
+          chunk_cols, part);
+    else
+      msm_bucket_kernel<8><<<grid, MSM_T, sizeof(MsmSmem), st>>>(
+          table, table_stride, shifted, (const uint32_t*)scalars + (size_t)r0 * row_stride * 8, row_stride, ncols,
+          chunk_cols, part);
+  }
+  msm_finish_kernel<<<(nrows + 63) / 64, 64, 0, st>>>(partials, nrows, nw, nchunks, shifted, out_ext, out_comp);
+}
+
+// sum of a few extended points + normalisation (used to add a blind*h term or combine rows)
+__global__ void combine_points_kernel(const fq_t* in_ext /*n x 4 ark*/, int n, fq_t* out_ext, uint32_t* out_comp) {
+  if (threadIdx.x || blockIdx.x) return;
+  pt_ext acc = pt_identity();
+  for (int i = 0; i < n; i++) {
+    pt_ext p;
+    p.X = fq_from_ark(in_ext[4 * i + 0]);
+    p.Y = fq_from_ark(in_ext[4 * i + 1]);
+    p.T = fq_from_ark(in_ext[4 * i + 2]);
+    p.Z = fq_from_ark(in_ext[4 * i + 3]);
+    acc = pt_add(acc, p);
+  }
+  fq_t x, y;
+  pt_to_affine_canonical(acc, x, y);
+  if (out_comp) {
+    uint32_t c[8];
+    pt_compress_canonical(x, y, c);
+    for (int l = 0; l < 8; l++) out_comp[l] = c[l];
+  }
+  if (out_ext) {
+    out_ext[0] = fq_to_ark(x);
+    out_ext[1] = fq_to_ark(y);
+    out_ext[2] = fq_to_ark(fq_mul(x, y));
+    out_ext[3] = fq_to_ark(fq_one());
+  }
+}
+void launch_combine_points(const fq_t* in_ext, int n, fq_t* out_ext, uint32_t* out_comp, cudaStream_t st) {
+  combine_points_kernel<<<1, 32, 0, st>>>(in_ext, n, out_ext, out_comp);
+}
+
+}  // namespace lb

@@ -1,0 +1,555 @@
+// lasso_b200 — CUDA kernels (sm_100a) for the multilinear-polynomial side of the Lasso prover
+// hot path: bind (K1), sumcheck round evaluation (K2, K3), eq evals (K4), subtable
+// materialisation + gather (K5), and the supporting reductions (K7).  SURVEY.md §2.2.
+//
+// All of these are streaming integer kernels over 32-byte field elements: one element per
+// thread per 256-bit load (a warp covers 1 KiB contiguous), grid sized as a multiple of the
+// 148 SMs, grid-stride loops, warp-shuffle + shared-memory reductions for partial sums.
+// No tensor cores: this is 256-bit modular integer arithmetic, not a dense contraction.
+#include "kernels.cuh"
+
+namespace lb {
+
+static constexpr int kThreads = 256;
+static constexpr int kBlocksPerSM = 4;
+static constexpr int kMaxBlocks = kNumSMs * kBlocksPerSM;  // 592
+
+static inline int grid_for(size_t n, int threads = kThreads, int max_blocks = kMaxBlocks) {
+  size_t b = (n + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > (size_t)max_blocks) b = max_blocks;
+  return (int)b;
+}
+int sumcheck_max_blocks() { return kMaxBlocks; }
+
+// ------------------------------------------------------------------------------------ K1
+// dense_mlpoly.rs:209-216 — algorithmic traffic 96 B per output element, 1 modmul.
+__global__ void __launch_bounds__(kThreads) bind_top_kernel(fr_t* base, size_t stride, size_t half, fr_t r) {
+  fr_t* Z = base + (size_t)blockIdx.y * stride;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
+    fr_t lo = ld_fr_stream(Z + i), hi = ld_fr_stream(Z + half + i);
+    st_fr(Z + i, fr_add(lo, fr_mul(r, fr_sub(hi, lo))));
+  }
+}
+__global__ void __launch_bounds__(kThreads) bind_top_ptrs_kernel(fr_t* const* ptrs, size_t half, fr_t r) {
+  fr_t* Z = ptrs[blockIdx.y];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
+    fr_t lo = ld_fr_stream(Z + i), hi = ld_fr_stream(Z + half + i);
+    st_fr(Z + i, fr_add(lo, fr_mul(r, fr_sub(hi, lo))));
+  }
+}
+// dense_mlpoly.rs:218-225
+__global__ void __launch_bounds__(kThreads) bind_bot_kernel(const fr_t* Z, fr_t* out, size_t half, fr_t r) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
+    fr_t lo = ld_fr(Z + 2 * i), hi = ld_fr(Z + 2 * i + 1);
+    st_fr(out + i, fr_add(lo, fr_mul(r, fr_sub(hi, lo))));
+  }
+}
+void launch_bind_top(fr_t* base, size_t stride, int npolys, size_t half, const fr_t& r, cudaStream_t st) {
+  if (half == 0 || npolys == 0) return;
+  int per = kMaxBlocks / npolys;
+  if (per < kNumSMs / 4) per = kNumSMs / 4;
+  dim3 grid(grid_for(half, kThreads, per), npolys);
+  bind_top_kernel<<<grid, kThreads, 0, st>>>(base, stride, half, r);
+}
+void launch_bind_top_ptrs(fr_t* const* d_ptrs, int npolys, size_t half, const fr_t& r, cudaStream_t st) {
+  if (half == 0 || npolys == 0) return;
+  int per = kMaxBlocks / npolys;
+  if (per < kNumSMs / 4) per = kNumSMs / 4;
+  dim3 grid(grid_for(half, kThreads, per), npolys);
+  bind_top_ptrs_kernel<<<grid, kThreads, 0, st>>>(d_ptrs, half, r);
+}
+void launch_bind_bot(const fr_t* Z, fr_t* out, size_t half, const fr_t& r, cudaStream_t st) {
+  if (half == 0) return;
+  bind_bot_kernel<<<grid_for(half), kThreads, 0, st>>>(Z, out, half, r);
+}
+
+// ------------------------------------------------------------------------------------ K4
+// eq_poly.rs:21-38.  evals[i] = prod_j (bit_{l-1-j}(i) ? r_j : 1 - r_j), r[0] <-> MSB.
+// Small tables by the reference's doubling recurrence inside one CTA; big tables as the outer
+// product T_hi (x) T_lo: one modmul and one 32-byte write per output.
+__global__ void __launch_bounds__(1024) eq_small_kernel(FrVec r, int r_off, int ell, fr_t* out) {
+  // out has 2^ell entries, ell <= 12
+  if (threadIdx.x == 0) out[0] = fr_one();
+  __syncthreads();
+  int size = 1;
+  for (int j = 0; j < ell; j++) {
+    fr_t rj = r.v[r_off + j];
+    fr_t old[2];
+    int cnt = 0;
+    for (int i = threadIdx.x; i < size; i += blockDim.x) old[cnt++] = out[i];
+    __syncthreads();
+    cnt = 0;
+    for (int i = threadIdx.x; i < size; i += blockDim.x) {
+      fr_t s = old[cnt++];
+      fr_t hi = fr_mul(s, rj);
+      out[2 * i + 1] = hi;
+      out[2 * i] = fr_sub(s, hi);
+    }
+    __syncthreads();
+    size *= 2;
+  }
+}
+__global__ void __launch_bounds__(kThreads) eq_outer_kernel(const fr_t* t_hi, const fr_t* t_lo, int ell_lo,
+                                                            size_t n, fr_t* out) {
+  size_t mask = ((size_t)1 << ell_lo) - 1;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    fr_t a = t_hi[i >> ell_lo], b = t_lo[i & mask];
+    st_fr(out + i, fr_mul(a, b));
+  }
+}
+void launch_eq_evals(const FrVec& r, int ell, fr_t* out, fr_t* scratch, cudaStream_t st) {
+  if (ell <= 11) {
+    eq_small_kernel<<<1, 1024, 0, st>>>(r, 0, ell, out);
+    return;
+  }
+  int ell_lo = ell / 2 > 11 ? 11 : ell / 2;
+  int ell_hi = ell - ell_lo;
+  if (ell_hi > 11) {  // very large tables: build hi recursively into the tail of `out` first
+    // 2^ell_hi entries fit in out; compute hi table there with a recursive outer product
+    fr_t* hi_tab = out + (((size_t)1 << ell) - ((size_t)1 << ell_hi));
+    FrVec rh = r;
+    launch_eq_evals(rh, ell_hi, hi_tab, scratch, st);  // uses scratch internally, finished before reuse below
+    eq_small_kernel<<<1, 1024, 0, st>>>(r, ell_hi, ell_lo, scratch);
+    // the in-place hazard: out[i] for i near the end overlaps hi_tab.  Process through a copy of hi_tab
+    // is avoided by noting out index i reads hi_tab[i >> ell_lo]; the last 2^ell_hi outputs (which
+    // overwrite hi_tab) only need hi_tab entries >= 2^ell_hi - 2^(ell_hi-ell_lo), i.e. a hazard exists.
+    // Keep it simple and correct: stage hi_tab in scratch + 4096.
+    // (ell_hi <= 16 here since ell <= 28 and ell_lo = 11 -> up to 2^17 entries; callers size scratch.)
+    cudaMemcpyAsync(scratch + 4096, hi_tab, sizeof(fr_t) << ell_hi, cudaMemcpyDeviceToDevice, st);
+    size_t n = (size_t)1 << ell;
+    eq_outer_kernel<<<grid_for(n), kThreads, 0, st>>>(scratch + 4096, scratch, ell_lo, n, out);
+    return;
+  }
+  eq_small_kernel<<<1, 1024, 0, st>>>(r, 0, ell_hi, scratch);
+  eq_small_kernel<<<1, 1024, 0, st>>>(r, ell_hi, ell_lo, scratch + 4096);
+  size_t n = (size_t)1 << ell;
+  eq_outer_kernel<<<grid_for(n), kThreads, 0, st>>>(scratch, scratch + 4096, ell_lo, n, out);
+}
+
+// ------------------------------------------------------------------------------------ partial-sum reduce
+// partial: [nv][nblocks]; out[v] = sum_b partial[v][b].  One CTA per value.
+__global__ void __launch_bounds__(kThreads) reduce_partials_kernel(const fr_t* partial, int nblocks, fr_t* out) {
+  __shared__ fr_t scratch[kThreads / 32];
+  const fr_t* p = partial + (size_t)blockIdx.x * nblocks;
+  fr_t acc[1] = {fr_zero()};
+  for (int i = threadIdx.x; i < nblocks; i += blockDim.x) acc[0] = fr_add(acc[0], p[i]);
+  block_sum_fr<1>(acc, scratch);
+  if (threadIdx.x == 0) out[blockIdx.x] = acc[0];
+}
+
+// ------------------------------------------------------------------------------------ K2
+// sumcheck.rs:179-237 for the strategies whose g is linear in the E_k:
+//   g(E, eq) = (sum_k 2^(k*inc) E_k) * eq      (and.rs:45-53, or.rs, xor.rs, range_check.rs:78-86)
+// degree 2 -> evaluation points t = 0, 1, 2 with P(t) = lo + t (hi - lo) built incrementally.
+// Reads 2 * 32 B per polynomial per index pair (64 B/pair/poly algorithmic).
+__global__ void __launch_bounds__(kThreads)
+    sc_eval_linear_kernel(const fr_t* base, size_t stride, int alpha, size_t half, FrVec w, fr_t* partial) {
+  __shared__ fr_t scratch[3 * kThreads / 32];
+  fr_t acc[3] = {fr_zero(), fr_zero(), fr_zero()};
+  const fr_t* eq = base + (size_t)alpha * stride;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
+    fr_t c0 = ld_fr_stream(base + i), c1 = ld_fr_stream(base + half + i);  // weight 2^0
+    for (int k = 1; k < alpha; k++) {
+      const fr_t* P = base + (size_t)k * stride;
+      c0 = fr_add(c0, fr_mul(w.v[k], ld_fr_stream(P + i)));
+      c1 = fr_add(c1, fr_mul(w.v[k], ld_fr_stream(P + half + i)));
+    }
+    fr_t q0 = ld_fr_stream(eq + i), q1 = ld_fr_stream(eq + half + i);
+    acc[0] = fr_add(acc[0], fr_mul(c0, q0));
+    acc[1] = fr_add(acc[1], fr_mul(c1, q1));
+    fr_t c2 = fr_sub(fr_dbl(c1), c0), q2 = fr_sub(fr_dbl(q1), q0);
+    acc[2] = fr_add(acc[2], fr_mul(c2, q2));
+  }
+  block_sum_fr<3>(acc, scratch);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int t = 0; t < 3; t++) partial[(size_t)t * gridDim.x + blockIdx.x] = acc[t];
+  }
+}
+
+// LT strategy (lt.rs:60-69): g = sum_i LT_i prod_{j<i} EQ_j, memories ordered LT_0, EQ_0, LT_1, ...
+// Evaluated by Horner from the last pair, h_t <- LT_k(t) + EQ_k(t) * h_t, for all C+2 points t at once
+// so only two polynomials' values are live at a time.
+template <int C>
+__global__ void __launch_bounds__(128)
+    sc_eval_lt_kernel(const fr_t* base, size_t stride, size_t half, fr_t* partial) {
+  constexpr int NP = C + 2;  // degree C+1
+  __shared__ fr_t scratch[NP * 128 / 32];
+  fr_t acc[NP];
+#pragma unroll
+  for (int t = 0; t < NP; t++) acc[t] = fr_zero();
+  const fr_t* eq = base + (size_t)(2 * C) * stride;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
+    fr_t h[NP];
+#pragma unroll
+    for (int t = 0; t < NP; t++) h[t] = fr_zero();
+#pragma unroll 1
+    for (int k = C - 1; k >= 0; k--) {
+      const fr_t* PL = base + (size_t)(2 * k) * stride;
+      const fr_t* PE = base + (size_t)(2 * k + 1) * stride;
+      fr_t l0 = ld_fr(PL + i), l1 = ld_fr(PL + half + i);
+      fr_t e0 = ld_fr(PE + i), e1 = ld_fr(PE + half + i);
+      fr_t dl = fr_sub(l1, l0), de = fr_sub(e1, e0);
+      fr_t cl = l0, ce = e0;
+#pragma unroll
+      for (int t = 0; t < NP; t++) {
+        h[t] = fr_add(cl, fr_mul(ce, h[t]));
+        cl = fr_add(cl, dl);
+        ce = fr_add(ce, de);
+      }
+    }
+    fr_t q0 = ld_fr(eq + i), q1 = ld_fr(eq + half + i);
+    fr_t dq = fr_sub(q1, q0), cq = q0;
+#pragma unroll
+    for (int t = 0; t < NP; t++) {
+      acc[t] = fr_add(acc[t], fr_mul(h[t], cq));
+      cq = fr_add(cq, dq);
+    }
+  }
+  block_sum_fr<NP>(acc, scratch);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int t = 0; t < NP; t++) partial[(size_t)t * gridDim.x + blockIdx.x] = acc[t];
+  }
+}
+
+static FrVec linear_weights(const Strategy& S) {
+  FrVec w;
+  int inc = S.kind == STRAT_RANGE ? S.log_m : S.log_m / 2;
+  for (int k = 0; k < S.num_memories(); k++) w.v[k] = fr_from_u64(1ull << (k * inc));  // F::from(1u64 << (i*inc))
+  return w;
+}
+
+template <int C>
+static void launch_lt(const fr_t* base, size_t stride, size_t half, fr_t* partial, int blocks, cudaStream_t st) {
+  sc_eval_lt_kernel<C><<<blocks, 128, 0, st>>>(base, stride, half, partial);
+}
+
+void launch_sumcheck_eval_arbitrary(const Strategy& S, const fr_t* base, size_t stride, size_t half, fr_t* partial,
+                                    fr_t* out, cudaStream_t st) {
+  int npts = S.sumcheck_poly_degree() + 1;
+  int blocks;
+  if (S.kind == STRAT_LT) {
+    blocks = grid_for(half, 128, kMaxBlocks);
+    switch (S.C) {
+      case 1: launch_lt<1>(base, stride, half, partial, blocks, st); break;
+      case 2: launch_lt<2>(base, stride, half, partial, blocks, st); break;
+      case 3: launch_lt<3>(base, stride, half, partial, blocks, st); break;
+      case 4: launch_lt<4>(base, stride, half, partial, blocks, st); break;
+      case 8: launch_lt<8>(base, stride, half, partial, blocks, st); break;
+      default: throw std::runtime_error("LT strategy: unsupported C (1,2,3,4,8 are built)");
+    }
+  } else {
+    blocks = grid_for(half);
+    sc_eval_linear_kernel<<<blocks, kThreads, 0, st>>>(base, stride, S.num_memories(), half, linear_weights(S), partial);
+  }
+  reduce_partials_kernel<<<npts, kThreads, 0, st>>>(partial, blocks, out);
+}
+
+// subtables/mod.rs:186-216: sum_k eq[k] * g(E_1[k], ..., E_alpha[k]) over the whole hypercube
+__global__ void __launch_bounds__(kThreads)
+    claim_linear_kernel(const fr_t* base, size_t stride, int alpha, size_t n, FrVec w, fr_t* partial) {
+  __shared__ fr_t scratch[kThreads / 32];
+  fr_t acc[1] = {fr_zero()};
+  const fr_t* eq = base + (size_t)alpha * stride;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    fr_t c = ld_fr_stream(base + i);
+    for (int k = 1; k < alpha; k++) c = fr_add(c, fr_mul(w.v[k], ld_fr_stream(base + (size_t)k * stride + i)));
+    acc[0] = fr_add(acc[0], fr_mul(c, ld_fr_stream(eq + i)));
+  }
+  block_sum_fr<1>(acc, scratch);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc[0];
+}
+__global__ void __launch_bounds__(kThreads)
+    claim_lt_kernel(const fr_t* base, size_t stride, int C, size_t n, fr_t* partial) {
+  __shared__ fr_t scratch[kThreads / 32];
+  fr_t acc[1] = {fr_zero()};
+  const fr_t* eq = base + (size_t)(2 * C) * stride;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    fr_t h = fr_zero();
+    for (int k = C - 1; k >= 0; k--) {
+      fr_t l = ld_fr(base + (size_t)(2 * k) * stride + i), e = ld_fr(base + (size_t)(2 * k + 1) * stride + i);
+      h = fr_add(l, fr_mul(e, h));
+    }
+    acc[0] = fr_add(acc[0], fr_mul(h, ld_fr(eq + i)));
+  }
+  block_sum_fr<1>(acc, scratch);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc[0];
+}
+void launch_sumcheck_claim(const Strategy& S, const fr_t* base, size_t stride, size_t n, fr_t* partial, fr_t* out,
+                           cudaStream_t st) {
+  int blocks = grid_for(n);
+  if (S.kind == STRAT_LT)
+    claim_lt_kernel<<<blocks, kThreads, 0, st>>>(base, stride, S.C, n, partial);
+  else
+    claim_linear_kernel<<<blocks, kThreads, 0, st>>>(base, stride, S.num_memories(), n, linear_weights(S), partial);
+  reduce_partials_kernel<<<1, kThreads, 0, st>>>(partial, blocks, out);
+}
+
+// ------------------------------------------------------------------------------------ K3
+// sumcheck.rs:49-93: per circuit (e0, e2, e3) = sum_i A B C at t = 0, 2, 3.
+__global__ void __launch_bounds__(kThreads)
+    sc_eval_cubic_kernel(fr_t* const* A, fr_t* const* B, const fr_t* Ceq, size_t half, fr_t* partial) {
+  __shared__ fr_t scratch[3 * kThreads / 32];
+  const fr_t* a = A[blockIdx.y];
+  const fr_t* b = B[blockIdx.y];
+  fr_t acc[3] = {fr_zero(), fr_zero(), fr_zero()};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
+    fr_t a0 = ld_fr_stream(a + i), a1 = ld_fr_stream(a + half + i);
+    fr_t b0 = ld_fr_stream(b + i), b1 = ld_fr_stream(b + half + i);
+    fr_t c0 = ld_fr(Ceq + i), c1 = ld_fr(Ceq + half + i);
+    acc[0] = fr_add(acc[0], fr_mul(fr_mul(a0, b0), c0));
+    fr_t da = fr_sub(a1, a0), db = fr_sub(b1, b0), dc = fr_sub(c1, c0);
+    fr_t a2 = fr_add(a1, da), b2 = fr_add(b1, db), c2 = fr_add(c1, dc);
+    acc[1] = fr_add(acc[1], fr_mul(fr_mul(a2, b2), c2));
+    fr_t a3 = fr_add(a2, da), b3 = fr_add(b2, db), c3 = fr_add(c2, dc);
+    acc[2] = fr_add(acc[2], fr_mul(fr_mul(a3, b3), c3));
+  }
+  block_sum_fr<3>(acc, scratch);
+  if (threadIdx.x == 0) {
+    // layout [circuit][t][block] so one reduce CTA handles one (circuit, t)
+#pragma unroll
+    for (int t = 0; t < 3; t++)
+      partial[((size_t)blockIdx.y * 3 + t) * gridDim.x + blockIdx.x] = acc[t];
+  }
+}
+void launch_sumcheck_eval_cubic(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Ceq, int ncirc, size_t half,
+                                fr_t* partial, fr_t* out, cudaStream_t st) {
+  int per = kMaxBlocks / ncirc;
+  if (per < 1) per = 1;
+  int bx = grid_for(half, kThreads, per);
+  dim3 grid(bx, ncirc);
+  sc_eval_cubic_kernel<<<grid, kThreads, 0, st>>>(d_A, d_B, Ceq, half, partial);
+  reduce_partials_kernel<<<ncirc * 3, kThreads, 0, st>>>(partial, bx, out);
+}
+
+// ------------------------------------------------------------------------------------ K5
+__device__ __forceinline__ uint32_t subtable_value(int kind, int sub, uint32_t idx, int log_m, int log_r) {
+  if (kind == STRAT_RANGE) {  // range_check.rs:15-34
+    if (sub == 0) return idx;
+    if (sub == 1) return idx < (1u << (log_r % log_m)) ? idx : 0u;
+    return 0u;
+  }
+  int bits = log_m / 2;  // utils/mod.rs:82-89 split_bits: (high, low)
+  uint32_t lhs = (idx >> bits) & ((1u << bits) - 1), rhs = idx & ((1u << bits) - 1);
+  switch (kind) {
+    case STRAT_AND: return lhs & rhs;
+    case STRAT_OR: return lhs | rhs;
+    case STRAT_XOR: return lhs ^ rhs;
+    default: return sub == 0 ? (lhs < rhs) : (lhs == rhs);  // lt.rs:16-30
+  }
+}
+__global__ void __launch_bounds__(kThreads)
+    materialize_kernel(int kind, int nsub, int log_m, int log_r, fr_t* tables_fr, uint32_t* tables_u32) {
+  size_t M = (size_t)1 << log_m, n = M * nsub;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t v = subtable_value(kind, (int)(i >> log_m), (uint32_t)(i & (M - 1)), log_m, log_r);
+    if (tables_u32) tables_u32[i] = v;
+    if (tables_fr) st_fr(tables_fr + i, fr_from_u64(v));
+  }
+}
+void launch_materialize_subtables(const Strategy& S, fr_t* tables_fr, uint32_t* tables_u32, cudaStream_t st) {
+  size_t n = (size_t)S.M() * S.num_subtables();
+  materialize_kernel<<<grid_for(n), kThreads, 0, st>>>(S.kind, S.num_subtables(), S.log_m, S.log_r, tables_fr,
+                                                       tables_u32);
+}
+struct GatherMap {
+  int sub[32], dim[32];
+};
+// subtables/mod.rs:78-92: E_k[j] = T_sub(k)[nz_dim(k)[j]]; 32 B written per (memory, lookup)
+__global__ void __launch_bounds__(kThreads)
+    gather_kernel(GatherMap map, int log_m, const fr_t* tables_fr, const uint32_t* tables_u32, const uint32_t* nz,
+                  size_t s, fr_t* E_fr, size_t E_stride, uint32_t* E_u32) {
+  int k = blockIdx.y;
+  const uint32_t* idx = nz + (size_t)map.dim[k] * s;
+  size_t toff = (size_t)map.sub[k] << log_m;
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < s; j += (size_t)gridDim.x * blockDim.x) {
+    uint32_t a = idx[j];
+    if (E_fr) st_fr(E_fr + (size_t)k * E_stride + j, ld_fr(tables_fr + toff + a));
+    if (E_u32) E_u32[(size_t)k * s + j] = tables_u32[toff + a];
+  }
+}
+void launch_gather_lookup_polys(const Strategy& S, const fr_t* tables_fr, const uint32_t* tables_u32,
+                                const uint32_t* nz, size_t s, fr_t* E_fr, size_t E_stride, uint32_t* E_u32,
+                                cudaStream_t st) {
+  GatherMap map;
+  for (int k = 0; k < S.num_memories(); k++) {
+    map.sub[k] = S.memory_to_subtable_index(k);
+    map.dim[k] = S.memory_to_dimension_index(k);
+  }
+  dim3 grid(grid_for(s, kThreads, kMaxBlocks / S.num_memories() + 1), S.num_memories());
+  gather_kernel<<<grid, kThreads, 0, st>>>(map, S.log_m, tables_fr, tables_u32, nz, s, E_fr, E_stride, E_u32);
+}
+__global__ void __launch_bounds__(kThreads) from_u32_kernel(const uint32_t* in, fr_t* out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    st_fr(out + i, fr_from_u64(in[i]));
+}
+void launch_from_u32(const uint32_t* in, fr_t* out, size_t n, cudaStream_t st) {
+  if (n) from_u32_kernel<<<grid_for(n), kThreads, 0, st>>>(in, out, n);
+}
+void launch_fill_zero(fr_t* out, size_t n, cudaStream_t st) {
+  if (n) cudaMemsetAsync(out, 0, n * sizeof(fr_t), st);
+}
+
+// ------------------------------------------------------------------------------------ K7
+// dense_mlpoly.rs:228-235 + utils/mod.rs:63-73 with the eq table shared by all polynomials
+__global__ void __launch_bounds__(kThreads)
+    multi_dot_kernel(const fr_t* base, size_t stride, const fr_t* eq, size_t n, fr_t* partial) {
+  __shared__ fr_t scratch[kThreads / 32];
+  const fr_t* P = base + (size_t)blockIdx.y * stride;
+  fr_t acc[1] = {fr_zero()};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    acc[0] = fr_add(acc[0], fr_mul(ld_fr_stream(P + i), ld_fr(eq + i)));
+  block_sum_fr<1>(acc, scratch);
+  if (threadIdx.x == 0) partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = acc[0];
+}
+void launch_multi_dot(const fr_t* base, size_t stride, int npolys, const fr_t* eq, size_t n, fr_t* partial,
+                      fr_t* out, cudaStream_t st) {
+  int per = kMaxBlocks / npolys;
+  if (per < 1) per = 1;
+  int bx = grid_for(n, kThreads, per);
+  dim3 grid(bx, npolys);
+  multi_dot_kernel<<<grid, kThreads, 0, st>>>(base, stride, eq, n, partial);
+  reduce_partials_kernel<<<npolys, kThreads, 0, st>>>(partial, bx, out);
+}
+
+// dense_mlpoly.rs:183-207: LZ[i] = sum_j L[j] Z[j*R + i].  Thread = column (coalesced across the
+// warp), rows split into chunks over blockIdx.y, second pass sums the chunk partials.
+static constexpr int kBoundChunks = 64;
+int bound_max_chunks() { return kBoundChunks; }
+__global__ void __launch_bounds__(kThreads)
+    bound_kernel(const fr_t* Z, const fr_t* L, size_t L_size, size_t R_size, size_t rows_per_chunk, fr_t* partial) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R_size) return;
+  size_t j0 = (size_t)blockIdx.y * rows_per_chunk, j1 = j0 + rows_per_chunk;
+  if (j1 > L_size) j1 = L_size;
+  fr_t acc = fr_zero();
+  for (size_t j = j0; j < j1; j++) acc = fr_add(acc, fr_mul(L[j], ld_fr_stream(Z + j * R_size + i)));
+  st_fr(partial + (size_t)blockIdx.y * R_size + i, acc);
+}
+__global__ void __launch_bounds__(kThreads) bound_reduce_kernel(const fr_t* partial, int chunks, size_t R_size, fr_t* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R_size) return;
+  fr_t acc = fr_zero();
+  for (int c = 0; c < chunks; c++) acc = fr_add(acc, ld_fr(partial + (size_t)c * R_size + i));
+  st_fr(out + i, acc);
+}
+void launch_bound(const fr_t* Z, const fr_t* L, size_t L_size, size_t R_size, fr_t* partial, fr_t* out,
+                  cudaStream_t st) {
+  int chunks = (int)(L_size < (size_t)kBoundChunks ? L_size : (size_t)kBoundChunks);
+  size_t rows_per_chunk = (L_size + chunks - 1) / chunks;
+  dim3 grid((unsigned)((R_size + kThreads - 1) / kThreads), chunks);
+  bound_kernel<<<grid, kThreads, 0, st>>>(Z, L, L_size, R_size, rows_per_chunk, partial);
+  bound_reduce_kernel<<<(unsigned)((R_size + kThreads - 1) / kThreads), kThreads, 0, st>>>(partial, chunks, R_size, out);
+}
+
+// memory_checking.rs:249-252: hash(a, v, t) = t*gamma^2 + v*gamma + a - tau
+__global__ void __launch_bounds__(kThreads)
+    fp_mem_kernel(const fr_t* table, const fr_t* final_fr, size_t M, fr_t gamma, fr_t gamma2, fr_t tau, fr_t* out_init,
+                  fr_t* out_final) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (size_t)gridDim.x * blockDim.x) {
+    fr_t h0 = fr_sub(fr_add(fr_mul(ld_fr(table + i), gamma), fr_from_u64(i)), tau);  // ts = 0
+    st_fr(out_init + i, h0);
+    st_fr(out_final + i, fr_add(h0, fr_mul(ld_fr(final_fr + i), gamma2)));
+  }
+}
+__global__ void __launch_bounds__(kThreads)
+    fp_ops_kernel(const fr_t* dim_fr, const fr_t* E_fr, const fr_t* read_fr, size_t s, fr_t gamma, fr_t gamma2,
+                  fr_t tau, fr_t* out_read, fr_t* out_write) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < s; i += (size_t)gridDim.x * blockDim.x) {
+    fr_t av = fr_sub(fr_add(fr_mul(ld_fr_stream(E_fr + i), gamma), ld_fr_stream(dim_fr + i)), tau);
+    fr_t hr = fr_add(av, fr_mul(ld_fr_stream(read_fr + i), gamma2));
+    st_fr(out_read + i, hr);
+    st_fr(out_write + i, fr_add(hr, gamma2));  // write ts = read ts + 1
+  }
+}
+void launch_gp_fingerprints_mem(const fr_t* table, const fr_t* final_fr, size_t M, const fr_t& gamma,
+                                const fr_t& tau, fr_t* out_init, fr_t* out_final, cudaStream_t st) {
+  fp_mem_kernel<<<grid_for(M), kThreads, 0, st>>>(table, final_fr, M, gamma, fr_sqr(gamma), tau, out_init, out_final);
+}
+void launch_gp_fingerprints_ops(const fr_t* dim_fr, const fr_t* E_fr, const fr_t* read_fr, size_t s,
+                                const fr_t& gamma, const fr_t& tau, fr_t* out_read, fr_t* out_write,
+                                cudaStream_t st) {
+  fp_ops_kernel<<<grid_for(s), kThreads, 0, st>>>(dim_fr, E_fr, read_fr, s, gamma, fr_sqr(gamma), tau, out_read,
+                                                  out_write);
+}
+// grand_product.rs:20-36 with the layer stored contiguously as [left | right]
+__global__ void __launch_bounds__(kThreads) product_layer_kernel(const fr_t* in, fr_t* out, size_t n_out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (size_t)gridDim.x * blockDim.x)
+    st_fr(out + i, fr_mul(ld_fr_stream(in + i), ld_fr_stream(in + n_out + i)));
+}
+void launch_product_layer(const fr_t* in, fr_t* out, size_t n_out, cudaStream_t st) {
+  product_layer_kernel<<<grid_for(n_out), kThreads, 0, st>>>(in, out, n_out);
+}
+
+// ---- Bulletproofs scalar-side helpers (bullet.rs:73-134) ----
+__global__ void __launch_bounds__(kThreads) fold_ab_kernel(fr_t* a, fr_t* b, size_t h, fr_t u, fr_t uinv) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < h; i += (size_t)gridDim.x * blockDim.x) {
+    fr_t aL = ld_fr(a + i), aR = ld_fr(a + h + i), bL = ld_fr(b + i), bR = ld_fr(b + h + i);
+    st_fr(a + i, fr_add(fr_mul(aL, u), fr_mul(uinv, aR)));
+    st_fr(b + i, fr_add(fr_mul(bL, uinv), fr_mul(u, bR)));
+  }
+}
+void launch_fold_ab(fr_t* a, fr_t* b, size_t h, const fr_t& u, const fr_t& uinv, cudaStream_t st) {
+  fold_ab_kernel<<<grid_for(h), kThreads, 0, st>>>(a, b, h, u, uinv);
+}
+__global__ void __launch_bounds__(kThreads) cross_ip_kernel(const fr_t* a, const fr_t* b, size_t h, fr_t* partial) {
+  __shared__ fr_t scratch[2 * kThreads / 32];
+  fr_t acc[2] = {fr_zero(), fr_zero()};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < h; i += (size_t)gridDim.x * blockDim.x) {
+    acc[0] = fr_add(acc[0], fr_mul(ld_fr(a + i), ld_fr(b + h + i)));
+    acc[1] = fr_add(acc[1], fr_mul(ld_fr(a + h + i), ld_fr(b + i)));
+  }
+  block_sum_fr<2>(acc, scratch);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = acc[0];
+    partial[gridDim.x + blockIdx.x] = acc[1];
+  }
+}
+void launch_cross_inner_products(const fr_t* a, const fr_t* b, size_t h, fr_t* partial, fr_t* out, cudaStream_t st) {
+  int bx = grid_for(h, kThreads, 64);
+  cross_ip_kernel<<<bx, kThreads, 0, st>>>(a, b, h, partial);
+  reduce_partials_kernel<<<2, kThreads, 0, st>>>(partial, bx, out);
+}
+__global__ void __launch_bounds__(kThreads)
+    expand_weights_kernel(const fr_t* w, fr_t* w_out, size_t n_in, fr_t u, fr_t uinv) {
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_in; t += (size_t)gridDim.x * blockDim.x) {
+    fr_t x = ld_fr(w + t);
+    st_fr(w_out + 2 * t, fr_mul(x, uinv));
+    st_fr(w_out + 2 * t + 1, fr_mul(x, u));
+  }
+}
+void launch_expand_weights(const fr_t* w, fr_t* w_out, size_t n_in, const fr_t& u, const fr_t& uinv, cudaStream_t st) {
+  expand_weights_kernel<<<grid_for(n_in), kThreads, 0, st>>>(w, w_out, n_in, u, uinv);
+}
+// Round with current length m (half h = m/2) over n original generators, weights w[t], t < n/m:
+//   sL[t*m + h + i] = a[i] * w[t],  sL[t*m + i] = 0
+//   sR[t*m + i]     = a[h+i] * w[t], sR[t*m + h + i] = 0           (i < h)
+__global__ void __launch_bounds__(kThreads)
+    bullet_scalars_kernel(const fr_t* a, const fr_t* w, size_t n, size_t m, fr_t* sL, fr_t* sR) {
+  size_t h = m / 2;
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
+    size_t t = j / m, pos = j % m;
+    fr_t wt = ld_fr(w + t);
+    if (pos >= h) {
+      st_fr(sL + j, fr_mul(ld_fr(a + (pos - h)), wt));
+      st_fr(sR + j, fr_zero());
+    } else {
+      st_fr(sL + j, fr_zero());
+      st_fr(sR + j, fr_mul(ld_fr(a + h + pos), wt));
+    }
+  }
+}
+void launch_bullet_scalars(const fr_t* a, const fr_t* w, size_t n, size_t m, fr_t* sL, fr_t* sR, cudaStream_t st) {
+  bullet_scalars_kernel<<<grid_for(n), kThreads, 0, st>>>(a, w, n, m, sL, sR);
+}
+__global__ void __launch_bounds__(kThreads) scale_kernel(const fr_t* in, fr_t* out, size_t n, fr_t k) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    st_fr(out + i, fr_mul(ld_fr(in + i), k));
+}
+void launch_scale(const fr_t* in, fr_t* out, size_t n, const fr_t& k, cudaStream_t st) {
+  scale_kernel<<<grid_for(n), kThreads, 0, st>>>(in, out, n, k);
+}
+
+}  // namespace lb
