@@ -1,0 +1,173 @@
+// lasso_b200 — host-side prover objects: context, device buffers, generator tables, the
+// densified representation and the proof byte writer.  The prover logic is in prover.cu.
+#pragma once
+#include <chrono>
+#include <map>
+#include <memory>
+#include <vector>
+
+#include "host_transcript.hpp"
+#include "kernels.cuh"
+#include "msm.cuh"
+
+namespace lb {
+
+extern unsigned long long g_launches;  // kernels launched by this process (bench.py's gpu_launches)
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  uint8_t* h_pin = nullptr;  // pinned staging for small device->host results
+  size_t h_pin_bytes = 0;
+  fr_t* d_partial = nullptr;  // block partial sums / bound chunks
+  size_t partial_elems = 0;
+  fr_t* d_small = nullptr;  // small results (<= 64K elements)
+  size_t small_elems = 0;
+  fr_t* d_eq_scratch = nullptr;
+  unsigned* d_flag = nullptr;
+  double t_densify_ms = 0, t_commit_ms = 0, t_prove_ms = 0;
+  std::map<std::string, double> spans;  // filled when LASSO_B200_SPANS=1 (forces syncs)
+  bool span_sync = false;
+
+  void sync() { LB_CUDA_CHECK(cudaStreamSynchronize(st)); }
+  // device -> host through the pinned buffer (small) or directly (large)
+  void d2h(void* dst, const void* src, size_t bytes) {
+    if (bytes <= h_pin_bytes) {
+      LB_CUDA_CHECK(cudaMemcpyAsync(h_pin, src, bytes, cudaMemcpyDeviceToHost, st));
+      sync();
+      memcpy(dst, h_pin, bytes);
+    } else {
+      LB_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+      sync();
+    }
+  }
+  void h2d(void* dst, const void* src, size_t bytes) {
+    LB_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    sync();  // the source may be a stack / pageable buffer
+  }
+};
+
+// stream-ordered device buffer
+template <class T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  Ctx* c = nullptr;
+  DBuf() {}
+  DBuf(Ctx* ctx, size_t count) { alloc(ctx, count); }
+  void alloc(Ctx* ctx, size_t count) {
+    release();
+    c = ctx;
+    n = count;
+    if (count) LB_CUDA_CHECK(cudaMallocAsync((void**)&p, count * sizeof(T), ctx->st));
+  }
+  void release() {
+    if (p) cudaFreeAsync(p, c->st);
+    p = nullptr;
+    n = 0;
+  }
+  ~DBuf() { release(); }
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  DBuf(DBuf&& o) noexcept : p(o.p), n(o.n), c(o.c) { o.p = nullptr; }
+  DBuf& operator=(DBuf&& o) noexcept {
+    release();
+    p = o.p;
+    n = o.n;
+    c = o.c;
+    o.p = nullptr;
+    return *this;
+  }
+};
+
+struct SpanTimer {
+  Ctx* c;
+  const char* name;
+  std::chrono::steady_clock::time_point t0;
+  SpanTimer(Ctx* ctx, const char* n) : c(ctx), name(n) {
+    if (c->span_sync) {
+      c->sync();
+      t0 = std::chrono::steady_clock::now();
+    }
+  }
+  ~SpanTimer() {
+    if (c->span_sync) {
+      c->sync();
+      c->spans[name] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+  }
+};
+
+// SparsePolyCommitmentGens<G> (lasso/surge.rs:25-58): one generator stream, three (n, Q, h) views
+struct Gens {
+  Ctx* ctx = nullptr;
+  size_t n_points = 0;
+  size_t c = 0, s = 0, num_memories = 0, log_m = 0;
+  size_t nv_l = 0, nv_m = 0, nv_d = 0;  // num_vars of the three committed polynomials
+  DBuf<fq_t> d_bases_ark;               // n_points x (x, y)
+  DBuf<pt_niels> d_table;               // kMsmFullWindows x n_points, T[w][j] = 2^(8w) G_j
+};
+
+// DensifiedRepresentation<F, C> (lasso/densified.rs:8-18), device resident
+struct Dense {
+  Ctx* ctx = nullptr;
+  size_t C = 0, s = 0, log_m = 0, m = 0, nv_l = 0, nv_m = 0;
+  DBuf<uint32_t> d_l_u32;  // 2^nv_l: dim_0..dim_{C-1} | read_0..read_{C-1} | 0..   (dim_usize = first C*s)
+  DBuf<uint32_t> d_m_u32;  // 2^nv_m: final_0..final_{C-1} | 0..
+  DBuf<fr_t> d_l_fr;       // combined_l_variate_polys
+  DBuf<fr_t> d_m_fr;       // combined_log_m_variate_polys
+  const uint32_t* nz() const { return d_l_u32.p; }
+  const fr_t* dim(size_t i) const { return d_l_fr.p + i * s; }
+  const fr_t* read(size_t i) const { return d_l_fr.p + (C + i) * s; }
+  const fr_t* fin(size_t i) const { return d_m_fr.p + i * m; }
+};
+
+// ark-serialize (compressed) writer
+struct ByteWriter {
+  std::vector<uint8_t> b;
+  void u64(uint64_t v) {
+    for (int i = 0; i < 8; i++) b.push_back((uint8_t)(v >> (8 * i)));
+  }
+  void fr(const fr_t& f) {
+    uint8_t t[32];
+    fr_to_bytes(f, t);
+    b.insert(b.end(), t, t + 32);
+  }
+  void raw(const void* p, size_t n) { b.insert(b.end(), (const uint8_t*)p, (const uint8_t*)p + n); }
+  void vec_fr(const std::vector<fr_t>& v) {
+    u64(v.size());
+    for (auto& f : v) fr(f);
+  }
+  void arr_fr(const std::vector<fr_t>& v) {
+    for (auto& f : v) fr(f);
+  }
+  void vec_pts(const std::vector<uint8_t>& comp) {  // comp = 32 B per point
+    u64(comp.size() / 32);
+    raw(comp.data(), comp.size());
+  }
+};
+
+inline size_t log2_exact_or_ceil(size_t x) {  // utils/math.rs:27-35 Math::log_2
+  if ((x & (x - 1)) == 0) return (size_t)__builtin_ctzll((unsigned long long)x);
+  return 64 - (size_t)__builtin_clzll((unsigned long long)x);
+}
+inline size_t next_pow2(size_t x) {
+  size_t p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+// entry points implemented in prover.cu
+Ctx* ctx_create(int device);
+void ctx_destroy(Ctx*);
+Gens* gens_create(Ctx*, const uint64_t* stream_affine, size_t n_points, size_t c, size_t s, size_t num_memories,
+                  size_t log_m);
+size_t gens_points_needed(size_t c, size_t s, size_t num_memories, size_t log_m);
+Dense* densify(Ctx*, const uint64_t* indices, size_t n_lookups, size_t C, size_t log_m, int* err);
+std::vector<uint8_t> commit(Ctx*, const Dense&, const Gens&);
+std::vector<uint8_t> prove(Ctx*, const Strategy& S, Dense&, const std::vector<fr_t>& r, const Gens&,
+                           const std::string& transcript_label, const std::string& tape_label, const fr_t& tape_seed,
+                           std::vector<fr_t>* challenges);
+void sample_generators(const std::string& label, size_t count, uint64_t* out_affine);
+
+}  // namespace lb

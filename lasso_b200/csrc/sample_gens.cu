@@ -1,0 +1,161 @@
+// lasso_b200 — MultiCommitGens::new (src/poly/commitments.rs:22-44) on the host: Shake256(label ||
+// compressed generator) -> 32-byte seed -> ChaCha20Rng -> G::rand x count.  Setup code, outside the timed
+// path (the reference bench runs it outside every instrumented span, bench.rs:54-57).  The RNG / sampling
+// conventions live in crates that are absent from the reference tree (sha3, rand_chacha, ark-ec: SURVEY.md
+// App. C "[memory]"), so the parity contract passes generators explicitly; this gives a deterministic,
+// prime-order generator stream with the same construction.
+#include "host_transcript.hpp"
+#include "prover.cuh"
+
+namespace lb {
+
+static std::vector<uint8_t> shake256(const std::vector<uint8_t>& msg, size_t outlen) {
+  const size_t rate = 136;
+  uint64_t lanes[25];
+  memset(lanes, 0, sizeof(lanes));
+  uint8_t* st = reinterpret_cast<uint8_t*>(lanes);
+  size_t pos = 0;
+  for (uint8_t b : msg) {
+    st[pos++] ^= b;
+    if (pos == rate) {
+      KeccakF1600::permute(lanes);
+      pos = 0;
+    }
+  }
+  st[pos] ^= 0x1f;
+  st[rate - 1] ^= 0x80;
+  KeccakF1600::permute(lanes);
+  std::vector<uint8_t> out;
+  pos = 0;
+  while (out.size() < outlen) {
+    if (pos == rate) {
+      KeccakF1600::permute(lanes);
+      pos = 0;
+    }
+    out.push_back(st[pos++]);
+  }
+  return out;
+}
+
+class ChaCha20Stream {  // rand_chacha::ChaCha20Rng::from_seed: 64-bit block counter, zero stream id
+ public:
+  explicit ChaCha20Stream(const uint8_t seed[32]) { memcpy(key_, seed, 32); }
+  uint32_t next_u32() {
+    if (idx_ == 16) refill();
+    return buf_[idx_++];
+  }
+  uint64_t next_u64() {
+    uint64_t lo = next_u32(), hi = next_u32();
+    return lo | (hi << 32);
+  }
+
+ private:
+  uint32_t key_[8], buf_[16];
+  uint64_t ctr_ = 0;
+  int idx_ = 16;
+  static uint32_t rl(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
+  static void quarter(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+    a += b; d = rl(d ^ a, 16);
+    c += d; b = rl(b ^ c, 12);
+    a += b; d = rl(d ^ a, 8);
+    c += d; b = rl(b ^ c, 7);
+  }
+  void refill() {
+    uint32_t in[16] = {0x61707865, 0x3320646e, 0x79622d32, 0x6b206574};
+    for (int i = 0; i < 8; i++) in[4 + i] = key_[i];
+    in[12] = (uint32_t)ctr_;
+    in[13] = (uint32_t)(ctr_ >> 32);
+    in[14] = in[15] = 0;
+    uint32_t x[16];
+    memcpy(x, in, 64);
+    for (int r = 0; r < 10; r++) {
+      quarter(x[0], x[4], x[8], x[12]); quarter(x[1], x[5], x[9], x[13]);
+      quarter(x[2], x[6], x[10], x[14]); quarter(x[3], x[7], x[11], x[15]);
+      quarter(x[0], x[5], x[10], x[15]); quarter(x[1], x[6], x[11], x[12]);
+      quarter(x[2], x[7], x[8], x[13]); quarter(x[3], x[4], x[9], x[14]);
+    }
+    for (int i = 0; i < 16; i++) buf_[i] = x[i] + in[i];
+    ctr_++;
+    idx_ = 0;
+  }
+};
+
+static fq_t fq_pow_2_252_m2(const fq_t& a) {  // a^((q+3)/8), (q+3)/8 = 2^252 - 2
+  // 2^252 - 2 = 2 * (2^251 - 1)
+  fq_t x = a;  // a^(2^1 - 1)
+  fq_t acc = a;
+  for (int i = 1; i < 251; i++) acc = fq_mul(fq_sqr(acc), x);  // a^(2^251 - 1)
+  return fq_sqr(acc);
+}
+static bool fq_gt_neg(const fq_t& x) {  // canonical x > (q-1)/2
+  fq_t cx = fq_canonical(x);
+  uint32_t out[8];
+  fq_t y = fq_zero();
+  pt_compress_canonical(cx, y, out);
+  return (out[7] >> 31) != 0;
+}
+
+void sample_generators(const std::string& label, size_t count, uint64_t* out_affine) {
+  // compressed base point: y = 4/5, x positive in the arkworks sense
+  const fq_t by = {{0x66666658u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u}};
+  std::vector<uint8_t> msg(label.begin(), label.end());
+  uint8_t gen[32];
+  memcpy(gen, by.v, 32);  // base point x = 0x2169... <= (q-1)/2: sign flag clear
+  msg.insert(msg.end(), gen, gen + 32);
+  std::vector<uint8_t> seed = shake256(msg, 32);
+  ChaCha20Stream rng(seed.data());
+  const fq_t d = {{0x135978a3u, 0x75eb4dcau, 0x4141d8abu, 0x00700a4du, 0x7779e898u, 0x8cc74079u, 0x2b6ffe73u, 0x52036ceeu}};
+  const fq_t sqrtm1 = {{0x4a0ea0b0u, 0xc4ee1b27u, 0xad2fe478u, 0x2f431806u, 0x3dfbd7a7u, 0x2b4d0099u, 0x4fc1df0bu, 0x2b832480u}};
+  const fq_t inv38 = fq_from_ark(fq_one());  // 38^-1
+  (void)inv38;
+  size_t produced = 0;
+  while (produced < count) {
+    // Fq::rand: 4 x u64, keep 255 bits, reject >= q; the bits are the Montgomery representation
+    uint32_t raw[8];
+    for (;;) {
+      for (int i = 0; i < 4; i++) {
+        uint64_t v = rng.next_u64();
+        raw[2 * i] = (uint32_t)v;
+        raw[2 * i + 1] = (uint32_t)(v >> 32);
+      }
+      raw[7] &= 0x7fffffffu;
+      bool ge = true;  // raw >= q  <=>  raw + 19 >= 2^255
+      uint64_t cc = 19;
+      uint32_t top = 0;
+      for (int i = 0; i < 8; i++) {
+        uint64_t u = (uint64_t)raw[i] + cc;
+        top = (uint32_t)u;
+        cc = u >> 32;
+      }
+      ge = (top >> 31) != 0;
+      if (!ge) break;
+    }
+    fq_t ym;
+    memcpy(ym.v, raw, 32);
+    fq_t y = fq_from_ark(ym);
+    bool greatest = (int32_t)rng.next_u32() < 0;
+    // x^2 = (y^2 - 1) / (d y^2 + 1)
+    fq_t y2 = fq_sqr(y);
+    fq_t num = fq_sub(y2, fq_one()), den = fq_add(fq_mul(d, y2), fq_one());
+    if (fq_is_zero(den)) continue;
+    fq_t x2 = fq_mul(num, fq_inv(den));
+    fq_t x = fq_pow_2_252_m2(x2);
+    if (!fq_equal(fq_sqr(x), x2)) {
+      x = fq_mul(x, sqrtm1);
+      if (!fq_equal(fq_sqr(x), x2)) continue;
+    }
+    fq_t nx = fq_neg(x);
+    if (fq_gt_neg(x) != greatest) x = nx;
+    // clear the cofactor (x8) and normalise
+    pt_ext p = pt_from_niels(niels_from_affine(x, y));
+    p = pt_dbl(pt_dbl(pt_dbl(p)));
+    fq_t ax, ay;
+    pt_to_affine_canonical(p, ax, ay);
+    fq_t xm = fq_to_ark(ax), ymm = fq_to_ark(ay);
+    memcpy(out_affine + 8 * produced, xm.v, 32);
+    memcpy(out_affine + 8 * produced + 4, ymm.v, 32);
+    produced++;
+  }
+}
+
+}  // namespace lb

@@ -1,0 +1,92 @@
+"""GPU parity on the whole path: Densify -> commit -> prove through the C-ABI must produce the same
+commitment bytes, the same Fiat-Shamir challenges and the same proof bytes as the CPU oracle, whose
+verifier must accept them (e2e_test.rs:64-99 shapes + the bench shapes)."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+CASES = [  # name, kind, C, log_m, log_r, lookups, same_index
+    ("prove_4d_lt", 3, 4, 4, 0, 16, True),
+    ("prove_4d_lt_big_s", 3, 4, 4, 0, 128, False),
+    ("prove_4d_and", 0, 4, 4, 0, 16, True),
+    ("prove_3d_range", 4, 3, 8, 40, 16, False),
+    ("and_c1_bench_shape", 0, 1, 16, 0, 1 << 10, True),
+    ("xor_c4", 2, 4, 16, 0, 1 << 12, True),
+    ("xor_c4_indep", 2, 4, 16, 0, 1 << 11, False),
+    ("or_c2_ragged", 1, 2, 8, 0, 700, False),
+    ("lt_c8", 3, 8, 8, 0, 1 << 9, False),
+    ("range_c4", 4, 4, 16, 40, 1 << 10, False),
+]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import lasso_b200 as lb
+
+    c = lb.Context(0)
+    yield c
+    c.close()
+
+
+def make_inputs(C, log_m, n, seed, same):
+    rng = np.random.default_rng(seed)
+    col = rng.integers(0, 1 << log_m, size=(n, 1), dtype=np.uint64)
+    idx = np.repeat(col, C, axis=1) if same else rng.integers(0, 1 << log_m, size=(n, C), dtype=np.uint64)
+    s = 1 << max(0, (n - 1).bit_length())
+    r = ol.rand_fr(rng, max(1, s.bit_length() - 1))
+    return np.ascontiguousarray(idx), r, ol.rand_fr(rng, 1)[0], s
+
+
+@pytest.mark.parametrize("name,kind,C,log_m,log_r,n,same", CASES)
+def test_prove_matches_oracle(ctx, name, kind, C, log_m, log_r, n, same):
+    import lasso_b200 as lb
+
+    idx, r, seed, s = make_inputs(C, log_m, n, len(name), same)
+    S = lb.Strategy(kind, C, log_m, log_r)
+    need = lb.gens_points_needed(C, s, S.num_memories, log_m)
+    stream = np.ascontiguousarray(ol.generators(max(need, 300))[:need])
+    gens = lb.SparsePolyCommitmentGens.new(ctx, b"gens_sparse_poly", C, s, S.num_memories, log_m, stream=stream)
+    dense = lb.DensifiedRepresentation.from_lookup_indices(ctx, idx, log_m)
+    assert dense.s == s
+    commitment = dense.commit(gens)
+    proof = lb.SparsePolynomialEvaluationProof.prove(ctx, S, dense, r, gens, tape_seed=seed)
+    ref = ol.prove(kind, C, log_m, log_r, idx, r, stream, seed, flags=1)
+    assert ref["rc"] == 0
+    assert commitment == ref["commitment"]
+    nch = min(len(proof.challenges), len(ref["challenges"]))
+    assert (proof.challenges[:nch] == ref["challenges"][:nch]).all(), "Fiat-Shamir challenges diverge"
+    assert len(proof.challenges) == len(ref["challenges"])
+    assert proof.bytes == ref["proof"]
+
+
+def test_densified_fields(ctx):
+    import lasso_b200 as lb
+
+    # memory_checking.rs:794-831 fixture through the product path: accesses [1,2,1,5], m = 8
+    idx = np.array([[1], [2], [1], [5]], dtype=np.uint64)
+    d = lb.DensifiedRepresentation.from_lookup_indices(ctx, idx, 3)
+    assert d.dim_usize.tolist() == [[1, 2, 1, 5]]
+    assert ol.fr_ints(d.read[0]) == [0, 0, 1, 0]
+    assert ol.fr_ints(d.final[0]) == [0, 2, 1, 0, 0, 1, 0, 0]
+    # padding with address 0 (densified.rs:37)
+    d = lb.DensifiedRepresentation.from_lookup_indices(ctx, idx[:3], 3)
+    assert d.s == 4 and d.dim_usize.tolist() == [[1, 2, 1, 0]] and ol.fr_ints(d.final[0])[0] == 1
+    with pytest.raises(lb.LassoError) as e:
+        lb.DensifiedRepresentation.from_lookup_indices(ctx, np.array([[9]], dtype=np.uint64), 3)
+    assert e.value.code == 3
+
+
+def test_prove_rejects_wrong_r_length(ctx):
+    import lasso_b200 as lb
+
+    idx, r, seed, s = make_inputs(2, 4, 16, 1, True)
+    S = lb.Strategy(lb.XOR, 2, 4)
+    stream = np.ascontiguousarray(ol.generators(300)[: lb.gens_points_needed(2, s, 2, 4)])
+    gens = lb.SparsePolyCommitmentGens.new(ctx, b"g", 2, s, 2, 4, stream=stream)
+    dense = lb.DensifiedRepresentation.from_lookup_indices(ctx, idx, 4)
+    with pytest.raises(lb.LassoError) as e:
+        lb.SparsePolynomialEvaluationProof.prove(ctx, S, dense, r[:-1], gens, tape_seed=seed)
+    assert e.value.code == 1  # assert_eq!(r.len(), log2(s)) surge.rs:131
