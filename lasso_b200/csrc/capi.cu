@@ -195,7 +195,7 @@ static void msm_variable_base(Ctx* c, const uint64_t* bases_affine, size_t nbase
   if (nw > kMsmFullWindows) nw = kMsmFullWindows;
   DBuf<pt_ext> part(c, msm_partials_count((int)nrows, (int)ncols, nw));
   DBuf<fq_t> oe(c, nrows * 4);
-  launch_msm_rows(tab.p, nbases, 0, canon.p, 8, ncols, (int)nrows, (int)ncols, nw, part.p, oe.p, nullptr, c->st);
+  launch_msm_rows(tab.p, nbases, 0, canon.p, 8, ncols, (int)nrows, (int)ncols, nw, part.p, oe.p, nullptr, nullptr, c->st);
   g_launches += 4;
   LB_CUDA_CHECK(cudaMemcpyAsync(out_ext, oe.p, nrows * 128, cudaMemcpyDeviceToHost, c->st));
   c->sync();

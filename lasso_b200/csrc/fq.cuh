@@ -91,7 +91,17 @@ LB_HD fq_t fq_neg(const fq_t& a) { return fq_sub(fq_zero(), a); }
 LB_HD fq_t fq_dbl(const fq_t& a) { return fq_add(a, a); }
 
 // 8x8 -> 16 limb product on the even/odd split accumulator (see fr.cuh), then 2^256 = 38 fold.
-LB_HD fq_t fq_mul(const fq_t& A, const fq_t& B) {
+// The MSM kernels compile this as a real (non-inlined) function: a bucket kernel inlines ~50 field
+// multiplications otherwise (>100 KB of SASS) and, with 3 warps per scheduler each in a different
+// phase, stalls on instruction fetch (ncu: stalled_no_instruction was the top stall reason).
+#ifndef LB_FQ_MUL_ATTR
+#define LB_FQ_MUL_ATTR LB_HD
+#endif
+#ifdef LB_FQ_MUL_BYVALUE
+LB_FQ_MUL_ATTR fq_t fq_mul(const fq_t A, const fq_t B) {
+#else
+LB_FQ_MUL_ATTR fq_t fq_mul(const fq_t& A, const fq_t& B) {
+#endif
   const uint32_t* a = A.v;
   const uint32_t* b = B.v;
   uint32_t ev[18], od[18];  // value = sum ev[k] 2^(32k) + sum od[k] 2^(32(k+1))

@@ -218,8 +218,61 @@ LB_HD void fr_mul_row(uint32_t e[9], uint32_t o[8], uint32_t& stray, const uint3
   for (int k = 0; k < 8; k++) o[k] = no[k];
 }
 
-// a * b * 2^-256 mod l
-LB_HD fr_t fr_mul(const fr_t& a, const fr_t& b) {
+#if !defined(__CUDA_ARCH__)
+// Host fast path (the prover's Fiat-Shamir glue: interpolation, challenge arithmetic, u^-1): plain
+// 4 x 64-bit CIOS with unsigned __int128, ~10x faster than emulating the 32-bit carry chains.
+inline fr_t fr_mul_host64(const fr_t& A, const fr_t& B) {
+  typedef unsigned __int128 u128;
+  static const uint64_t P[4] = {0x5812631a5cf5d3edULL, 0x14def9dea2f79cd6ULL, 0x0ULL, 0x1000000000000000ULL};
+  const uint64_t INV = 0xd2b51da312547e1bULL;
+  uint64_t a[4], b[4];
+  for (int i = 0; i < 4; i++) {
+    a[i] = (uint64_t)A.v[2 * i] | ((uint64_t)A.v[2 * i + 1] << 32);
+    b[i] = (uint64_t)B.v[2 * i] | ((uint64_t)B.v[2 * i + 1] << 32);
+  }
+  uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) {
+    u128 c = 0;
+    for (int j = 0; j < 4; j++) {
+      c += (u128)t[j] + (u128)a[j] * b[i];
+      t[j] = (uint64_t)c;
+      c >>= 64;
+    }
+    c += t[4];
+    t[4] = (uint64_t)c;
+    t[5] = (uint64_t)(c >> 64);
+    uint64_t m = t[0] * INV;
+    c = ((u128)t[0] + (u128)m * P[0]) >> 64;
+    for (int j = 1; j < 4; j++) {
+      c += (u128)t[j] + (u128)m * P[j];
+      t[j - 1] = (uint64_t)c;
+      c >>= 64;
+    }
+    c += t[4];
+    t[3] = (uint64_t)c;
+    t[4] = t[5] + (uint64_t)(c >> 64);
+  }
+  // t < 2l: one conditional subtraction
+  uint64_t s[4];
+  u128 bw = 0;
+  for (int i = 0; i < 4; i++) {
+    u128 d = (u128)t[i] - P[i] - (uint64_t)bw;
+    s[i] = (uint64_t)d;
+    bw = (d >> 64) & 1;
+  }
+  bool ge = t[4] != 0 || bw == 0;
+  fr_t r;
+  for (int i = 0; i < 4; i++) {
+    uint64_t v = ge ? s[i] : t[i];
+    r.v[2 * i] = (uint32_t)v;
+    r.v[2 * i + 1] = (uint32_t)(v >> 32);
+  }
+  return r;
+}
+#endif
+
+// the even/odd carry-chain multiplication (device path; also runs on the host for validation)
+LB_HD fr_t fr_mul_chain(const fr_t& a, const fr_t& b) {
   uint32_t e[9], o[8], stray = 0;
   fr_mul_row(e, o, stray, a.v, b.v[0], true);
 #pragma unroll
@@ -235,6 +288,14 @@ LB_HD fr_t fr_mul(const fr_t& a, const fr_t& b) {
   LB_ADDC_CC(t[6], e[6], o[5]);
   LB_ADDC(t[7], e[7], o[6]);
   return fr_reduce_once(t);
+}
+// a * b * 2^-256 mod l
+LB_HD fr_t fr_mul(const fr_t& a, const fr_t& b) {
+#if defined(__CUDA_ARCH__)
+  return fr_mul_chain(a, b);
+#else
+  return fr_mul_host64(a, b);
+#endif
 }
 LB_HD fr_t fr_sqr(const fr_t& a) { return fr_mul(a, a); }
 

@@ -1,0 +1,114 @@
+// lasso_b200 — host-side Fq = GF(2^255 - 19) on 4 x 64-bit limbs (unsigned __int128), used only to
+// normalise / compress the one or two group elements a Bulletproofs round sends to the transcript:
+// a single Fq inversion is a 265-step serial chain — ~3 us on a CPU core, ~100 us on one GPU thread.
+// Values are plain (non-Montgomery) integers, loosely reduced below 2^256 like the device code (fq.cuh).
+#pragma once
+#include <cstdint>
+#include <cstring>
+
+namespace lb {
+namespace h64 {
+
+typedef unsigned __int128 u128;
+struct fe {
+  uint64_t v[4];
+};
+
+inline fe from_limbs32(const uint32_t* p) {
+  fe r;
+  memcpy(r.v, p, 32);
+  return r;
+}
+inline void fold(uint64_t t[4], uint64_t c) {  // t += 38 * c, twice
+  u128 acc = (u128)c * 38;
+  for (int i = 0; i < 4; i++) {
+    acc += t[i];
+    t[i] = (uint64_t)acc;
+    acc >>= 64;
+  }
+  t[0] += (uint64_t)acc * 38;  // second wrap cannot ripple (value is tiny when it happens)
+}
+inline fe mul(const fe& a, const fe& b) {
+  uint64_t p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) {
+    u128 c = 0;
+    for (int j = 0; j < 4; j++) {
+      c += (u128)a.v[j] * b.v[i] + p[i + j];
+      p[i + j] = (uint64_t)c;
+      c >>= 64;
+    }
+    p[i + 4] = (uint64_t)c;
+  }
+  fe r;
+  u128 c = 0;
+  for (int k = 0; k < 4; k++) {
+    c += (u128)p[4 + k] * 38 + p[k];
+    r.v[k] = (uint64_t)c;
+    c >>= 64;
+  }
+  fold(r.v, (uint64_t)c);
+  return r;
+}
+inline fe sqr_n(fe a, int n) {
+  for (int i = 0; i < n; i++) a = mul(a, a);
+  return a;
+}
+inline fe inv(const fe& z) {  // z^(2^255 - 21)
+  fe z2 = mul(z, z);
+  fe z9 = mul(sqr_n(z2, 2), z);
+  fe z11 = mul(z9, z2);
+  fe z2_5_0 = mul(mul(z11, z11), z9);
+  fe z2_10_0 = mul(sqr_n(z2_5_0, 5), z2_5_0);
+  fe z2_20_0 = mul(sqr_n(z2_10_0, 10), z2_10_0);
+  fe z2_40_0 = mul(sqr_n(z2_20_0, 20), z2_20_0);
+  fe z2_50_0 = mul(sqr_n(z2_40_0, 10), z2_10_0);
+  fe z2_100_0 = mul(sqr_n(z2_50_0, 50), z2_50_0);
+  fe z2_200_0 = mul(sqr_n(z2_100_0, 100), z2_100_0);
+  fe z2_250_0 = mul(sqr_n(z2_200_0, 50), z2_50_0);
+  return mul(sqr_n(z2_250_0, 5), z11);
+}
+inline fe canonical(const fe& a) {
+  uint64_t t[4] = {a.v[0], a.v[1], a.v[2], a.v[3]};
+  for (int rep = 0; rep < 2; rep++) {
+    uint64_t top = t[3] >> 63;
+    t[3] &= 0x7fffffffffffffffULL;
+    u128 c = (u128)top * 19;
+    for (int i = 0; i < 4; i++) {
+      c += t[i];
+      t[i] = (uint64_t)c;
+      c >>= 64;
+    }
+  }
+  uint64_t s[4];
+  u128 c = 19;
+  for (int i = 0; i < 4; i++) {
+    c += t[i];
+    s[i] = (uint64_t)c;
+    c >>= 64;
+  }
+  bool ge = (s[3] >> 63) != 0;
+  s[3] &= 0x7fffffffffffffffULL;
+  fe r;
+  for (int i = 0; i < 4; i++) r.v[i] = ge ? s[i] : t[i];
+  return r;
+}
+// (X, Y, Z) internal limbs (3 x 8 u32) -> ark-serialize compressed point (32 bytes)
+inline void compress_xyz(const uint32_t* xyz, uint8_t out[32]) {
+  fe X = from_limbs32(xyz), Y = from_limbs32(xyz + 8), Z = from_limbs32(xyz + 16);
+  fe zi = inv(Z);
+  fe x = canonical(mul(X, zi)), y = canonical(mul(Y, zi));
+  // x > (q-1)/2  <=>  x + 9 >= 2^254
+  u128 c = 9;
+  uint64_t top = 0;
+  for (int i = 0; i < 4; i++) {
+    c += x.v[i];
+    top = (uint64_t)c;
+    c >>= 64;
+  }
+  bool neg = (top >> 62) != 0;
+  memcpy(out, y.v, 32);
+  if (neg) out[31] |= 0x80;
+}
+
+}  // namespace h64
+}  // namespace lb

@@ -58,6 +58,11 @@ int sumcheck_max_blocks();
 void launch_sumcheck_eval_cubic(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Ceq, int ncirc, size_t half,
                                 fr_t* partial, fr_t* out, cudaStream_t st);
 
+// fused: bind A_k, B_k (in place) and eq (Cin -> Cout) with r, then evaluate the next round on the bound
+// values; h = bound length (>= 2).  Returns the number of kernels launched.
+int launch_sumcheck_bind_eval_cubic(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Cin, fr_t* Cout, int ncirc, size_t h,
+                                    const fr_t& r, fr_t* partial, fr_t* out, cudaStream_t st);
+
 // ---- K5: subtables (subtables/*.rs) ----
 // tables_fr: nsub x M Montgomery elements; tables_u32: nsub x M raw values
 void launch_materialize_subtables(const Strategy& S, fr_t* tables_fr, uint32_t* tables_u32, cudaStream_t st);

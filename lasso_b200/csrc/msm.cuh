@@ -17,11 +17,12 @@ size_t msm_partials_count(int nrows, int ncols, int nw);
 //   row r uses scalars[r*row_stride .. +ncols); nw = number of 8-bit windows to process
 //   (must cover max_bits + 2; <= 5 for u32, <= 32 for 256-bit)
 //   shifted != 0: `table` holds nw window tables (fixed-base); else only window 0 (variable-base)
-// Outputs (either may be null): out_ext = nrows x (x,y,t,z) arkworks Montgomery limbs with z = 1;
-// out_comp = nrows x 32 bytes ark-serialize compressed.
+// Outputs (any may be null): out_ext = nrows x (x,y,t,z) arkworks Montgomery limbs with z = 1;
+// out_comp = nrows x 32 bytes ark-serialize compressed; out_raw = nrows x 96 B un-normalised (X,Y,Z)
+// internal limbs for host-side normalisation (host_fq64.hpp) when there are only a few rows.
 void launch_msm_rows(const pt_niels* table, size_t table_stride, int shifted, const void* scalars, int scalar_limbs,
                      size_t row_stride, int nrows, int ncols, int nw, pt_ext* partials, fq_t* out_ext,
-                     uint32_t* out_comp, cudaStream_t st);
+                     uint32_t* out_comp, uint32_t* out_raw, cudaStream_t st);
 void launch_combine_points(const fq_t* in_ext, int n, fq_t* out_ext, uint32_t* out_comp, cudaStream_t st);
 
 inline int msm_windows_for_bits(unsigned max_bits) {

@@ -18,6 +18,10 @@
 // For bases without a precomputed table (variable-base lasso_msm) the same kernels run with the
 // single window-0 table and the finish kernel does the 8-doubling Horner combination instead.
 // Integer-ALU bound (7 Fq muls per bucket add), not HBM bound: reported as point-adds/s.
+#if defined(__CUDACC__)
+#define LB_FQ_MUL_ATTR static __host__ __device__ __noinline__
+#define LB_FQ_MUL_BYVALUE
+#endif
 #include "kernels.cuh"
 #include "msm.cuh"
 
@@ -231,10 +235,18 @@ __global__ void __launch_bounds__(MSM_T)
         const int bend = sm.off[b + 1];
         const int run_end = bend < hi ? bend : hi;
         pt_ext acc = pt_identity();
+        // software pipeline: the next point's 96 B are in flight while the current addition runs
+        uint16_t e = sm.list[pos];
+        pt_niels nn = ld_niels(tw + c_begin + (e & 0x7fff));
         for (int p = pos; p < run_end; p++) {
-          uint16_t e = sm.list[p];
-          pt_niels nn = ld_niels(tw + c_begin + (e & 0x7fff));
-          acc = (e & 0x8000) ? pt_msub(acc, nn) : pt_madd(acc, nn);
+          const uint16_t ecur = e;
+          const pt_niels ncur = nn;
+          if (p + 1 < run_end) {
+            e = sm.list[p + 1];
+            nn = ld_niels(tw + c_begin + (e & 0x7fff));
+          }
+          // P - Q = P + (-Q): negating an affine-niels point is a swap and one negation
+          acc = pt_madd(acc, (ecur & 0x8000) ? niels_neg(ncur) : ncur);
         }
         const bool complete = (pos == sm.off[b]) && (run_end == bend);
         if (complete) {
@@ -251,22 +263,34 @@ __global__ void __launch_bounds__(MSM_T)
     }
   }
   __syncthreads();
-  // stitch partial runs into their buckets: thread t owns bucket t+1
+  // stitch partial runs into their buckets: thread t owns bucket t+1.  A bucket that is not wholly
+  // inside one thread's slice was split over a CONTIGUOUS range of threads [t_lo, t_hi], each holding
+  // exactly one partial for it, so the owner walks just that range (typically 2-3 threads) instead of
+  // scanning all 128 slots — scanning made every warp execute ~64 divergent point additions.
   {
     const int b = tid + 1;
-    pt_ext acc = sm_load_pt(sm.bucket, MSM_NB + 1, b);
-    bool touched = false;
-    for (int t = 0; t < MSM_T; t++) {
-      if (sm.pf_b[t] == b) {
-        acc = pt_add(acc, sm_load_pt(sm.pfirst, MSM_T, t));
-        touched = true;
-      }
-      if (sm.pl_b[t] == b) {
-        acc = pt_add(acc, sm_load_pt(sm.plast, MSM_T, t));
-        touched = true;
+    const int s0 = sm.off[b], s1 = sm.off[b + 1];
+    if (s1 > s0) {
+      auto slice_lo = [&](int t) { return (int)(((long long)t * N) / MSM_T); };
+      auto thread_of = [&](int pos) {
+        int t = (int)(((long long)pos * MSM_T) / N);
+        if (t > MSM_T - 1) t = MSM_T - 1;
+        while (t + 1 < MSM_T && slice_lo(t + 1) <= pos) t++;
+        while (t > 0 && slice_lo(t) > pos) t--;
+        return t;
+      };
+      const int t_lo = thread_of(s0), t_hi = thread_of(s1 - 1);
+      if (t_lo != t_hi) {
+        pt_ext acc = pt_identity();
+        for (int t = t_lo; t <= t_hi; t++) {
+          if (sm.pf_b[t] == b)
+            acc = pt_add(acc, sm_load_pt(sm.pfirst, MSM_T, t));
+          else if (sm.pl_b[t] == b)
+            acc = pt_add(acc, sm_load_pt(sm.plast, MSM_T, t));
+        }
+        sm_store_pt(sm.bucket, MSM_NB + 1, b, acc);
       }
     }
-    if (touched) sm_store_pt(sm.bucket, MSM_NB + 1, b, acc);
   }
   __syncthreads();
   // weighted sum  sum_b b * B_b = sum_{k>=1} (sum_{b>=k} B_b): suffix scan, then tree reduction.
@@ -301,24 +325,63 @@ __global__ void __launch_bounds__(MSM_T)
 }
 
 // ---------------------------------------------------------------- finish: combine, normalise, emit
-// out_ext: per row 4 x Fq arkworks Montgomery limbs (x, y, t, z=1) or null; out_comp: 32 B/row or null.
-__global__ void __launch_bounds__(64)
+__device__ __forceinline__ pt_ext shfl_down_pt(const pt_ext& p, int d) {
+  pt_ext r;
+#pragma unroll
+  for (int l = 0; l < 8; l++) {
+    r.X.v[l] = __shfl_down_sync(0xffffffffu, p.X.v[l], d);
+    r.Y.v[l] = __shfl_down_sync(0xffffffffu, p.Y.v[l], d);
+    r.Z.v[l] = __shfl_down_sync(0xffffffffu, p.Z.v[l], d);
+    r.T.v[l] = __shfl_down_sync(0xffffffffu, p.T.v[l], d);
+  }
+  return r;
+}
+__device__ __forceinline__ pt_ext ld_pt(const pt_ext* p) {
+  pt_ext r;
+  r.X = ld_fq(&p->X);
+  r.Y = ld_fq(&p->Y);
+  r.Z = ld_fq(&p->Z);
+  r.T = ld_fq(&p->T);
+  return r;
+}
+// One warp per row.  out_ext: (x,y,t,z=1) arkworks Montgomery limbs; out_comp: 32 B compressed;
+// out_raw: un-normalised (X, Y, Z) internal limbs, 96 B/row — the caller normalises on the host
+// (used when there are only a couple of rows: one inversion is a 265-step serial chain).
+__global__ void __launch_bounds__(32)
     msm_finish_kernel(const pt_ext* partials, int nrows, int nw, int nchunks, int shifted, fq_t* out_ext,
-                      uint32_t* out_comp) {
-  int row = blockIdx.x * blockDim.x + threadIdx.x;
+                      uint32_t* out_comp, uint32_t* out_raw) {
+  const int row = blockIdx.x, lane = threadIdx.x;
   if (row >= nrows) return;
   const pt_ext* p = partials + (size_t)row * nw * nchunks;
   pt_ext acc = pt_identity();
   if (shifted) {
-    for (int i = 0; i < nw * nchunks; i++) acc = pt_add(acc, p[i]);
-  } else {
+    const int total = nw * nchunks;
+    for (int i = lane; i < total; i += 32) acc = pt_add(acc, ld_pt(p + i));
+    if (total > 1) {
+#pragma unroll 1
+      for (int d = 16; d >= 1; d >>= 1) {
+        pt_ext o = shfl_down_pt(acc, d);
+        acc = pt_add(acc, o);
+      }
+    }
+  } else if (lane == 0) {
     // msm/mod.rs:150-163: total = sum_w 2^(8w) W_w, high to low with 8 doublings per window
     for (int w = nw - 1; w >= 0; w--) {
       if (w != nw - 1)
         for (int k = 0; k < 8; k++) acc = pt_dbl(acc);
-      for (int c = 0; c < nchunks; c++) acc = pt_add(acc, p[(size_t)w * nchunks + c]);
+      for (int c = 0; c < nchunks; c++) acc = pt_add(acc, ld_pt(p + (size_t)w * nchunks + c));
     }
   }
+  if (lane != 0) return;
+  if (out_raw) {
+#pragma unroll
+    for (int l = 0; l < 8; l++) {
+      out_raw[(size_t)row * 24 + l] = acc.X.v[l];
+      out_raw[(size_t)row * 24 + 8 + l] = acc.Y.v[l];
+      out_raw[(size_t)row * 24 + 16 + l] = acc.Z.v[l];
+    }
+  }
+  if (!out_comp && !out_ext) return;
   fq_t x, y;
   pt_to_affine_canonical(acc, x, y);
   if (out_comp) {
@@ -336,19 +399,30 @@ __global__ void __launch_bounds__(64)
   }
 }
 
+// Column-chunk size: whole rows per CTA when there are many rows; with only a few rows (Bulletproofs
+// rounds) split the columns so that at least ~2 CTAs per SM exist.
+static int msm_chunk_cols(int nrows, int ncols, int nw) {
+  long long ctas = (long long)nrows * nw;
+  int want = (int)((1LL * kNumSMs + ctas - 1) / ctas);  // chunks needed for ~1 CTA per SM
+  int chunk = want > 1 ? (ncols + want - 1) / want : ncols;
+  if (chunk < 256) chunk = 256;
+  if (chunk > MSM_CHUNK) chunk = MSM_CHUNK;
+  if (chunk > ncols) chunk = ncols;
+  if (chunk < 1) chunk = 1;
+  return chunk;
+}
 size_t msm_partials_count(int nrows, int ncols, int nw) {
-  int chunk_cols = ncols < MSM_CHUNK ? ncols : MSM_CHUNK;
+  int chunk_cols = msm_chunk_cols(nrows, ncols, nw);
   int nchunks = (ncols + chunk_cols - 1) / chunk_cols;
   return (size_t)nrows * nw * nchunks;
 }
 
 void launch_msm_rows(const pt_niels* table, size_t table_stride, int shifted, const void* scalars, int scalar_limbs,
                      size_t row_stride, int nrows, int ncols, int nw, pt_ext* partials, fq_t* out_ext,
-                     uint32_t* out_comp, cudaStream_t st) {
+                     uint32_t* out_comp, uint32_t* out_raw, cudaStream_t st) {
   if (nrows <= 0) return;
   if (nw < 1) nw = 1;
-  int chunk_cols = ncols < MSM_CHUNK ? ncols : MSM_CHUNK;
-  if (chunk_cols < 1) chunk_cols = 1;
+  int chunk_cols = msm_chunk_cols(nrows, ncols, nw);
   int nchunks = (ncols + chunk_cols - 1) / chunk_cols;
   if (nchunks < 1) nchunks = 1;
   static bool attr_set = false;
@@ -371,7 +445,7 @@ void launch_msm_rows(const pt_niels* table, size_t table_stride, int shifted, co
           table, table_stride, shifted, (const uint32_t*)scalars + (size_t)r0 * row_stride * 8, row_stride, ncols,
           chunk_cols, part);
   }
-  msm_finish_kernel<<<(nrows + 63) / 64, 64, 0, st>>>(partials, nrows, nw, nchunks, shifted, out_ext, out_comp);
+  msm_finish_kernel<<<nrows, 32, 0, st>>>(partials, nrows, nw, nchunks, shifted, out_ext, out_comp, out_raw);
 }
 
 // sum of a few extended points + normalisation (used to add a blind*h term or combine rows)

@@ -314,6 +314,72 @@ __global__ void __launch_bounds__(kThreads)
       partial[((size_t)blockIdx.y * 3 + t) * gridDim.x + blockIdx.x] = acc[t];
   }
 }
+// Fused round: bind every A_k, B_k (in place) and the shared eq polynomial (Cin -> Cout, ping-pong: it is
+// read by all circuits) with the challenge of round j, and evaluate round j+1 on the bound values in the
+// same pass.  Per element pair this reads 4 and writes 2 elements instead of (2 + 2 reads, 1 write) x 2
+// kernels: 40 % less HBM traffic and one launch per round instead of three (sumcheck.rs:49-120).
+// h = number of bound outputs per polynomial (current length / 2), must be >= 2.
+__global__ void __launch_bounds__(kThreads)
+    sc_bind_eval_cubic_kernel(fr_t* const* A, fr_t* const* B, const fr_t* Cin, fr_t* Cout, size_t h, fr_t r,
+                              fr_t* partial, fr_t* out_direct) {
+  __shared__ fr_t scratch[3 * kThreads / 32];
+  fr_t* a = A[blockIdx.y];
+  fr_t* b = B[blockIdx.y];
+  const size_t q = h / 2;
+  fr_t acc[3] = {fr_zero(), fr_zero(), fr_zero()};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < q; i += (size_t)gridDim.x * blockDim.x) {
+    fr_t lo, hi;
+    lo = ld_fr_stream(a + i); hi = ld_fr_stream(a + i + h);
+    fr_t a0 = fr_add(lo, fr_mul(r, fr_sub(hi, lo)));
+    lo = ld_fr_stream(a + i + q); hi = ld_fr_stream(a + i + q + h);
+    fr_t a1 = fr_add(lo, fr_mul(r, fr_sub(hi, lo)));
+    st_fr(a + i, a0);
+    st_fr(a + i + q, a1);
+    lo = ld_fr_stream(b + i); hi = ld_fr_stream(b + i + h);
+    fr_t b0 = fr_add(lo, fr_mul(r, fr_sub(hi, lo)));
+    lo = ld_fr_stream(b + i + q); hi = ld_fr_stream(b + i + q + h);
+    fr_t b1 = fr_add(lo, fr_mul(r, fr_sub(hi, lo)));
+    st_fr(b + i, b0);
+    st_fr(b + i + q, b1);
+    lo = ld_fr(Cin + i); hi = ld_fr(Cin + i + h);
+    fr_t c0 = fr_add(lo, fr_mul(r, fr_sub(hi, lo)));
+    lo = ld_fr(Cin + i + q); hi = ld_fr(Cin + i + q + h);
+    fr_t c1 = fr_add(lo, fr_mul(r, fr_sub(hi, lo)));
+    if (blockIdx.y == 0) {
+      st_fr(Cout + i, c0);
+      st_fr(Cout + i + q, c1);
+    }
+    acc[0] = fr_add(acc[0], fr_mul(fr_mul(a0, b0), c0));
+    fr_t da = fr_sub(a1, a0), db = fr_sub(b1, b0), dc = fr_sub(c1, c0);
+    fr_t a2 = fr_add(a1, da), b2 = fr_add(b1, db), c2 = fr_add(c1, dc);
+    acc[1] = fr_add(acc[1], fr_mul(fr_mul(a2, b2), c2));
+    fr_t a3 = fr_add(a2, da), b3 = fr_add(b2, db), c3 = fr_add(c2, dc);
+    acc[2] = fr_add(acc[2], fr_mul(fr_mul(a3, b3), c3));
+  }
+  block_sum_fr<3>(acc, scratch);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+      if (gridDim.x == 1)
+        out_direct[(size_t)blockIdx.y * 3 + t] = acc[t];
+      else
+        partial[((size_t)blockIdx.y * 3 + t) * gridDim.x + blockIdx.x] = acc[t];
+    }
+  }
+}
+// returns the number of kernels launched
+int launch_sumcheck_bind_eval_cubic(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Cin, fr_t* Cout, int ncirc, size_t h,
+                                    const fr_t& r, fr_t* partial, fr_t* out, cudaStream_t st) {
+  size_t q = h / 2;
+  int per = kMaxBlocks / ncirc;
+  if (per < 1) per = 1;
+  int bx = grid_for(q, kThreads, per);
+  dim3 grid(bx, ncirc);
+  sc_bind_eval_cubic_kernel<<<grid, kThreads, 0, st>>>(d_A, d_B, Cin, Cout, h, r, partial, out);
+  if (bx == 1) return 1;
+  reduce_partials_kernel<<<ncirc * 3, kThreads, 0, st>>>(partial, bx, out);
+  return 2;
+}
 void launch_sumcheck_eval_cubic(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Ceq, int ncirc, size_t half,
                                 fr_t* partial, fr_t* out, cudaStream_t st) {
   int per = kMaxBlocks / ncirc;

@@ -19,6 +19,8 @@
 
 #include <thread>
 
+#include "host_fq64.hpp"
+
 namespace lb {
 
 unsigned long long g_launches = 0;
@@ -58,6 +60,7 @@ void ctx_destroy(Ctx* c) {
   cudaFree(c->d_small);
   cudaFree(c->d_eq_scratch);
   cudaFree(c->d_flag);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
   cudaFreeHost(c->h_pin);
   cudaStreamDestroy(c->st);
   delete c;
@@ -116,7 +119,8 @@ static std::vector<uint8_t> msm_rows_u32(Ctx* c, const Gens& g, const uint32_t* 
   if (nw > 5) throw std::runtime_error("u32 MSM path: scalars wider than 32 bits");
   DBuf<pt_ext> part(c, msm_partials_count(nrows, ncols, nw));
   DBuf<uint32_t> comp(c, (size_t)nrows * 8);
-  launch_msm_rows(g.d_table.p, g.n_points, 1, d_scal, 1, row_stride, nrows, ncols, nw, part.p, nullptr, comp.p, c->st);
+  launch_msm_rows(g.d_table.p, g.n_points, 1, d_scal, 1, row_stride, nrows, ncols, nw, part.p, nullptr, comp.p, nullptr,
+                  c->st);
   g_launches += 2;
   std::vector<uint8_t> out((size_t)nrows * 32);
   c->d2h(out.data(), comp.p, out.size());
@@ -129,11 +133,23 @@ static std::vector<uint8_t> msm_rows_fr(Ctx* c, const Gens& g, const fr_t* d_sca
   launch_canonicalize(d_scal_mont, canon.p, (size_t)nrows * ncols, c->d_flag, c->st);
   int nw = kMsmFullWindows;
   DBuf<pt_ext> part(c, msm_partials_count(nrows, ncols, nw));
+  std::vector<uint8_t> out((size_t)nrows * 32);
+  if (nrows <= 8) {
+    // a couple of points per Bulletproofs round: ship (X, Y, Z) and invert on the host (3 us vs ~100 us
+    // for the same serial chain on one GPU thread)
+    DBuf<uint32_t> raw(c, (size_t)nrows * 24);
+    launch_msm_rows(g.d_table.p + col0, g.n_points, 1, canon.p, 8, (size_t)ncols, nrows, ncols, nw, part.p, nullptr,
+                    nullptr, raw.p, c->st);
+    g_launches += 3;
+    uint32_t xyz[8 * 24];
+    c->d2h(xyz, raw.p, (size_t)nrows * 96);
+    for (int i = 0; i < nrows; i++) h64::compress_xyz(xyz + 24 * i, out.data() + 32 * i);
+    return out;
+  }
   DBuf<uint32_t> comp(c, (size_t)nrows * 8);
   launch_msm_rows(g.d_table.p + col0, g.n_points, 1, canon.p, 8, (size_t)ncols, nrows, ncols, nw, part.p, nullptr, comp.p,
-                  c->st);
+                  nullptr, c->st);
   g_launches += 3;
-  std::vector<uint8_t> out((size_t)nrows * 32);
   c->d2h(out.data(), comp.p, out.size());
   return out;
 }
@@ -162,14 +178,18 @@ Dense* densify(Ctx* c, const uint64_t* indices, size_t n, size_t C, size_t log_m
   d->nv_l = log2_exact_or_ceil(next_pow2(2 * C * d->s));
   d->nv_m = log2_exact_or_ceil(next_pow2(C)) + log_m;
   const size_t s = d->s, m = d->m, nl = (size_t)1 << d->nv_l, nm = (size_t)1 << d->nv_m;
-  std::vector<uint32_t> l_host(nl, 0), m_host(nm, 0);
+  // pinned, reused across calls: no per-call page faults, and the upload runs at full PCIe rate
+  uint32_t* l_host = c->stage(nl + nm);
+  uint32_t* m_host = l_host + nl;
+  if (nl > 2 * C * s) memset(l_host + 2 * C * s, 0, (nl - 2 * C * s) * sizeof(uint32_t));
+  memset(m_host, 0, nm * sizeof(uint32_t));
   // densified.rs:33-56: per dimension, pad with address 0 and run the (inherently sequential) timestamp
   // counters; dimensions are independent, so one host thread each.
   std::vector<int> bad(C, 0);
   auto work = [&](size_t i) {
-    uint32_t* dim = l_host.data() + i * s;
-    uint32_t* rd = l_host.data() + (C + i) * s;
-    uint32_t* fin = m_host.data() + i * m;
+    uint32_t* dim = l_host + i * s;
+    uint32_t* rd = l_host + (C + i) * s;
+    uint32_t* fin = m_host + i * m;
     for (size_t k = 0; k < s; k++) {
       uint64_t addr = k < n ? indices[k * C + i] : 0;
       if (addr >= m) {
@@ -197,8 +217,8 @@ Dense* densify(Ctx* c, const uint64_t* indices, size_t n, size_t C, size_t log_m
   d->d_m_u32.alloc(c, nm);
   d->d_l_fr.alloc(c, nl);
   d->d_m_fr.alloc(c, nm);
-  LB_CUDA_CHECK(cudaMemcpyAsync(d->d_l_u32.p, l_host.data(), nl * 4, cudaMemcpyHostToDevice, c->st));
-  LB_CUDA_CHECK(cudaMemcpyAsync(d->d_m_u32.p, m_host.data(), nm * 4, cudaMemcpyHostToDevice, c->st));
+  LB_CUDA_CHECK(cudaMemcpyAsync(d->d_l_u32.p, l_host, nl * 4, cudaMemcpyHostToDevice, c->st));
+  LB_CUDA_CHECK(cudaMemcpyAsync(d->d_m_u32.p, m_host, nm * 4, cudaMemcpyHostToDevice, c->st));
   launch_from_u32(d->d_l_u32.p, d->d_l_fr.p, nl, c->st);  // DensePolynomial::from_usize + merge
   launch_from_u32(d->d_m_u32.p, d->d_m_fr.p, nm, c->st);
   g_launches += 2;
@@ -353,7 +373,7 @@ static GPAProof prove_gpa(Ctx* c, std::vector<Circuit*>& circuits, std::vector<f
   const int ncirc = (int)circuits.size();
   const size_t num_layers = circuits[0]->num_layers;
   DBuf<fr_t*> d_A(c, ncirc), d_B(c, ncirc), d_AB(c, 2 * ncirc);
-  DBuf<fr_t> eqbuf(c, std::max<size_t>(circuits[0]->N / 2, 1));
+  DBuf<fr_t> eqbuf(c, std::max<size_t>(circuits[0]->N / 2, 1)), eqbuf2(c, std::max<size_t>(circuits[0]->N / 4, 1));
   std::vector<fr_t*> hA(ncirc), hB(ncirc), hAB(2 * ncirc);
   std::vector<fr_t> rand;
   std::vector<fr_t> ev((size_t)ncirc * 3), fin((size_t)2 * ncirc);
@@ -377,10 +397,14 @@ static GPAProof prove_gpa(Ctx* c, std::vector<Circuit*>& circuits, std::vector<f
     LayerProof lp;
     std::vector<fr_t> rand_prod;
     size_t cur = half_len;  // current length of A_k / B_k / C
+    fr_t* Ccur = eqbuf.p;
+    fr_t* Cnext = eqbuf2.p;
+    if (cur > 1) {  // round 0 evaluation; later rounds come out of the fused bind+eval kernel
+      launch_sumcheck_eval_cubic(d_A.p, d_B.p, Ccur, ncirc, cur / 2, c->d_partial, c->d_small, c->st);
+      g_launches += 2;
+    }
     while (cur > 1) {
       size_t half = cur / 2;
-      launch_sumcheck_eval_cubic(d_A.p, d_B.p, eqbuf.p, ncirc, half, c->d_partial, c->d_small, c->st);
-      g_launches += 2;
       c->d2h(ev.data(), c->d_small, ev.size() * sizeof(fr_t));
       fr_t c0 = fr_zero(), c2 = fr_zero(), c3 = fr_zero();
       for (int k = 0; k < ncirc; k++) {  // sumcheck.rs:95-97
@@ -393,9 +417,15 @@ static GPAProof prove_gpa(Ctx* c, std::vector<Circuit*>& circuits, std::vector<f
       unipoly_append(coeffs, transcript);
       fr_t r_j = transcript.challenge_scalar("challenge_nextround");
       rand_prod.push_back(r_j);
-      launch_bind_top_ptrs(d_AB.p, 2 * ncirc, half, r_j, c->st);
-      launch_bind_top(eqbuf.p, 0, 1, half, r_j, c->st);
-      g_launches += 2;
+      if (half > 1) {
+        // bind with r_j and evaluate the next round in one pass (sumcheck.rs:116-120 + 63-89)
+        g_launches += launch_sumcheck_bind_eval_cubic(d_A.p, d_B.p, Ccur, Cnext, ncirc, half, r_j, c->d_partial,
+                                                      c->d_small, c->st);
+        std::swap(Ccur, Cnext);
+      } else {
+        launch_bind_top_ptrs(d_AB.p, 2 * ncirc, half, r_j, c->st);
+        g_launches += 1;
+      }
       e = unipoly_evaluate(coeffs, r_j);
       lp.proof.push_back(unipoly_compress(coeffs));
       cur = half;
@@ -476,6 +506,7 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
   if (n + 2 > g.n_points) throw std::runtime_error("generator stream too short");
   const size_t lg_n = rv;
   // L, R = factored eq evals (eq_poly.rs:44-52); LZ = L . Z (dense_mlpoly.rs:183-207)
+  std::unique_ptr<SpanTimer> sp1(new SpanTimer(c, "PE.1 eq+bound"));
   DBuf<fr_t> Lvec(c, L_size), a(c, n), b(c, n);
   eq_evals_dev(c, r, 0, lv, Lvec.p);
   eq_evals_dev(c, r, lv, rv, b.p);  // a_vec of the dot product proof = R
@@ -484,6 +515,7 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
   g_launches += 2;
 
   // ---- DotProductProofLog::prove
+  sp1.reset(new SpanTimer(c, "PE.2 Cx,Cy,append a"));
   transcript.append_protocol_name("dot product proof (log)");
   fr_t d = tape.random_scalar("d");
   fr_t r_delta = tape.random_scalar("r_delta");
@@ -508,6 +540,7 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
     transcript.append_scalars_bytes("a", bytes.data(), n);
   }
   // ---- BulletReductionProof::prove with unfolded generators (see file header)
+  sp1.reset(new SpanTimer(c, "PE.3 bullet rounds"));
   fr_t blind_fin = fr_zero();  // blind_Gamma = blind_x + blind_y = 0
   DBuf<fr_t> W0(c, n), W1(c, n), sLR(c, 2 * (n + 2));
   fr_t* W = W0.p;
@@ -538,6 +571,7 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
     out.R_vec.insert(out.R_vec.end(), LR.begin() + 32, LR.begin() + 64);
     m = h;
   }
+  sp1.reset(new SpanTimer(c, "PE.4 delta,beta"));
   fr_t ab[2];
   LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin, a.p, 32, cudaMemcpyDeviceToHost, c->st));
   LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin + 32, b.p, 32, cudaMemcpyDeviceToHost, c->st));

@@ -25,6 +25,17 @@ struct Ctx {
   size_t small_elems = 0;
   fr_t* d_eq_scratch = nullptr;
   unsigned* d_flag = nullptr;
+  uint32_t* h_stage = nullptr;  // pinned staging for the densified integer arrays (grown on demand, reused)
+  size_t h_stage_elems = 0;
+  uint32_t* stage(size_t elems) {
+    if (elems > h_stage_elems) {
+      if (h_stage) cudaFreeHost(h_stage);
+      h_stage = nullptr;
+      LB_CUDA_CHECK(cudaMallocHost((void**)&h_stage, elems * sizeof(uint32_t)));
+      h_stage_elems = elems;
+    }
+    return h_stage;
+  }
   double t_densify_ms = 0, t_commit_ms = 0, t_prove_ms = 0;
   std::map<std::string, double> spans;  // filled when LASSO_B200_SPANS=1 (forces syncs)
   bool span_sync = false;
