@@ -162,6 +162,9 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--log-s", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharded", action="store_true",
+                    help="N > 1: ONE proof sharded over the N GPUs (strong scaling, NCCL exchange per sumcheck round) "
+                         "instead of one independent proof per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -183,8 +186,12 @@ def main():
     C, log_m, log_s = 4, 16, args.log_s
     s = 1 << log_s
     S = lb.Strategy(lb.XOR, C, log_m)
-    idx, r, tape_seed = make_inputs(log_s, C, log_m, 0x4C4153534F + rank)  # each rank: its own batch
+    sharded = args.sharded and world > 1
+    # independent proofs: each rank its own batch; sharded: every rank the same lookups (one proof)
+    idx, r, tape_seed = make_inputs(log_s, C, log_m, 0x4C4153534F + (0 if sharded else rank))
     ctx = lb.Context(local_rank)
+    if sharded:
+        ctx.init_comm(rank, world)
     need = lb.gens_points_needed(C, s, S.num_memories, log_m)
     cache = os.path.join(ROOT, "oracle", "_build", "gens_gens_sparse_poly_%d.npy" % need)
     stream = np.load(cache) if os.path.exists(cache) else lb.sample_generators(b"gens_sparse_poly", need)
@@ -256,16 +263,19 @@ def main():
         nv_l = int(np.log2(2 * C * s))
         h2d = 4 * ((1 << nv_l) + (C << log_m))
         line = {
-            "metric": METRIC, "value": world * args.steps * s / t_res, "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": (1 if sharded else world) * args.steps * s / t_res, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (8-limb 256-bit Montgomery)",
+            "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
+            "dtype": "u32 (8-limb 256-bit Montgomery)",
             "data": "synthetic",
             "config": {"workload": "Lasso XOR subtable, C=4, M=2^16, 2^%d lookups per GPU, G=curve25519: commit + prove "
                                    "(densify in e2e); proof bit-exact vs CPU oracle" % log_s,
                        "l2": "inputs larger than L2 (>= 128 MiB per polynomial set)",
-                       "parallelism": "independent proof per GPU (weak scaling, no data-path collective)",
+                       "parallelism": ("ONE proof sharded over %d GPUs by the low index bits: NCCL all-gather of the partial "
+                                       "sums per sumcheck round + gather-then-add of partial MSM points" % world) if sharded
+                       else "independent proof per GPU (weak scaling, no data-path collective)",
                        "proof_bytes": proof_bytes, "commitment_bytes": com_bytes, "wall_s_resident": wall},
-            "e2e": {"value": world * args.steps * s / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "e2e": {"value": (1 if sharded else world) * args.steps * s / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": proof_bytes + com_bytes, "ms_per_step": 1e3 * t_e2e / args.steps},
             "gpu_launches": launches,
             "clocks": clocks,

@@ -50,6 +50,15 @@ const char* lasso_last_error(void);
 int lasso_ctx_create(lasso_ctx** out, int device_id);
 void lasso_ctx_destroy(lasso_ctx* ctx);
 
+/* One proof sharded over `world` GPUs (one process per GPU, world a power of two): rank 0 obtains an id with
+ * lasso_comm_unique_id, every rank receives it out of band (e.g. torch.distributed broadcast) and calls
+ * lasso_ctx_init_comm before any other call.  Afterwards lasso_densify / lasso_commit / lasso_prove are
+ * collective: every rank passes the SAME arguments, holds the low-index-bit shard of every polynomial, and
+ * receives the same (bit-identical to single-GPU) commitment and proof bytes.  Exchanges: one small all-gather
+ * per sumcheck round and one gather-then-add of partial points per row-MSM (NCCL over NVLink). */
+int lasso_comm_unique_id(uint8_t out[128]);
+int lasso_ctx_init_comm(lasso_ctx*, const uint8_t id[128], int rank, int world);
+
 /* ---------------------------------------------------------------- per-loop entry points (host buffers) */
 
 /* DensePolynomial::bound_poly_var_top  poly/dense_mlpoly.rs:209-216.  Z has `len` elements; the first
@@ -126,6 +135,9 @@ int lasso_prove(lasso_ctx*, int strategy, int log_R, lasso_dense*, const uint64_
  * (ms) of the last densify / commit / prove calls. */
 unsigned long long lasso_launch_count(const lasso_ctx*);
 void lasso_last_timings(const lasso_ctx*, double out_ms[3]);
+/* With LASSO_B200_SPANS=1 in the environment the prover synchronises around named spans (the analogue of the
+ * reference's tracing spans, e.g. "Sumcheck.prove", "Subtables.commit"); this drains them as "name=ms;..." */
+size_t lasso_spans(const lasso_ctx*, char* buf, size_t cap);
 
 /* Device-resident bind benchmark hook (bench.py roofline leg): allocates npolys x len random elements on the
  * device once, then runs `iters` top-binds over them on the context stream and returns the average kernel

@@ -105,6 +105,25 @@ class Context:
         except Exception:
             pass
 
+    def init_comm(self, rank=None, world=None):
+        """Shard ONE proof over the GPUs of a torch.distributed job (one process per GPU, world a power of two).
+        The NCCL id is created on rank 0 and broadcast through torch.distributed (any backend)."""
+        import torch
+        import torch.distributed as dist
+
+        rank = dist.get_rank() if rank is None else rank
+        world = dist.get_world_size() if world is None else world
+        ident = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            _chk(lib().lasso_comm_unique_id(_p(ident)))
+        t = torch.from_numpy(ident)
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, src=0)
+        ident = np.ascontiguousarray(t.cpu().numpy())
+        _chk(lib().lasso_ctx_init_comm(self._h, _p(ident), int(rank), int(world)))
+        self.rank, self.world = rank, world
+
     @property
     def launches(self):
         return int(lib().lasso_launch_count(self._h))

@@ -45,8 +45,21 @@ int lasso_ctx_create(lasso_ctx** out, int device_id) {
 }
 void lasso_ctx_destroy(lasso_ctx* ctx) {
   if (!ctx) return;
+  comm_destroy(ctx->c);
   ctx_destroy(ctx->c);
   delete ctx;
+}
+int lasso_comm_unique_id(uint8_t out[128]) {
+  LB_TRY
+  comm_unique_id(out);
+  return 0;
+  LB_CATCH
+}
+int lasso_ctx_init_comm(lasso_ctx* h, const uint8_t id[128], int rank, int world) {
+  LB_TRY
+  comm_init(h->c, id, rank, world);
+  return 0;
+  LB_CATCH
 }
 
 int lasso_bind_top(lasso_ctx* h, uint64_t* Z, size_t len, const uint64_t r[4]) {
@@ -195,7 +208,7 @@ static void msm_variable_base(Ctx* c, const uint64_t* bases_affine, size_t nbase
   if (nw > kMsmFullWindows) nw = kMsmFullWindows;
   DBuf<pt_ext> part(c, msm_partials_count((int)nrows, (int)ncols, nw));
   DBuf<fq_t> oe(c, nrows * 4);
-  launch_msm_rows(tab.p, nbases, 0, canon.p, 8, ncols, (int)nrows, (int)ncols, nw, part.p, oe.p, nullptr, nullptr, c->st);
+  launch_msm_rows(tab.p, nbases, 0, canon.p, 8, ncols, (int)nrows, (int)ncols, nw, 1, 0, part.p, oe.p, nullptr, nullptr, c->st);
   g_launches += 4;
   LB_CUDA_CHECK(cudaMemcpyAsync(out_ext, oe.p, nrows * 128, cudaMemcpyDeviceToHost, c->st));
   c->sync();

@@ -86,8 +86,9 @@ void launch_bound(const fr_t* Z, const fr_t* L, size_t L_size, size_t R_size, fr
                   cudaStream_t st);
 int bound_max_chunks();
 // Reed-Solomon fingerprints (memory_checking.rs:236-310).  init/final over M cells, read/write over s ops.
-void launch_gp_fingerprints_mem(const fr_t* table, const fr_t* final_fr, size_t M, const fr_t& gamma,
-                                const fr_t& tau, fr_t* out_init, fr_t* out_final, cudaStream_t st);
+// M_local cells of this rank; local cell i = global address i*G + g; `table` is the full M-entry table
+void launch_gp_fingerprints_mem(const fr_t* table, const fr_t* final_fr, size_t M_local, int G, int g,
+                                const fr_t& gamma, const fr_t& tau, fr_t* out_init, fr_t* out_final, cudaStream_t st);
 void launch_gp_fingerprints_ops(const fr_t* dim_fr, const fr_t* E_fr, const fr_t* read_fr, size_t s,
                                 const fr_t& gamma, const fr_t& tau, fr_t* out_read, fr_t* out_write,
                                 cudaStream_t st);
@@ -101,7 +102,9 @@ void launch_cross_inner_products(const fr_t* a, const fr_t* b, size_t h, fr_t* p
 // w'[2t] = w[t]*uinv, w'[2t+1] = w[t]*u  (weights of the unfolded generators, see msm_kernels.cu)
 void launch_expand_weights(const fr_t* w, fr_t* w_out, size_t n_in, const fr_t& u, const fr_t& uinv, cudaStream_t st);
 // scalars for the L / R MSMs over the ORIGINAL generators: see prover.cu
-void launch_bullet_scalars(const fr_t* a, const fr_t* w, size_t n, size_t m, fr_t* sL, fr_t* sR, cudaStream_t st);
+void launch_bullet_scalars(const fr_t* a, const fr_t* w, size_t n_loc, size_t m, int G, int g, int a_rep, fr_t* sL,
+                           fr_t* sR, cudaStream_t st);
+void launch_scale_strided(const fr_t* in, fr_t* out, size_t n, size_t stride, size_t off, const fr_t& k, cudaStream_t st);
 void launch_scale(const fr_t* in, fr_t* out, size_t n, const fr_t& k, cudaStream_t st);
 
 }  // namespace lb

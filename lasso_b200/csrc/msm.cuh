@@ -18,11 +18,14 @@ size_t msm_partials_count(int nrows, int ncols, int nw);
 //   (must cover max_bits + 2; <= 5 for u32, <= 32 for 256-bit)
 //   shifted != 0: `table` holds nw window tables (fixed-base); else only window 0 (variable-base)
 // Outputs (any may be null): out_ext = nrows x (x,y,t,z) arkworks Montgomery limbs with z = 1;
-// out_comp = nrows x 32 bytes ark-serialize compressed; out_raw = nrows x 96 B un-normalised (X,Y,Z)
-// internal limbs for host-side normalisation (host_fq64.hpp) when there are only a few rows.
+// out_comp = nrows x 32 bytes ark-serialize compressed; out_raw = nrows x 128 B un-normalised (X,Y,Z,T)
+// internal limbs for host-side normalisation (host_fq64.hpp) or the cross-GPU gather-then-add.
+// Local column c uses generator index c*col_mul + col_add.
 void launch_msm_rows(const pt_niels* table, size_t table_stride, int shifted, const void* scalars, int scalar_limbs,
-                     size_t row_stride, int nrows, int ncols, int nw, pt_ext* partials, fq_t* out_ext,
-                     uint32_t* out_comp, uint32_t* out_raw, cudaStream_t st);
+                     size_t row_stride, int nrows, int ncols, int nw, int col_mul, int col_add, pt_ext* partials,
+                     fq_t* out_ext, uint32_t* out_comp, uint32_t* out_raw, cudaStream_t st);
+// raw[(k*nrows + row)*32 ..): (X,Y,Z,T) of source k; adds the nsrc sources per row (cross-GPU gather-then-add)
+void launch_sum_raw_points(const uint32_t* raw, int nsrc, int nrows, uint32_t* out_raw, uint32_t* out_comp, cudaStream_t st);
 void launch_combine_points(const fq_t* in_ext, int n, fq_t* out_ext, uint32_t* out_comp, cudaStream_t st);
 
 inline int msm_windows_for_bits(unsigned max_bits) {

@@ -150,7 +150,8 @@ struct MsmSmem {
 template <int SL>
 __global__ void __launch_bounds__(MSM_T)
     msm_bucket_kernel(const pt_niels* table, size_t table_stride, int shifted, const uint32_t* scalars,
-                      size_t row_stride /*in scalars*/, int ncols, int chunk_cols, pt_ext* partials) {
+                      size_t row_stride /*in scalars*/, int ncols, int chunk_cols, int col_mul, int col_add,
+                      pt_ext* partials) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   MsmSmem& sm = *reinterpret_cast<MsmSmem*>(smem_raw);
   const int w = blockIdx.x, row = blockIdx.y, chunk = blockIdx.z, tid = threadIdx.x;
@@ -237,13 +238,15 @@ __global__ void __launch_bounds__(MSM_T)
         pt_ext acc = pt_identity();
         // software pipeline: the next point's 96 B are in flight while the current addition runs
         uint16_t e = sm.list[pos];
-        pt_niels nn = ld_niels(tw + c_begin + (e & 0x7fff));
+        // local column c -> generator index c * col_mul + col_add (col_mul = #GPUs when one proof is sharded
+        // by the low index bits: this rank owns the columns congruent to its rank)
+        pt_niels nn = ld_niels(tw + (size_t)(c_begin + (e & 0x7fff)) * col_mul + col_add);
         for (int p = pos; p < run_end; p++) {
           const uint16_t ecur = e;
           const pt_niels ncur = nn;
           if (p + 1 < run_end) {
             e = sm.list[p + 1];
-            nn = ld_niels(tw + c_begin + (e & 0x7fff));
+            nn = ld_niels(tw + (size_t)(c_begin + (e & 0x7fff)) * col_mul + col_add);
           }
           // P - Q = P + (-Q): negating an affine-niels point is a swap and one negation
           acc = pt_madd(acc, (ecur & 0x8000) ? niels_neg(ncur) : ncur);
@@ -345,8 +348,8 @@ __device__ __forceinline__ pt_ext ld_pt(const pt_ext* p) {
   return r;
 }
 // One warp per row.  out_ext: (x,y,t,z=1) arkworks Montgomery limbs; out_comp: 32 B compressed;
-// out_raw: un-normalised (X, Y, Z) internal limbs, 96 B/row — the caller normalises on the host
-// (used when there are only a couple of rows: one inversion is a 265-step serial chain).
+// out_raw: un-normalised (X, Y, Z, T) internal limbs, 128 B/row — for host-side normalisation (a couple of
+// rows: one inversion is a 265-step serial chain) or for the cross-GPU gather-then-add of partial points.
 __global__ void __launch_bounds__(32)
     msm_finish_kernel(const pt_ext* partials, int nrows, int nw, int nchunks, int shifted, fq_t* out_ext,
                       uint32_t* out_comp, uint32_t* out_raw) {
@@ -376,9 +379,10 @@ __global__ void __launch_bounds__(32)
   if (out_raw) {
 #pragma unroll
     for (int l = 0; l < 8; l++) {
-      out_raw[(size_t)row * 24 + l] = acc.X.v[l];
-      out_raw[(size_t)row * 24 + 8 + l] = acc.Y.v[l];
-      out_raw[(size_t)row * 24 + 16 + l] = acc.Z.v[l];
+      out_raw[(size_t)row * 32 + l] = acc.X.v[l];
+      out_raw[(size_t)row * 32 + 8 + l] = acc.Y.v[l];
+      out_raw[(size_t)row * 32 + 16 + l] = acc.Z.v[l];
+      out_raw[(size_t)row * 32 + 24 + l] = acc.T.v[l];
     }
   }
   if (!out_comp && !out_ext) return;
@@ -418,8 +422,8 @@ size_t msm_partials_count(int nrows, int ncols, int nw) {
 }
 
 void launch_msm_rows(const pt_niels* table, size_t table_stride, int shifted, const void* scalars, int scalar_limbs,
-                     size_t row_stride, int nrows, int ncols, int nw, pt_ext* partials, fq_t* out_ext,
-                     uint32_t* out_comp, uint32_t* out_raw, cudaStream_t st) {
+                     size_t row_stride, int nrows, int ncols, int nw, int col_mul, int col_add, pt_ext* partials,
+                     fq_t* out_ext, uint32_t* out_comp, uint32_t* out_raw, cudaStream_t st) {
   if (nrows <= 0) return;
   if (nw < 1) nw = 1;
   int chunk_cols = msm_chunk_cols(nrows, ncols, nw);
@@ -439,13 +443,55 @@ void launch_msm_rows(const pt_niels* table, size_t table_stride, int shifted, co
     if (scalar_limbs == 1)
       msm_bucket_kernel<1><<<grid, MSM_T, sizeof(MsmSmem), st>>>(
           table, table_stride, shifted, (const uint32_t*)scalars + (size_t)r0 * row_stride, row_stride, ncols,
-          chunk_cols, part);
+          chunk_cols, col_mul, col_add, part);
     else
       msm_bucket_kernel<8><<<grid, MSM_T, sizeof(MsmSmem), st>>>(
           table, table_stride, shifted, (const uint32_t*)scalars + (size_t)r0 * row_stride * 8, row_stride, ncols,
-          chunk_cols, part);
+          chunk_cols, col_mul, col_add, part);
   }
   msm_finish_kernel<<<nrows, 32, 0, st>>>(partials, nrows, nw, nchunks, shifted, out_ext, out_comp, out_raw);
+}
+
+// Cross-GPU "bucket-sum reduce": raw[(k * nrows + row) * 32 ..] = partial (X,Y,Z,T) of source k for `row`
+// (k < nsrc: the all-gathered per-rank partials, plus optionally a replicated tail term).  One warp-lane
+// per row adds the nsrc points; output raw again (few rows -> host normalisation) and/or compressed.
+__global__ void __launch_bounds__(64)
+    sum_raw_points_kernel(const uint32_t* raw, int nsrc, int nrows, uint32_t* out_raw, uint32_t* out_comp) {
+  int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= nrows) return;
+  pt_ext acc = pt_identity();
+  for (int k = 0; k < nsrc; k++) {
+    const uint32_t* p = raw + ((size_t)k * nrows + row) * 32;
+    pt_ext q;
+#pragma unroll
+    for (int l = 0; l < 8; l++) {
+      q.X.v[l] = p[l];
+      q.Y.v[l] = p[8 + l];
+      q.Z.v[l] = p[16 + l];
+      q.T.v[l] = p[24 + l];
+    }
+    acc = pt_add(acc, q);
+  }
+  if (out_raw) {
+#pragma unroll
+    for (int l = 0; l < 8; l++) {
+      out_raw[(size_t)row * 32 + l] = acc.X.v[l];
+      out_raw[(size_t)row * 32 + 8 + l] = acc.Y.v[l];
+      out_raw[(size_t)row * 32 + 16 + l] = acc.Z.v[l];
+      out_raw[(size_t)row * 32 + 24 + l] = acc.T.v[l];
+    }
+  }
+  if (out_comp) {
+    fq_t x, y;
+    pt_to_affine_canonical(acc, x, y);
+    uint32_t c[8];
+    pt_compress_canonical(x, y, c);
+#pragma unroll
+    for (int l = 0; l < 8; l++) out_comp[(size_t)row * 8 + l] = c[l];
+  }
+}
+void launch_sum_raw_points(const uint32_t* raw, int nsrc, int nrows, uint32_t* out_raw, uint32_t* out_comp, cudaStream_t st) {
+  sum_raw_points_kernel<<<(nrows + 63) / 64, 64, 0, st>>>(raw, nsrc, nrows, out_raw, out_comp);
 }
 
 // sum of a few extended points + normalisation (used to add a blind*h term or combine rows)

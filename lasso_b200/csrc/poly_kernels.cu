@@ -512,10 +512,12 @@ void launch_bound(const fr_t* Z, const fr_t* L, size_t L_size, size_t R_size, fr
 
 // memory_checking.rs:249-252: hash(a, v, t) = t*gamma^2 + v*gamma + a - tau
 __global__ void __launch_bounds__(kThreads)
-    fp_mem_kernel(const fr_t* table, const fr_t* final_fr, size_t M, fr_t gamma, fr_t gamma2, fr_t tau, fr_t* out_init,
-                  fr_t* out_final) {
+    fp_mem_kernel(const fr_t* table, const fr_t* final_fr, size_t M, int G, int g, fr_t gamma, fr_t gamma2, fr_t tau,
+                  fr_t* out_init, fr_t* out_final) {
+  // M = local cells; local cell i is global address i*G + g (low-bit partition); `table` is the full table
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (size_t)gridDim.x * blockDim.x) {
-    fr_t h0 = fr_sub(fr_add(fr_mul(ld_fr(table + i), gamma), fr_from_u64(i)), tau);  // ts = 0
+    size_t gi = i * G + g;
+    fr_t h0 = fr_sub(fr_add(fr_mul(ld_fr(table + gi), gamma), fr_from_u64(gi)), tau);  // ts = 0
     st_fr(out_init + i, h0);
     st_fr(out_final + i, fr_add(h0, fr_mul(ld_fr(final_fr + i), gamma2)));
   }
@@ -530,9 +532,10 @@ __global__ void __launch_bounds__(kThreads)
     st_fr(out_write + i, fr_add(hr, gamma2));  // write ts = read ts + 1
   }
 }
-void launch_gp_fingerprints_mem(const fr_t* table, const fr_t* final_fr, size_t M, const fr_t& gamma,
-                                const fr_t& tau, fr_t* out_init, fr_t* out_final, cudaStream_t st) {
-  fp_mem_kernel<<<grid_for(M), kThreads, 0, st>>>(table, final_fr, M, gamma, fr_sqr(gamma), tau, out_init, out_final);
+void launch_gp_fingerprints_mem(const fr_t* table, const fr_t* final_fr, size_t M_local, int G, int g,
+                                const fr_t& gamma, const fr_t& tau, fr_t* out_init, fr_t* out_final, cudaStream_t st) {
+  fp_mem_kernel<<<grid_for(M_local), kThreads, 0, st>>>(table, final_fr, M_local, G, g, gamma, fr_sqr(gamma), tau,
+                                                        out_init, out_final);
 }
 void launch_gp_fingerprints_ops(const fr_t* dim_fr, const fr_t* E_fr, const fr_t* read_fr, size_t s,
                                 const fr_t& gamma, const fr_t& tau, fr_t* out_read, fr_t* out_write,
@@ -589,26 +592,43 @@ __global__ void __launch_bounds__(kThreads)
 void launch_expand_weights(const fr_t* w, fr_t* w_out, size_t n_in, const fr_t& u, const fr_t& uinv, cudaStream_t st) {
   expand_weights_kernel<<<grid_for(n_in), kThreads, 0, st>>>(w, w_out, n_in, u, uinv);
 }
-// Round with current length m (half h = m/2) over n original generators, weights w[t], t < n/m:
-//   sL[t*m + h + i] = a[i] * w[t],  sL[t*m + i] = 0
-//   sR[t*m + i]     = a[h+i] * w[t], sR[t*m + h + i] = 0           (i < h)
+// Round with current vector length m (half h = m/2) over n original generators, weights w[t], t < n/m.
+// Global column j = t*m + pos:   sL[j] = a[pos-h] * w[t] for pos >= h (else 0),
+//                                sR[j] = a[h+pos] * w[t] for pos <  h (else 0).
+// Sharded over G GPUs this rank owns the columns j = j'*G + g (n_loc of them).  `a` is either this rank's
+// low-bit shard of the folded vector (a_rep = 0, valid while m >= 2G: element p lives at p / G) or the
+// replicated full vector of the tail rounds (a_rep = 1).
 __global__ void __launch_bounds__(kThreads)
-    bullet_scalars_kernel(const fr_t* a, const fr_t* w, size_t n, size_t m, fr_t* sL, fr_t* sR) {
+    bullet_scalars_kernel(const fr_t* a, const fr_t* w, size_t n_loc, size_t m, int G, int g, int a_rep, fr_t* sL,
+                          fr_t* sR) {
   size_t h = m / 2;
-  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
+  for (size_t jl = (size_t)blockIdx.x * blockDim.x + threadIdx.x; jl < n_loc; jl += (size_t)gridDim.x * blockDim.x) {
+    size_t j = jl * G + g;
     size_t t = j / m, pos = j % m;
     fr_t wt = ld_fr(w + t);
     if (pos >= h) {
-      st_fr(sL + j, fr_mul(ld_fr(a + (pos - h)), wt));
-      st_fr(sR + j, fr_zero());
+      size_t idx = pos - h;
+      st_fr(sL + jl, fr_mul(ld_fr(a + (a_rep ? idx : idx / G)), wt));
+      st_fr(sR + jl, fr_zero());
     } else {
-      st_fr(sL + j, fr_zero());
-      st_fr(sR + j, fr_mul(ld_fr(a + h + pos), wt));
+      size_t idx = h + pos;
+      st_fr(sL + jl, fr_zero());
+      st_fr(sR + jl, fr_mul(ld_fr(a + (a_rep ? idx : idx / G)), wt));
     }
   }
 }
-void launch_bullet_scalars(const fr_t* a, const fr_t* w, size_t n, size_t m, fr_t* sL, fr_t* sR, cudaStream_t st) {
-  bullet_scalars_kernel<<<grid_for(n), kThreads, 0, st>>>(a, w, n, m, sL, sR);
+void launch_bullet_scalars(const fr_t* a, const fr_t* w, size_t n_loc, size_t m, int G, int g, int a_rep, fr_t* sL,
+                           fr_t* sR, cudaStream_t st) {
+  bullet_scalars_kernel<<<grid_for(n_loc), kThreads, 0, st>>>(a, w, n_loc, m, G, g, a_rep, sL, sR);
+}
+// out[i] = in[i*stride + off] * k
+__global__ void __launch_bounds__(kThreads)
+    scale_strided_kernel(const fr_t* in, fr_t* out, size_t n, size_t stride, size_t off, fr_t k) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    st_fr(out + i, fr_mul(ld_fr(in + i * stride + off), k));
+}
+void launch_scale_strided(const fr_t* in, fr_t* out, size_t n, size_t stride, size_t off, const fr_t& k, cudaStream_t st) {
+  scale_strided_kernel<<<grid_for(n), kThreads, 0, st>>>(in, out, n, stride, off, k);
 }
 __global__ void __launch_bounds__(kThreads) scale_kernel(const fr_t* in, fr_t* out, size_t n, fr_t k) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)

@@ -108,57 +108,126 @@ Gens* gens_create(Ctx* c, const uint64_t* stream_affine, size_t n_points, size_t
   return g.release();
 }
 
-// ---------------------------------------------------------------------------------------------- MSM helpers
-struct MsmOut {
-  std::vector<uint8_t> comp;  // 32 B per row
-};
-// rows of u32 integer scalars over generator columns [0, ncols)
-static std::vector<uint8_t> msm_rows_u32(Ctx* c, const Gens& g, const uint32_t* d_scal, size_t row_stride, int nrows,
-                                         int ncols, unsigned max_bits) {
-  int nw = msm_windows_for_bits(max_bits);
-  if (nw > 5) throw std::runtime_error("u32 MSM path: scalars wider than 32 bits");
-  DBuf<pt_ext> part(c, msm_partials_count(nrows, ncols, nw));
-  DBuf<uint32_t> comp(c, (size_t)nrows * 8);
-  launch_msm_rows(g.d_table.p, g.n_points, 1, d_scal, 1, row_stride, nrows, ncols, nw, part.p, nullptr, comp.p, nullptr,
-                  c->st);
-  g_launches += 2;
-  std::vector<uint8_t> out((size_t)nrows * 32);
-  c->d2h(out.data(), comp.p, out.size());
-  return out;
+// ---------------------------------------------------------------------------------------------- sharding helpers
+// One proof sharded over G = c->world GPUs: every array of global length n >= G is partitioned by the low
+// log2(G) index bits (rank g holds X[i*G + g]); see comm.cu.  With G == 1 all of this is the identity.
+static inline size_t loc(const Ctx* c, size_t n) {
+  if (n % (size_t)c->world) throw std::runtime_error("array shorter than the number of GPUs");
+  return n / (size_t)c->world;
 }
-// rows of Montgomery Fr scalars (device) over generator columns [col0, col0 + ncols); full-width windows
-static std::vector<uint8_t> msm_rows_fr(Ctx* c, const Gens& g, const fr_t* d_scal_mont, int nrows, int ncols,
-                                        size_t col0) {
-  DBuf<fr_t> canon(c, (size_t)nrows * ncols);
-  launch_canonicalize(d_scal_mont, canon.p, (size_t)nrows * ncols, c->d_flag, c->st);
-  int nw = kMsmFullWindows;
-  DBuf<pt_ext> part(c, msm_partials_count(nrows, ncols, nw));
+// sum a device-side partial result over the ranks, then bring it to the host
+static void reduce_to_host(Ctx* c, fr_t* d_buf, int count, fr_t* h_out) {
+  comm_allreduce_fr(c, d_buf, count);
+  c->d2h(h_out, d_buf, (size_t)count * sizeof(fr_t));
+}
+// this rank's shard of eq(r[off .. off+ell)) (eq_poly.rs:21-38): eq[i*G + g] = eq_hi[i] * eq_lo[g] where
+// eq_lo is the table of the LAST log2(G) coordinates (they bind the low index bits: r[0] <-> MSB)
+static void eq_evals_shard(Ctx* c, const std::vector<fr_t>& r, size_t off, size_t ell, fr_t* out) {
+  const size_t lg = (size_t)c->lg_world;
+  if (ell < lg) throw std::runtime_error("eq table smaller than the number of GPUs");
+  eq_evals_dev(c, r, off, ell - lg, out);
+  if (lg == 0) return;
+  fr_t k = fr_one();
+  for (size_t j = 0; j < lg; j++) {
+    const fr_t& rj = r[off + ell - lg + j];
+    bool bit = (c->rank >> (lg - 1 - j)) & 1;
+    k = fr_mul(k, bit ? rj : fr_sub(fr_one(), rj));
+  }
+  launch_scale(out, out, (size_t)1 << (ell - lg), k, c->st);
+  g_launches += 1;
+}
+
+// ---------------------------------------------------------------------------------------------- MSM helpers
+// Row-MSMs over the generator table.  `d_scal` holds this rank's columns (ncols_loc per row, local column c'
+// = global column c'*G + g + col0).  Optional replicated tail: `d_tail` = nrows x ntail scalars on the
+// generators [tail_col0, tail_col0 + ntail) (the Q and h terms of a Bulletproofs round) — identical on
+// every rank, so it is added once, after the cross-GPU gather.  Returns nrows compressed points.
+static std::vector<uint8_t> msm_rows(Ctx* c, const Gens& g, const void* d_scal, int limbs, size_t row_stride, int nrows,
+                                     int ncols_loc, int nw, const fr_t* d_tail_canon, int ntail, size_t tail_col0) {
+  const int G = c->world;
   std::vector<uint8_t> out((size_t)nrows * 32);
-  if (nrows <= 8) {
-    // a couple of points per Bulletproofs round: ship (X, Y, Z) and invert on the host (3 us vs ~100 us
-    // for the same serial chain on one GPU thread)
-    DBuf<uint32_t> raw(c, (size_t)nrows * 24);
-    launch_msm_rows(g.d_table.p + col0, g.n_points, 1, canon.p, 8, (size_t)ncols, nrows, ncols, nw, part.p, nullptr,
-                    nullptr, raw.p, c->st);
-    g_launches += 3;
-    uint32_t xyz[8 * 24];
-    c->d2h(xyz, raw.p, (size_t)nrows * 96);
-    for (int i = 0; i < nrows; i++) h64::compress_xyz(xyz + 24 * i, out.data() + 32 * i);
+  const bool few = nrows <= 8;
+  DBuf<pt_ext> part(c, msm_partials_count(nrows, ncols_loc, nw));
+  if (G == 1 && !d_tail_canon && !few) {  // the common single-GPU commit: normalise on the device
+    DBuf<uint32_t> comp(c, (size_t)nrows * 8);
+    launch_msm_rows(g.d_table.p, g.n_points, 1, d_scal, limbs, row_stride, nrows, ncols_loc, nw, 1, 0, part.p, nullptr,
+                    comp.p, nullptr, c->st);
+    g_launches += 2;
+    c->d2h(out.data(), comp.p, out.size());
+    return out;
+  }
+  // general path: raw partial points -> (gather over ranks) -> (+ tail) -> sum -> normalise
+  const int nsrc = G + (d_tail_canon ? 1 : 0);
+  DBuf<uint32_t> raw(c, (size_t)(nsrc + 1) * nrows * 32);
+  uint32_t* mine = raw.p + (size_t)nsrc * nrows * 32;  // scratch slot for this rank's partials
+  launch_msm_rows(g.d_table.p, g.n_points, 1, d_scal, limbs, row_stride, nrows, ncols_loc, nw, G, c->rank, part.p, nullptr,
+                  nullptr, G == 1 ? raw.p : mine, c->st);
+  g_launches += 2;
+  if (G > 1) comm_allgather(c, mine, raw.p, (size_t)nrows * 128);
+  if (d_tail_canon) {
+    DBuf<pt_ext> tpart(c, msm_partials_count(nrows, ntail, kMsmFullWindows));
+    launch_msm_rows(g.d_table.p + tail_col0, g.n_points, 1, d_tail_canon, 8, (size_t)ntail, nrows, ntail, kMsmFullWindows,
+                    1, 0, tpart.p, nullptr, nullptr, raw.p + (size_t)G * nrows * 32, c->st);
+    g_launches += 2;
+  }
+  if (few) {
+    uint32_t xyzt[8 * 32];
+    if (nsrc > 1) {
+      launch_sum_raw_points(raw.p, nsrc, nrows, mine, nullptr, c->st);
+      g_launches += 1;
+      c->d2h(xyzt, mine, (size_t)nrows * 128);
+    } else {
+      c->d2h(xyzt, raw.p, (size_t)nrows * 128);
+    }
+    // a couple of points per Bulletproofs round: invert on the host (3 us vs ~100 us on one GPU thread)
+    for (int i = 0; i < nrows; i++) h64::compress_xyz(xyzt + 32 * i, out.data() + 32 * i);
     return out;
   }
   DBuf<uint32_t> comp(c, (size_t)nrows * 8);
-  launch_msm_rows(g.d_table.p + col0, g.n_points, 1, canon.p, 8, (size_t)ncols, nrows, ncols, nw, part.p, nullptr, comp.p,
-                  nullptr, c->st);
-  g_launches += 3;
+  launch_sum_raw_points(raw.p, nsrc, nrows, nullptr, comp.p, c->st);
+  g_launches += 1;
   c->d2h(out.data(), comp.p, out.size());
   return out;
 }
+// rows of Montgomery Fr scalars (this rank's columns) + optional replicated Montgomery tail scalars
+static std::vector<uint8_t> msm_rows_fr(Ctx* c, const Gens& g, const fr_t* d_scal_mont, int nrows, int ncols_loc,
+                                        const fr_t* d_tail_mont = nullptr, int ntail = 0, size_t tail_col0 = 0) {
+  DBuf<fr_t> canon(c, (size_t)nrows * ncols_loc + (size_t)nrows * ntail);
+  launch_canonicalize(d_scal_mont, canon.p, (size_t)nrows * ncols_loc, c->d_flag, c->st);
+  g_launches += 1;
+  fr_t* tcan = nullptr;
+  if (d_tail_mont) {
+    tcan = canon.p + (size_t)nrows * ncols_loc;
+    launch_canonicalize(d_tail_mont, tcan, (size_t)nrows * ntail, c->d_flag, c->st);
+    g_launches += 1;
+  }
+  return msm_rows(c, g, canon.p, 8, (size_t)ncols_loc, nrows, ncols_loc, kMsmFullWindows, tcan, ntail, tail_col0);
+}
+// replicated tiny MSM on generators [col0, col0 + ncols): every rank computes the same point, no exchange
+static std::vector<uint8_t> msm_replicated_fr(Ctx* c, const Gens& g, const fr_t* d_scal_mont, int ncols, size_t col0) {
+  DBuf<fr_t> canon(c, (size_t)ncols);
+  launch_canonicalize(d_scal_mont, canon.p, (size_t)ncols, c->d_flag, c->st);
+  DBuf<pt_ext> part(c, msm_partials_count(1, ncols, kMsmFullWindows));
+  DBuf<uint32_t> raw(c, 32);
+  launch_msm_rows(g.d_table.p + col0, g.n_points, 1, canon.p, 8, (size_t)ncols, 1, ncols, kMsmFullWindows, 1, 0, part.p,
+                  nullptr, nullptr, raw.p, c->st);
+  g_launches += 3;
+  uint32_t xyzt[32];
+  c->d2h(xyzt, raw.p, 128);
+  std::vector<uint8_t> out(32);
+  h64::compress_xyz(xyzt, out.data());
+  return out;
+}
 
-// DensePolynomial::commit (dense_mlpoly.rs:152-181) for an integer-valued polynomial of 2^nv entries
-static std::vector<uint8_t> commit_u32(Ctx* c, const Gens& g, const uint32_t* d_vals, size_t nv, unsigned max_bits) {
+// DensePolynomial::commit (dense_mlpoly.rs:152-181) for an integer-valued polynomial of 2^nv entries viewed as
+// L x R; this rank holds, for every row, the R/G columns congruent to its rank (= its low-bit shard of the array)
+static std::vector<uint8_t> commit_u32(Ctx* c, const Gens& g, const uint32_t* d_vals_loc, size_t nv, unsigned max_bits) {
   size_t L = (size_t)1 << (nv / 2), R = (size_t)1 << (nv - nv / 2);
   if (R + 2 > g.n_points) throw std::runtime_error("generator stream too short for this polynomial");
-  return msm_rows_u32(c, g, d_vals, R, (int)L, (int)R, max_bits);
+  int nw = msm_windows_for_bits(max_bits);
+  if (nw > 5) throw std::runtime_error("u32 MSM path: scalars wider than 32 bits");
+  size_t R_loc = loc(c, R);
+  return msm_rows(c, g, d_vals_loc, 1, R_loc, (int)L, (int)R_loc, nw, nullptr, 0, 0);
 }
 
 // ---------------------------------------------------------------------------------------------- densify
@@ -169,6 +238,7 @@ Dense* densify(Ctx* c, const uint64_t* indices, size_t n, size_t C, size_t log_m
     *err = 4;
     return nullptr;
   }
+  const size_t G = (size_t)c->world, gr = (size_t)c->rank;
   std::unique_ptr<Dense> d(new Dense());
   d->ctx = c;
   d->C = C;
@@ -177,19 +247,29 @@ Dense* densify(Ctx* c, const uint64_t* indices, size_t n, size_t C, size_t log_m
   d->m = (size_t)1 << log_m;
   d->nv_l = log2_exact_or_ceil(next_pow2(2 * C * d->s));
   d->nv_m = log2_exact_or_ceil(next_pow2(C)) + log_m;
-  const size_t s = d->s, m = d->m, nl = (size_t)1 << d->nv_l, nm = (size_t)1 << d->nv_m;
+  const size_t s = d->s, m = d->m;
+  if (G > 1 && (s < 2 * G || m < 2 * G)) {
+    *err = 4;
+    return nullptr;
+  }
+  d->s_loc = s / G;
+  d->m_loc = m / G;
+  const size_t s_loc = d->s_loc, m_loc = d->m_loc;
+  const size_t nl = ((size_t)1 << d->nv_l) / G, nm = ((size_t)1 << d->nv_m) / G;  // local lengths
   // pinned, reused across calls: no per-call page faults, and the upload runs at full PCIe rate
-  uint32_t* l_host = c->stage(nl + nm);
+  uint32_t* l_host = c->stage(nl + nm + (G > 1 ? (2 * s + m) * C : 0));
   uint32_t* m_host = l_host + nl;
-  if (nl > 2 * C * s) memset(l_host + 2 * C * s, 0, (nl - 2 * C * s) * sizeof(uint32_t));
-  memset(m_host, 0, nm * sizeof(uint32_t));
+  uint32_t* full = m_host + nm;  // G > 1: whole-sequence scratch (every rank runs the full scan, keeps its shard)
+  if (nl > 2 * C * s_loc) memset(l_host + 2 * C * s_loc, 0, (nl - 2 * C * s_loc) * sizeof(uint32_t));
+  if (nm > C * m_loc) memset(m_host + C * m_loc, 0, (nm - C * m_loc) * sizeof(uint32_t));
   // densified.rs:33-56: per dimension, pad with address 0 and run the (inherently sequential) timestamp
   // counters; dimensions are independent, so one host thread each.
   std::vector<int> bad(C, 0);
   auto work = [&](size_t i) {
-    uint32_t* dim = l_host + i * s;
-    uint32_t* rd = l_host + (C + i) * s;
-    uint32_t* fin = m_host + i * m;
+    uint32_t* dim = G == 1 ? l_host + i * s : full + i * (2 * s + m);
+    uint32_t* rd = G == 1 ? l_host + (C + i) * s : dim + s;
+    uint32_t* fin = G == 1 ? m_host + i * m : dim + 2 * s;
+    memset(fin, 0, m * sizeof(uint32_t));
     for (size_t k = 0; k < s; k++) {
       uint64_t addr = k < n ? indices[k * C + i] : 0;
       if (addr >= m) {
@@ -200,6 +280,16 @@ Dense* densify(Ctx* c, const uint64_t* indices, size_t n, size_t C, size_t log_m
       uint32_t ts = fin[addr];
       rd[k] = ts;
       fin[addr] = ts + 1;
+    }
+    if (G > 1) {  // keep the low-bit shard
+      uint32_t* ld = l_host + i * s_loc;
+      uint32_t* lr = l_host + (C + i) * s_loc;
+      uint32_t* lf = m_host + i * m_loc;
+      for (size_t k = 0; k < s_loc; k++) {
+        ld[k] = dim[k * G + gr];
+        lr[k] = rd[k * G + gr];
+      }
+      for (size_t k = 0; k < m_loc; k++) lf[k] = fin[k * G + gr];
     }
   };
   {
@@ -310,19 +400,36 @@ static void ser_sumcheck(ByteWriter& w, const SumcheckProof& p) {
 }
 
 // ---------------------------------------------------------------------------------------------- sumcheck
-// sumcheck.rs:149-260 over device polynomials W_k = base + k*stride (k <= alpha, the last is eq)
-static SumcheckProof prove_arbitrary(Ctx* c, const Strategy& S, fr_t* base, size_t stride, size_t len,
+// sumcheck.rs:149-260 over device polynomials W_k = base + k*stride (k <= alpha, the last is eq); `len_loc` is
+// this rank's length.  Sharded rounds: local eval -> sum over ranks -> host; local bind.  When one element
+// per rank is left the G-element remainders are all-gathered and the last log2(G) rounds run replicated.
+static SumcheckProof prove_arbitrary(Ctx* c, const Strategy& S, fr_t* base, size_t stride, size_t len_loc,
                                      Transcript& transcript, std::vector<fr_t>& r) {
   SpanTimer sp(c, "Sumcheck.prove");
   SumcheckProof proof;
   r.clear();
   const int npts = S.sumcheck_poly_degree() + 1, npolys = S.num_memories() + 1;
   std::vector<fr_t> evals(npts);
-  while (len > 1) {
+  DBuf<fr_t> tail;
+  bool sharded = c->world > 1;
+  size_t len = len_loc;
+  for (;;) {
+    if (sharded && len == 1) {  // hand over to the replicated tail
+      tail.alloc(c, (size_t)npolys * c->world);
+      comm_gather_heads(c, nullptr, base, stride, npolys, tail.p);
+      base = tail.p;
+      stride = (size_t)c->world;
+      len = (size_t)c->world;
+      sharded = false;
+    }
+    if (len <= 1) break;
     size_t half = len / 2;
     launch_sumcheck_eval_arbitrary(S, base, stride, half, c->d_partial, c->d_small, c->st);
     g_launches += 2;
-    c->d2h(evals.data(), c->d_small, (size_t)npts * sizeof(fr_t));
+    if (sharded)
+      reduce_to_host(c, c->d_small, npts, evals.data());
+    else
+      c->d2h(evals.data(), c->d_small, (size_t)npts * sizeof(fr_t));
     std::vector<fr_t> coeffs = unipoly_from_evals(evals);
     unipoly_append(coeffs, transcript);
     fr_t r_j = transcript.challenge_scalar("challenge_nextround");
@@ -338,24 +445,55 @@ static SumcheckProof prove_arbitrary(Ctx* c, const Strategy& S, fr_t* base, size
 // ---------------------------------------------------------------------------------------------- grand products
 // GrandProductCircuit (grand_product.rs:14-66): layer k is one contiguous array of N/2^k elements,
 // left_vec[k] = first half, right_vec[k] = second half; layer k+1[i] = layer k[i] * layer k[i + N/2^(k+1)].
+// Sharded: layers with N/2^k >= G are held as low-bit shards (local length N/(2^k G)); the layer of global
+// length G is all-gathered and the few layers above it are kept replicated on every rank.
 struct Circuit {
-  DBuf<fr_t> tree;  // 2N elements: layer 0 at 0, layer 1 at N, layer 2 at N + N/2, ...
+  DBuf<fr_t> tree;   // local shards: layer 0 at 0 (N/G elements), layer 1 after it, ...
+  DBuf<fr_t> rtree;  // replicated top: layer k_rep (G elements), k_rep + 1, ...   (empty when G == 1)
   size_t N = 0, num_layers = 0;
-  fr_t* layer(size_t k) const {
-    size_t off = 0, len = N;
+  int G = 1;
+  size_t k_rep = 0;  // first replicated layer: N >> k_rep == G
+  bool layer_is_sharded(size_t k) const { return G == 1 || (N >> k) >= 2 * (size_t)G; }
+  size_t layer_len_global(size_t k) const { return N >> k; }
+  fr_t* layer_local(size_t k) const {  // valid for (N >> k) >= G
+    size_t off = 0, len = N / G;
     for (size_t i = 0; i < k; i++) {
       off += len;
       len /= 2;
     }
     return tree.p + off;
   }
-  size_t layer_len(size_t k) const { return N >> k; }
+  fr_t* layer_rep(size_t k) const {  // valid for k >= k_rep (G > 1)
+    size_t off = 0, len = (size_t)G;
+    for (size_t i = k_rep; i < k; i++) {
+      off += len;
+      len /= 2;
+    }
+    return rtree.p + off;
+  }
 };
+static void circuit_alloc(Ctx* c, Circuit& ci, size_t N) {
+  ci.N = N;
+  ci.G = c->world;
+  ci.num_layers = log2_exact_or_ceil(N);
+  ci.tree.alloc(c, 2 * (N / ci.G));
+  if (ci.G > 1) {
+    ci.k_rep = ci.num_layers - (size_t)c->lg_world;
+    ci.rtree.alloc(c, 2 * (size_t)ci.G);
+  }
+}
 static void build_tree(Ctx* c, Circuit& ci) {  // grand_product.rs:38-58 (layer 0 already filled)
-  ci.num_layers = log2_exact_or_ceil(ci.N);
-  for (size_t k = 0; k + 1 < ci.num_layers; k++) {
-    launch_product_layer(ci.layer(k), ci.layer(k + 1), ci.layer_len(k + 1), c->st);
+  const size_t last_local = ci.G == 1 ? ci.num_layers - 1 : ci.k_rep;
+  for (size_t k = 0; k < last_local; k++) {
+    launch_product_layer(ci.layer_local(k), ci.layer_local(k + 1), ci.layer_len_global(k + 1) / ci.G, c->st);
     g_launches += 1;
+  }
+  if (ci.G > 1) {
+    comm_gather_heads(c, nullptr, ci.layer_local(ci.k_rep), 0, 1, ci.layer_rep(ci.k_rep));
+    for (size_t k = ci.k_rep; k + 1 < ci.num_layers; k++) {
+      launch_product_layer(ci.layer_rep(k), ci.layer_rep(k + 1), ci.layer_len_global(k + 1), c->st);
+      g_launches += 1;
+    }
   }
 }
 
@@ -370,42 +508,74 @@ static GPAProof prove_gpa(Ctx* c, std::vector<Circuit*>& circuits, std::vector<f
                           Transcript& transcript, std::vector<fr_t>& rand_out) {
   SpanTimer sp(c, "BatchedGrandProductArgument.prove");
   GPAProof out;
-  const int ncirc = (int)circuits.size();
+  const int ncirc = (int)circuits.size(), G = c->world;
   const size_t num_layers = circuits[0]->num_layers;
   DBuf<fr_t*> d_A(c, ncirc), d_B(c, ncirc), d_AB(c, 2 * ncirc);
-  DBuf<fr_t> eqbuf(c, std::max<size_t>(circuits[0]->N / 2, 1)), eqbuf2(c, std::max<size_t>(circuits[0]->N / 4, 1));
+  const size_t eq_cap = std::max<size_t>(circuits[0]->N / 2 / G, (size_t)G);
+  DBuf<fr_t> eqbuf(c, eq_cap), eqbuf2(c, std::max<size_t>(eq_cap / 2, 1));
+  DBuf<fr_t> tail(c, (size_t)(2 * ncirc + 1) * G);  // replicated remainders of A_k, B_k, C (G elements each)
   std::vector<fr_t*> hA(ncirc), hB(ncirc), hAB(2 * ncirc);
   std::vector<fr_t> rand;
   std::vector<fr_t> ev((size_t)ncirc * 3), fin((size_t)2 * ncirc);
-  for (size_t layer_id = num_layers; layer_id-- > 0;) {
-    const size_t len = circuits[0]->layer_len(layer_id);
-    size_t half_len = len / 2;  // |A| = |B| = |C|
+  auto upload_ptrs = [&]() {
     for (int k = 0; k < ncirc; k++) {
-      hA[k] = circuits[k]->layer(layer_id);
-      hB[k] = hA[k] + half_len;
       hAB[2 * k] = hA[k];
       hAB[2 * k + 1] = hB[k];
     }
     LB_CUDA_CHECK(cudaMemcpyAsync(d_A.p, hA.data(), ncirc * sizeof(fr_t*), cudaMemcpyHostToDevice, c->st));
     LB_CUDA_CHECK(cudaMemcpyAsync(d_B.p, hB.data(), ncirc * sizeof(fr_t*), cudaMemcpyHostToDevice, c->st));
     LB_CUDA_CHECK(cudaMemcpyAsync(d_AB.p, hAB.data(), 2 * ncirc * sizeof(fr_t*), cudaMemcpyHostToDevice, c->st));
-    c->sync();  // the host arrays are reused next layer
-    eq_evals_dev(c, rand, 0, rand.size(), eqbuf.p);  // poly_C = eq(rand), grand_product.rs:122
+    c->sync();  // the host arrays are rewritten afterwards
+  };
+  for (size_t layer_id = num_layers; layer_id-- > 0;) {
+    const size_t len_g = circuits[0]->layer_len_global(layer_id);
+    bool sharded = G > 1 && circuits[0]->layer_is_sharded(layer_id);
+    const bool replicated_layer = G > 1 && !sharded;
+    // |A| = |B| = |C| = len/2 globally; per rank len/(2G) when sharded
+    size_t cur = replicated_layer ? len_g / 2 : len_g / 2 / (size_t)G;
+    for (int k = 0; k < ncirc; k++) {
+      hA[k] = replicated_layer ? circuits[k]->layer_rep(layer_id) : circuits[k]->layer_local(layer_id);
+      hB[k] = hA[k] + cur;
+    }
+    upload_ptrs();
+    // poly_C = eq(rand), grand_product.rs:122
+    if (sharded)
+      eq_evals_shard(c, rand, 0, rand.size(), eqbuf.p);
+    else
+      eq_evals_dev(c, rand, 0, rand.size(), eqbuf.p);
     std::vector<fr_t> coeff_vec = transcript.challenge_vector("rand_coeffs_next_layer", ncirc);
     fr_t e = fr_zero();
     for (int k = 0; k < ncirc; k++) e = fr_add(e, fr_mul(claims_to_verify[k], coeff_vec[k]));
     LayerProof lp;
     std::vector<fr_t> rand_prod;
-    size_t cur = half_len;  // current length of A_k / B_k / C
     fr_t* Ccur = eqbuf.p;
     fr_t* Cnext = eqbuf2.p;
-    if (cur > 1) {  // round 0 evaluation; later rounds come out of the fused bind+eval kernel
-      launch_sumcheck_eval_cubic(d_A.p, d_B.p, Ccur, ncirc, cur / 2, c->d_partial, c->d_small, c->st);
-      g_launches += 2;
-    }
-    while (cur > 1) {
+    bool have_evals = false;
+    for (;;) {
+      if (sharded && cur == 1) {  // all-gather the G-element remainders; the tail rounds run replicated
+        comm_gather_heads(c, d_AB.p, nullptr, 0, 2 * ncirc, tail.p);
+        comm_gather_heads(c, nullptr, Ccur, 0, 1, tail.p + (size_t)2 * ncirc * G);
+        for (int k = 0; k < ncirc; k++) {
+          hA[k] = tail.p + (size_t)(2 * k) * G;
+          hB[k] = tail.p + (size_t)(2 * k + 1) * G;
+        }
+        upload_ptrs();
+        Ccur = tail.p + (size_t)2 * ncirc * G;
+        Cnext = eqbuf2.p;
+        cur = (size_t)G;
+        sharded = false;
+        have_evals = false;
+      }
+      if (cur <= 1) break;
+      if (!have_evals) {  // first round of a phase; later rounds come out of the fused bind+eval kernel
+        launch_sumcheck_eval_cubic(d_A.p, d_B.p, Ccur, ncirc, cur / 2, c->d_partial, c->d_small, c->st);
+        g_launches += 2;
+      }
       size_t half = cur / 2;
-      c->d2h(ev.data(), c->d_small, ev.size() * sizeof(fr_t));
+      if (sharded)
+        reduce_to_host(c, c->d_small, 3 * ncirc, ev.data());
+      else
+        c->d2h(ev.data(), c->d_small, ev.size() * sizeof(fr_t));
       fr_t c0 = fr_zero(), c2 = fr_zero(), c3 = fr_zero();
       for (int k = 0; k < ncirc; k++) {  // sumcheck.rs:95-97
         c0 = fr_add(c0, fr_mul(ev[3 * k], coeff_vec[k]));
@@ -422,9 +592,12 @@ static GPAProof prove_gpa(Ctx* c, std::vector<Circuit*>& circuits, std::vector<f
         g_launches += launch_sumcheck_bind_eval_cubic(d_A.p, d_B.p, Ccur, Cnext, ncirc, half, r_j, c->d_partial,
                                                       c->d_small, c->st);
         std::swap(Ccur, Cnext);
+        have_evals = true;
       } else {
         launch_bind_top_ptrs(d_AB.p, 2 * ncirc, half, r_j, c->st);
-        g_launches += 1;
+        launch_bind_top(Ccur, 0, 1, half, r_j, c->st);
+        g_launches += 2;
+        have_evals = false;
       }
       e = unipoly_evaluate(coeffs, r_j);
       lp.proof.push_back(unipoly_compress(coeffs));
@@ -481,12 +654,13 @@ static void ser_dpl(ByteWriter& w, const DotProductProofLogBytes& p) {
   w.fr(p.z2);
 }
 
-__global__ void set_tail_kernel(fr_t* sL, fr_t* sR, size_t n, const fr_t* ip, fr_t blind_L, fr_t blind_R) {
+// dst (nrows x 2, row-major) <- [ip[0], blind_L ; ip[1], blind_R]
+__global__ void set_tail_kernel(fr_t* dst0, fr_t* dst1, const fr_t* ip, fr_t blind_L, fr_t blind_R) {
   if (threadIdx.x || blockIdx.x) return;
-  sL[n] = ip[0];      // c_L on Q
-  sL[n + 1] = blind_L;  // on H
-  sR[n] = ip[1];
-  sR[n + 1] = blind_R;
+  dst0[0] = ip[0];  // c_L on Q
+  dst0[1] = blind_L;  // on H
+  dst1[0] = ip[1];
+  dst1[1] = blind_R;
 }
 __global__ void set_elems_kernel(fr_t* dst, fr_t a, fr_t b) {
   if (threadIdx.x || blockIdx.x) return;
@@ -495,23 +669,26 @@ __global__ void set_elems_kernel(fr_t* dst, fr_t a, fr_t b) {
 }
 
 // PolyEvalProof::prove (dense_mlpoly.rs:301-359) -> DotProductProofLog::prove (dot_product.rs:166-249)
-// -> BulletReductionProof::prove (bullet.rs:40-154).  Z: device polynomial of 2^nv elements.
+// -> BulletReductionProof::prove (bullet.rs:40-154).  Z: this rank's shard of a polynomial of 2^nv elements,
+// i.e. for every one of the L rows the R/G columns congruent to the rank.
 static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t* Z, size_t nv,
                                                const std::vector<fr_t>& r, const fr_t& Zr, Transcript& transcript,
                                                RandomTape& tape) {
   SpanTimer sp(c, "DensePolyEval.prove");
   transcript.append_protocol_name("polynomial evaluation proof");
   if (r.size() != nv) throw std::runtime_error("PolyEvalProof: r.len() != num_vars");
+  const int G = c->world, gr = c->rank;
   const size_t lv = nv / 2, rv = nv - nv / 2, L_size = (size_t)1 << lv, n = (size_t)1 << rv;  // n = R_size
   if (n + 2 > g.n_points) throw std::runtime_error("generator stream too short");
-  const size_t lg_n = rv;
+  if (n < 2 * (size_t)G) throw std::runtime_error("opening narrower than 2 x #GPUs");
+  const size_t lg_n = rv, n_loc = n / G;
   // L, R = factored eq evals (eq_poly.rs:44-52); LZ = L . Z (dense_mlpoly.rs:183-207)
   std::unique_ptr<SpanTimer> sp1(new SpanTimer(c, "PE.1 eq+bound"));
-  DBuf<fr_t> Lvec(c, L_size), a(c, n), b(c, n);
-  eq_evals_dev(c, r, 0, lv, Lvec.p);
-  eq_evals_dev(c, r, lv, rv, b.p);  // a_vec of the dot product proof = R
-  if ((size_t)bound_max_chunks() * n > c->partial_elems) throw std::runtime_error("bound scratch too small");
-  launch_bound(Z, Lvec.p, L_size, n, c->d_partial, a.p, c->st);  // x_vec = LZ
+  DBuf<fr_t> Lvec(c, L_size), a(c, n_loc), b(c, n_loc), arep(c, 2 * (size_t)G);
+  eq_evals_dev(c, r, 0, lv, Lvec.p);          // rows are not sharded: L is replicated
+  eq_evals_shard(c, r, lv, rv, b.p);          // a_vec of the dot product proof = R (this rank's columns)
+  if ((size_t)bound_max_chunks() * n_loc > c->partial_elems) throw std::runtime_error("bound scratch too small");
+  launch_bound(Z, Lvec.p, L_size, n_loc, c->d_partial, a.p, c->st);  // x_vec = LZ
   g_launches += 2;
 
   // ---- DotProductProofLog::prove
@@ -524,44 +701,74 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
   std::vector<fr_t> v2 = tape.random_vector("blinds_vec_2", 2 * lg_n);
   DotProductProofLogBytes out;
   // Cx = batch_commit(x_vec, blind_x = 0) ; Cy = y*Q + 0*h
-  std::vector<uint8_t> Cx = msm_rows_fr(c, g, a.p, 1, (int)n, 0);
+  std::vector<uint8_t> Cx = msm_rows_fr(c, g, a.p, 1, (int)n_loc);
   transcript.append_point_compressed("Cx", Cx.data());
-  DBuf<fr_t> two(c, 2);
+  DBuf<fr_t> two(c, 4);
   set_elems_kernel<<<1, 32, 0, c->st>>>(two.p, Zr, fr_zero());
   g_launches += 1;
-  std::vector<uint8_t> Cy = msm_rows_fr(c, g, two.p, 1, 2, n);
+  std::vector<uint8_t> Cy = msm_replicated_fr(c, g, two.p, 2, n);
   transcript.append_point_compressed("Cy", Cy.data());
-  {  // append_scalars(b"a", a_vec): canonical bytes straight from the device
-    DBuf<fr_t> canon(c, n);
-    launch_canonicalize(b.p, canon.p, n, c->d_flag, c->st);
+  {  // append_scalars(b"a", a_vec): canonical bytes straight from the device (all ranks need the whole vector)
+    DBuf<fr_t> canon(c, n_loc), all(c, G > 1 ? n : 0);
+    launch_canonicalize(b.p, canon.p, n_loc, c->d_flag, c->st);
     g_launches += 1;
     std::vector<uint8_t> bytes(n * 32);
-    c->d2h(bytes.data(), canon.p, bytes.size());
+    if (G == 1) {
+      c->d2h(bytes.data(), canon.p, bytes.size());
+    } else {
+      comm_allgather(c, canon.p, all.p, n_loc * 32);
+      std::vector<uint8_t> tmp(n * 32);
+      c->d2h(tmp.data(), all.p, tmp.size());
+      for (int q = 0; q < G; q++)  // rank q's local column j' is global column j'*G + q
+        for (size_t j = 0; j < n_loc; j++) memcpy(&bytes[(j * G + q) * 32], &tmp[((size_t)q * n_loc + j) * 32], 32);
+    }
     transcript.append_scalars_bytes("a", bytes.data(), n);
   }
   // ---- BulletReductionProof::prove with unfolded generators (see file header)
   sp1.reset(new SpanTimer(c, "PE.3 bullet rounds"));
   fr_t blind_fin = fr_zero();  // blind_Gamma = blind_x + blind_y = 0
-  DBuf<fr_t> W0(c, n), W1(c, n), sLR(c, 2 * (n + 2));
-  fr_t* W = W0.p;
+  const size_t ncols_main = G == 1 ? n + 2 : n_loc;  // single GPU: Q and h ride along as columns n, n+1
+  DBuf<fr_t> W0(c, n), W1(c, n), sLR(c, 2 * ncols_main), tailsc(c, 4);
+  fr_t* W = W0.p;   // weights of the unfolded generators: replicated (indexed by the HIGH column bits)
   fr_t* Wn = W1.p;
   set_elems_kernel<<<1, 32, 0, c->st>>>(W, fr_one(), fr_zero());
   g_launches += 1;
   fr_t* sL = sLR.p;
-  fr_t* sR = sLR.p + (n + 2);
-  size_t m = n, nw_count = 1;  // current vector length, number of weights
+  fr_t* sR = sLR.p + ncols_main;
+  fr_t* av = a.p;  // current a / b vectors: sharded while m >= 2G, replicated afterwards
+  fr_t* bv = b.p;
+  bool sharded = G > 1;
+  size_t m = n, nw_count = 1;  // current (global) vector length, number of weights
   for (size_t round = 0; m != 1; round++) {
-    size_t h = m / 2;
-    launch_cross_inner_products(a.p, b.p, h, c->d_partial, c->d_small, c->st);  // c_L, c_R (bullet.rs:78-79)
-    launch_bullet_scalars(a.p, W, n, m, sL, sR, c->st);
-    set_tail_kernel<<<1, 32, 0, c->st>>>(sL, sR, n, c->d_small, v1[round], v2[round]);
-    g_launches += 4;
-    std::vector<uint8_t> LR = msm_rows_fr(c, g, sLR.p, 2, (int)(n + 2), 0);
+    if (sharded && m == (size_t)G) {  // one element per rank left: gather, finish replicated
+      comm_gather_heads(c, nullptr, av, 0, 1, arep.p);
+      comm_gather_heads(c, nullptr, bv, 0, 1, arep.p + G);
+      av = arep.p;
+      bv = arep.p + G;
+      sharded = false;
+    }
+    const size_t h = m / 2;
+    const size_t h_arr = sharded ? h / G : h;  // half length of the arrays this rank holds
+    launch_cross_inner_products(av, bv, h_arr, c->d_partial, c->d_small, c->st);  // c_L, c_R (bullet.rs:78-79)
+    g_launches += 2;
+    if (sharded) comm_allreduce_fr(c, c->d_small, 2);
+    launch_bullet_scalars(av, W, n_loc, m, G, gr, (G > 1 && !sharded) ? 1 : 0, sL, sR, c->st);
+    g_launches += 1;
+    std::vector<uint8_t> LR;
+    if (G == 1) {
+      set_tail_kernel<<<1, 32, 0, c->st>>>(sL + n, sR + n, c->d_small, v1[round], v2[round]);
+      g_launches += 1;
+      LR = msm_rows_fr(c, g, sLR.p, 2, (int)(n + 2));
+    } else {
+      set_tail_kernel<<<1, 32, 0, c->st>>>(tailsc.p, tailsc.p + 2, c->d_small, v1[round], v2[round]);
+      g_launches += 1;
+      LR = msm_rows_fr(c, g, sLR.p, 2, (int)n_loc, tailsc.p, 2, n);
+    }
     transcript.append_point_compressed("L", LR.data());
     transcript.append_point_compressed("R", LR.data() + 32);
     fr_t u = transcript.challenge_scalar("u");
     fr_t u_inv = fr_inv(u);
-    launch_fold_ab(a.p, b.p, h, u, u_inv, c->st);  // bullet.rs:127-130 (scalars only; G stays unfolded)
+    launch_fold_ab(av, bv, h_arr, u, u_inv, c->st);  // bullet.rs:127-130 (scalars only; G stays unfolded)
     launch_expand_weights(W, Wn, nw_count, u, u_inv, c->st);
     g_launches += 2;
     std::swap(W, Wn);
@@ -573,23 +780,31 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
   }
   sp1.reset(new SpanTimer(c, "PE.4 delta,beta"));
   fr_t ab[2];
-  LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin, a.p, 32, cudaMemcpyDeviceToHost, c->st));
-  LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin + 32, b.p, 32, cudaMemcpyDeviceToHost, c->st));
+  LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin, av, 32, cudaMemcpyDeviceToHost, c->st));
+  LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin + 32, bv, 32, cudaMemcpyDeviceToHost, c->st));
   c->sync();
   memcpy(ab, c->h_pin, 64);
   fr_t x_hat = ab[0], a_hat = ab[1], rhat_Gamma = blind_fin;
   fr_t y_hat = fr_mul(x_hat, a_hat);
   // delta = d * g_hat + r_delta * h with g_hat = sum_j W[j] G_j  (dot_product.rs:219-227)
-  launch_scale(W, sL, n, d, c->st);
-  set_elems_kernel<<<1, 32, 0, c->st>>>(sL + n, fr_zero(), r_delta);
-  g_launches += 2;
-  std::vector<uint8_t> delta = msm_rows_fr(c, g, sL, 1, (int)(n + 2), 0);
+  std::vector<uint8_t> delta;
+  if (G == 1) {
+    launch_scale(W, sL, n, d, c->st);
+    set_elems_kernel<<<1, 32, 0, c->st>>>(sL + n, fr_zero(), r_delta);
+    g_launches += 2;
+    delta = msm_rows_fr(c, g, sL, 1, (int)(n + 2));
+  } else {
+    launch_scale_strided(W, sL, n_loc, (size_t)G, (size_t)gr, d, c->st);
+    set_elems_kernel<<<1, 32, 0, c->st>>>(tailsc.p, fr_zero(), r_delta);
+    g_launches += 2;
+    delta = msm_rows_fr(c, g, sL, 1, (int)n_loc, tailsc.p, 2, n);
+  }
   memcpy(out.delta, delta.data(), 32);
   transcript.append_point_compressed("delta", out.delta);
   // beta = d * Q + r_beta * h  (dot_product.rs:229-230)
   set_elems_kernel<<<1, 32, 0, c->st>>>(two.p, d, r_beta);
   g_launches += 1;
-  std::vector<uint8_t> beta = msm_rows_fr(c, g, two.p, 1, 2, n);
+  std::vector<uint8_t> beta = msm_replicated_fr(c, g, two.p, 2, n);
   memcpy(out.beta, beta.data(), 32);
   transcript.append_point_compressed("beta", out.beta);
   fr_t cc = transcript.challenge_scalar("c");
@@ -631,28 +846,30 @@ std::vector<uint8_t> prove(Ctx* c, const Strategy& S, Dense& dense, const std::v
   Transcript transcript(transcript_label);
   transcript.trace = challenges;
   RandomTape tape(tape_label, tape_seed);
+  const int G = c->world, gr = c->rank;
   const size_t s = dense.s, C = dense.C, M = dense.m, alpha = (size_t)S.num_memories();
+  const size_t s_loc = dense.s_loc, M_loc = dense.m_loc;
   const size_t log_s = log2_exact_or_ceil(s);
   if ((size_t)S.C != C || (size_t)S.log_m != dense.log_m) throw std::runtime_error("strategy does not match the densified representation");
   if (g.nv_d != log2_exact_or_ceil(next_pow2(alpha * s)) || g.nv_l != dense.nv_l || g.nv_m != dense.nv_m)
     throw std::runtime_error("generators were built for different (c, s, num_memories, log_m)");
   transcript.append_protocol_name("Lasso SparsePolynomialEvaluationProof");
 
-  // ---- Subtables::new (subtables/mod.rs:116-129): materialise, gather, merge
-  const size_t nv_d = g.nv_d, nd = (size_t)1 << nv_d;
+  // ---- Subtables::new (subtables/mod.rs:116-129): materialise (replicated, 2-6 MiB), gather, merge
+  const size_t nv_d = g.nv_d, nd_loc = ((size_t)1 << nv_d) / G;
   const int nsub = S.num_subtables();
   DBuf<fr_t> tables_fr(c, (size_t)nsub * M);
   DBuf<uint32_t> tables_u32(c, (size_t)nsub * M);
-  DBuf<fr_t> E(c, nd);          // combined_poly = E_0 | .. | E_{alpha-1} | 0-pad
-  DBuf<uint32_t> E_u32(c, nd);  // same values as integers for the small-scalar commit
+  DBuf<fr_t> E(c, nd_loc);          // combined_poly = E_0 | .. | E_{alpha-1} | 0-pad (this rank's shard)
+  DBuf<uint32_t> E_u32(c, nd_loc);  // same values as integers for the small-scalar commit
   {
     SpanTimer sp(c, "Subtables.new");
     launch_materialize_subtables(S, tables_fr.p, tables_u32.p, c->st);
-    launch_gather_lookup_polys(S, tables_fr.p, tables_u32.p, dense.nz(), s, E.p, s, E_u32.p, c->st);
+    launch_gather_lookup_polys(S, tables_fr.p, tables_u32.p, dense.nz(), s_loc, E.p, s_loc, E_u32.p, c->st);
     g_launches += 2;
-    if (nd > alpha * s) {
-      launch_fill_zero(E.p + alpha * s, nd - alpha * s, c->st);
-      LB_CUDA_CHECK(cudaMemsetAsync(E_u32.p + alpha * s, 0, (nd - alpha * s) * 4, c->st));
+    if (nd_loc > alpha * s_loc) {
+      launch_fill_zero(E.p + alpha * s_loc, nd_loc - alpha * s_loc, c->st);
+      LB_CUDA_CHECK(cudaMemsetAsync(E_u32.p + alpha * s_loc, 0, (nd_loc - alpha * s_loc) * 4, c->st));
     }
   }
   ByteWriter w;
@@ -671,27 +888,27 @@ std::vector<uint8_t> prove(Ctx* c, const Strategy& S, Dense& dense, const std::v
   // ---- primary sumcheck (surge.rs:142-172)
   std::vector<fr_t> r_z;
   {
-    DBuf<fr_t> Wk(c, (alpha + 1) * s);  // clones of E_i + eq(r): the sumcheck binds them in place
-    LB_CUDA_CHECK(cudaMemcpyAsync(Wk.p, E.p, alpha * s * sizeof(fr_t), cudaMemcpyDeviceToDevice, c->st));
-    eq_evals_dev(c, r, 0, log_s, Wk.p + alpha * s);
-    launch_sumcheck_claim(S, Wk.p, s, s, c->d_partial, c->d_small, c->st);  // subtables/mod.rs:186-216
+    DBuf<fr_t> Wk(c, (alpha + 1) * s_loc);  // clones of E_i + eq(r): the sumcheck binds them in place
+    LB_CUDA_CHECK(cudaMemcpyAsync(Wk.p, E.p, alpha * s_loc * sizeof(fr_t), cudaMemcpyDeviceToDevice, c->st));
+    eq_evals_shard(c, r, 0, log_s, Wk.p + alpha * s_loc);
+    launch_sumcheck_claim(S, Wk.p, s_loc, s_loc, c->d_partial, c->d_small, c->st);  // subtables/mod.rs:186-216
     g_launches += 2;
     fr_t claimed_eval;
-    c->d2h(&claimed_eval, c->d_small, sizeof(fr_t));
+    reduce_to_host(c, c->d_small, 1, &claimed_eval);
     transcript.append_scalar("claim_eval_scalar_product", claimed_eval);
-    SumcheckProof primary = prove_arbitrary(c, S, Wk.p, s, s, transcript, r_z);
+    SumcheckProof primary = prove_arbitrary(c, S, Wk.p, s_loc, s_loc, transcript, r_z);
     ser_sumcheck(w, primary);
     w.fr(claimed_eval);
   }
   // ---- eval_derefs = E_i(r_z) (surge.rs:175-176) and the combined opening (177-184)
-  DBuf<fr_t> eqtab(c, std::max(s, M));
+  DBuf<fr_t> eqtab(c, std::max(s_loc, M_loc));
   std::vector<fr_t> eval_derefs(alpha);
   {
     SpanTimer sp(c, "CombinedEval.prove");
-    eq_evals_dev(c, r_z, 0, log_s, eqtab.p);
-    launch_multi_dot(E.p, s, (int)alpha, eqtab.p, s, c->d_partial, c->d_small, c->st);
+    eq_evals_shard(c, r_z, 0, log_s, eqtab.p);
+    launch_multi_dot(E.p, s_loc, (int)alpha, eqtab.p, s_loc, c->d_partial, c->d_small, c->st);
     g_launches += 2;
-    c->d2h(eval_derefs.data(), c->d_small, alpha * sizeof(fr_t));
+    reduce_to_host(c, c->d_small, (int)alpha, eval_derefs.data());
     w.arr_fr(eval_derefs);
     transcript.append_protocol_name("Lasso CombinedTableEvalProof");
     ser_dpl(w, prove_joint(c, g, E.p, nv_d, eval_derefs, true, "evals_ops_val", "challenge_combine_n_to_one",
@@ -710,16 +927,16 @@ std::vector<uint8_t> prove(Ctx* c, const Strategy& S, Dense& dense, const std::v
       size_t j = (size_t)S.memory_to_dimension_index((int)i), k = (size_t)S.memory_to_subtable_index((int)i);
       for (auto* pc : {&init[i], &fin[i]}) {
         pc->reset(new Circuit());
-        (*pc)->N = M;
-        (*pc)->tree.alloc(c, 2 * M);
+        circuit_alloc(c, **pc, M);
       }
       for (auto* pc : {&rd[i], &wr[i]}) {
         pc->reset(new Circuit());
-        (*pc)->N = s;
-        (*pc)->tree.alloc(c, 2 * s);
+        circuit_alloc(c, **pc, s);
       }
-      launch_gp_fingerprints_mem(tables_fr.p + k * M, dense.fin(j), M, gamma, tau, init[i]->tree.p, fin[i]->tree.p, c->st);
-      launch_gp_fingerprints_ops(dense.dim(j), E.p + i * s, dense.read(j), s, gamma, tau, rd[i]->tree.p, wr[i]->tree.p, c->st);
+      launch_gp_fingerprints_mem(tables_fr.p + k * M, dense.fin(j), M_loc, G, gr, gamma, tau, init[i]->tree.p,
+                                 fin[i]->tree.p, c->st);
+      launch_gp_fingerprints_ops(dense.dim(j), E.p + i * s_loc, dense.read(j), s_loc, gamma, tau, rd[i]->tree.p,
+                                 wr[i]->tree.p, c->st);
       g_launches += 2;
       build_tree(c, *init[i]);
       build_tree(c, *fin[i]);
@@ -728,9 +945,9 @@ std::vector<uint8_t> prove(Ctx* c, const Strategy& S, Dense& dense, const std::v
     }
     // ProductLayerProof::prove (memory_checking.rs:673-731)
     transcript.append_protocol_name("Lasso ProductLayerProof");
-    auto evaluate = [&](Circuit& ci) {  // grand_product.rs:60-65
+    auto evaluate = [&](Circuit& ci) {  // grand_product.rs:60-65 (the top layer is replicated when G > 1)
       fr_t top[2];
-      c->d2h(top, ci.layer(ci.num_layers - 1), 64);
+      c->d2h(top, G == 1 ? ci.layer_local(ci.num_layers - 1) : ci.layer_rep(ci.num_layers - 1), 64);
       return fr_mul(top[0], top[1]);
     };
     std::vector<fr_t> claims_rw, claims_if;
@@ -767,13 +984,13 @@ std::vector<uint8_t> prove(Ctx* c, const Strategy& S, Dense& dense, const std::v
     SpanTimer sp(c, "HashLayer.prove");
     transcript.append_protocol_name("Lasso HashLayerProof");
     std::vector<fr_t> eval_derefs2(alpha), eval_dim(C), eval_read(C), eval_final(C);
-    eq_evals_dev(c, rand_ops, 0, rand_ops.size(), eqtab.p);
-    launch_multi_dot(E.p, s, (int)alpha, eqtab.p, s, c->d_partial, c->d_small, c->st);
-    launch_multi_dot(dense.d_l_fr.p, s, (int)(2 * C), eqtab.p, s, c->d_partial + 65536, c->d_small + 64, c->st);
+    eq_evals_shard(c, rand_ops, 0, rand_ops.size(), eqtab.p);
+    launch_multi_dot(E.p, s_loc, (int)alpha, eqtab.p, s_loc, c->d_partial, c->d_small, c->st);
+    launch_multi_dot(dense.d_l_fr.p, s_loc, (int)(2 * C), eqtab.p, s_loc, c->d_partial + 65536, c->d_small + 64, c->st);
     g_launches += 4;
     {
       std::vector<fr_t> tmp(64 + 2 * C);
-      c->d2h(tmp.data(), c->d_small, tmp.size() * sizeof(fr_t));
+      reduce_to_host(c, c->d_small, (int)tmp.size(), tmp.data());
       for (size_t i = 0; i < alpha; i++) eval_derefs2[i] = tmp[i];
       for (size_t i = 0; i < C; i++) {
         eval_dim[i] = tmp[64 + i];
@@ -784,10 +1001,10 @@ std::vector<uint8_t> prove(Ctx* c, const Strategy& S, Dense& dense, const std::v
     DotProductProofLogBytes proof_derefs =
         prove_joint(c, g, E.p, nv_d, eval_derefs2, true, "evals_ops_val", "challenge_combine_n_to_one",
                     "joint_claim_eval", rand_ops, transcript, tape);
-    eq_evals_dev(c, rand_mem, 0, rand_mem.size(), eqtab.p);
-    launch_multi_dot(dense.d_m_fr.p, M, (int)C, eqtab.p, M, c->d_partial, c->d_small, c->st);
+    eq_evals_shard(c, rand_mem, 0, rand_mem.size(), eqtab.p);
+    launch_multi_dot(dense.d_m_fr.p, M_loc, (int)C, eqtab.p, M_loc, c->d_partial, c->d_small, c->st);
     g_launches += 2;
-    c->d2h(eval_final.data(), c->d_small, C * sizeof(fr_t));
+    reduce_to_host(c, c->d_small, (int)C, eval_final.data());
     std::vector<fr_t> evals_ops = eval_dim;
     evals_ops.insert(evals_ops.end(), eval_read.begin(), eval_read.end());
     DotProductProofLogBytes proof_ops =

@@ -36,6 +36,11 @@ struct Ctx {
     }
     return h_stage;
   }
+  // ---- single proof sharded over `world` GPUs (comm.cu); world == 1: everything below is inert
+  int world = 1, rank = 0, lg_world = 0;
+  void* nccl_comm = nullptr;
+  fr_t* d_gather = nullptr;  // all-gather landing zone
+  size_t gather_elems = 0;
   double t_densify_ms = 0, t_commit_ms = 0, t_prove_ms = 0;
   std::map<std::string, double> spans;  // filled when LASSO_B200_SPANS=1 (forces syncs)
   bool span_sync = false;
@@ -123,14 +128,15 @@ struct Gens {
 struct Dense {
   Ctx* ctx = nullptr;
   size_t C = 0, s = 0, log_m = 0, m = 0, nv_l = 0, nv_m = 0;
-  DBuf<uint32_t> d_l_u32;  // 2^nv_l: dim_0..dim_{C-1} | read_0..read_{C-1} | 0..   (dim_usize = first C*s)
-  DBuf<uint32_t> d_m_u32;  // 2^nv_m: final_0..final_{C-1} | 0..
-  DBuf<fr_t> d_l_fr;       // combined_l_variate_polys
+  size_t s_loc = 0, m_loc = 0;  // this rank's share (s / G, m / G): element i' is global element i'*G + rank
+  DBuf<uint32_t> d_l_u32;  // (2^nv_l)/G: dim_0..dim_{C-1} | read_0..read_{C-1} | 0..   (dim_usize = first C*s_loc)
+  DBuf<uint32_t> d_m_u32;  // (2^nv_m)/G: final_0..final_{C-1} | 0..
+  DBuf<fr_t> d_l_fr;       // combined_l_variate_polys (this rank's low-bit shard)
   DBuf<fr_t> d_m_fr;       // combined_log_m_variate_polys
   const uint32_t* nz() const { return d_l_u32.p; }
-  const fr_t* dim(size_t i) const { return d_l_fr.p + i * s; }
-  const fr_t* read(size_t i) const { return d_l_fr.p + (C + i) * s; }
-  const fr_t* fin(size_t i) const { return d_m_fr.p + i * m; }
+  const fr_t* dim(size_t i) const { return d_l_fr.p + i * s_loc; }
+  const fr_t* read(size_t i) const { return d_l_fr.p + (C + i) * s_loc; }
+  const fr_t* fin(size_t i) const { return d_m_fr.p + i * m_loc; }
 };
 
 // ark-serialize (compressed) writer
@@ -180,5 +186,15 @@ std::vector<uint8_t> prove(Ctx*, const Strategy& S, Dense&, const std::vector<fr
                            const std::string& transcript_label, const std::string& tape_label, const fr_t& tape_seed,
                            std::vector<fr_t>* challenges);
 void sample_generators(const std::string& label, size_t count, uint64_t* out_affine);
+
+// comm.cu
+void comm_unique_id(uint8_t out[128]);
+void comm_init(Ctx*, const uint8_t id[128], int rank, int world);
+void comm_destroy(Ctx*);
+void comm_allgather(Ctx*, const void* d_send, void* d_recv, size_t bytes_per_rank);
+void comm_allreduce_fr(Ctx*, fr_t* d_buf, int count);
+// every rank holds one element per polynomial (ptrs[k][0], or base[k*stride] when ptrs == null);
+// d_out[k*G + g] <- rank g's element of polynomial k
+void comm_gather_heads(Ctx*, fr_t* const* d_ptrs, const fr_t* base, size_t stride, int npolys, fr_t* d_out);
 
 }  // namespace lb

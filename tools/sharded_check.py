@@ -1,0 +1,50 @@
+"""Run under torchrun with WORLD_SIZE GPUs: ONE proof sharded over all ranks; rank 0 checks that commitment,
+challenges and proof bytes equal the CPU oracle's (and therefore the single-GPU path's).
+usage: torchrun --nproc-per-node N tools/sharded_check.py [kind C log_m log_r lookups same]"""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import torch
+import torch.distributed as dist
+import lasso_b200 as lb
+import oracle_lib as ol
+
+rank = int(os.environ.get("RANK", 0)); local = int(os.environ.get("LOCAL_RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+cases = [(2, 4, 16, 0, 1 << 12, 1), (3, 4, 4, 0, 128, 0), (0, 1, 16, 0, 1 << 10, 1), (4, 3, 8, 40, 256, 0), (3, 8, 8, 0, 512, 0),
+         (1, 2, 8, 0, 700, 0)]
+if len(sys.argv) > 6:
+    cases = [tuple(int(x) for x in sys.argv[1:7])]
+ctx = lb.Context(local)
+ctx.init_comm()
+ok = True
+for kind, C, log_m, log_r, n, same in cases:
+    rng = np.random.default_rng(kind * 7 + C)
+    col = rng.integers(0, 1 << log_m, size=(n, 1), dtype=np.uint64)
+    idx = np.ascontiguousarray(np.repeat(col, C, axis=1) if same else rng.integers(0, 1 << log_m, size=(n, C), dtype=np.uint64))
+    s = 1 << (n - 1).bit_length()
+    r = ol.rand_fr(rng, s.bit_length() - 1); seed = ol.rand_fr(rng, 1)[0]
+    S = lb.Strategy(kind, C, log_m, log_r)
+    need = lb.gens_points_needed(C, s, S.num_memories, log_m)
+    stream = np.ascontiguousarray(ol.generators(max(need, 300))[:need])
+    gens = lb.SparsePolyCommitmentGens.new(ctx, b"g", C, s, S.num_memories, log_m, stream=stream)
+    t0 = time.time()
+    dense = lb.DensifiedRepresentation.from_lookup_indices(ctx, idx, log_m)
+    com = dense.commit(gens)
+    proof = lb.SparsePolynomialEvaluationProof.prove(ctx, S, dense, r, gens, tape_seed=seed)
+    dt = time.time() - t0
+    if rank == 0:
+        ref = ol.prove(kind, C, log_m, log_r, idx, r, stream, seed, flags=1)
+        good = ref["rc"] == 0 and com == ref["commitment"] and proof.bytes == ref["proof"]
+        nch = min(len(proof.challenges), len(ref["challenges"]))
+        first_bad = next((i for i in range(nch) if (proof.challenges[i] != ref["challenges"][i]).any()), None)
+        print("case kind=%d C=%d log_m=%d n=%d world=%d: %s (%.1f ms, commit_ok=%s, first diverging challenge=%s)" % (
+            kind, C, log_m, n, world, "OK" if good else "MISMATCH", dt * 1e3, com == ref["commitment"], first_bad), flush=True)
+        ok = ok and good
+dist.barrier()
+dist.destroy_process_group()
+if rank == 0:
+    print("SHARDED_CHECK", "PASS" if ok else "FAIL")
+    sys.exit(0 if ok else 1)
