@@ -47,7 +47,7 @@ def test_bind_errors(ctx):
     assert e.value.code == 2  # DensePolynomial::new: power of two
 
 
-@pytest.mark.parametrize("ell", [0, 1, 2, 7, 11, 12, 13, 17, 20, 22])
+@pytest.mark.parametrize("ell", [0, 1, 2, 7, 11, 12, 13, 17, 20, 22, 23, 24])
 def test_eq_evals(ctx, ell):
     import lasso_b200 as lb
 
