@@ -26,6 +26,35 @@ namespace lb {
 unsigned long long g_launches = 0;
 
 // ---------------------------------------------------------------------------------------------- context
+__global__ void publish_kernel(const uint32_t* src, int nwords, uint32_t* mapped, uint32_t seq) {
+  for (int i = threadIdx.x; i < nwords; i += blockDim.x) mapped[i] = src[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    *((volatile uint32_t*)(mapped + 1024)) = seq;
+  }
+}
+void Ctx::d2h_small(void* dst, const void* src, size_t bytes) {
+  const uint32_t seq = ++mapped_seq;
+  publish_kernel<<<1, 128, 0, st>>>((const uint32_t*)src, (int)((bytes + 3) / 4), d_mapped, seq);
+  g_launches += 1;
+  volatile uint32_t* flag = h_mapped + 1024;
+  auto t0 = std::chrono::steady_clock::now();
+  unsigned spins = 0;
+  while (*flag != seq) {
+    __builtin_ia32_pause();
+    if ((++spins & 0xffff) == 0) {  // surface kernel faults instead of spinning forever
+      if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 0.5) {
+        LB_CUDA_CHECK(cudaStreamQuery(st) == cudaErrorNotReady ? cudaSuccess : cudaStreamSynchronize(st));
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 120.0)
+          throw std::runtime_error("timeout waiting for a device result");
+      }
+    }
+  }
+  __sync_synchronize();
+  memcpy(dst, (const void*)h_mapped, bytes);
+}
 Ctx* ctx_create(int device) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
@@ -48,6 +77,14 @@ Ctx* ctx_create(int device) {
   LB_CUDA_CHECK(cudaMalloc((void**)&c->d_small, c->small_elems * sizeof(fr_t)));
   LB_CUDA_CHECK(cudaMalloc((void**)&c->d_eq_scratch, (size_t)(4096 + (1 << 17) + 4096) * sizeof(fr_t)));
   LB_CUDA_CHECK(cudaMalloc((void**)&c->d_flag, 64));
+  {
+    const char* nm = getenv("LASSO_B200_NO_MAPPED");
+    if (!(nm && nm[0] == '1')) {
+      LB_CUDA_CHECK(cudaHostAlloc((void**)&c->h_mapped, 4096 + 64, cudaHostAllocMapped));
+      memset(c->h_mapped, 0, 4096 + 64);
+      LB_CUDA_CHECK(cudaHostGetDevicePointer((void**)&c->d_mapped, c->h_mapped, 0));
+    }
+  }
   const char* sp = getenv("LASSO_B200_SPANS");
   c->span_sync = sp && sp[0] == '1';
   return c.release();
@@ -61,6 +98,7 @@ void ctx_destroy(Ctx* c) {
   cudaFree(c->d_eq_scratch);
   cudaFree(c->d_flag);
   if (c->h_stage) cudaFreeHost(c->h_stage);
+  if (c->h_mapped) cudaFreeHost(c->h_mapped);
   cudaFreeHost(c->h_pin);
   cudaStreamDestroy(c->st);
   delete c;

@@ -46,8 +46,19 @@ struct Ctx {
   bool span_sync = false;
 
   void sync() { LB_CUDA_CHECK(cudaStreamSynchronize(st)); }
+  // Round messages (<= 4 KiB): a one-warp kernel copies the result into mapped pinned host memory and then
+  // raises a sequence flag; the host spins on the flag.  ~10-15 us cheaper per sumcheck round than
+  // cudaMemcpyAsync + cudaStreamSynchronize, and a proof has ~400 such rounds.
+  uint32_t* h_mapped = nullptr;  // [0..1024) payload words, [1024] flag
+  uint32_t* d_mapped = nullptr;
+  uint32_t mapped_seq = 0;
+  void d2h_small(void* dst, const void* src, size_t bytes);  // prover.cu
   // device -> host through the pinned buffer (small) or directly (large)
   void d2h(void* dst, const void* src, size_t bytes) {
+    if (bytes <= 4096 && h_mapped) {
+      d2h_small(dst, src, bytes);
+      return;
+    }
     if (bytes <= h_pin_bytes) {
       LB_CUDA_CHECK(cudaMemcpyAsync(h_pin, src, bytes, cudaMemcpyDeviceToHost, st));
       sync();
