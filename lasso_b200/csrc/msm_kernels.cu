@@ -216,12 +216,13 @@ __global__ void __launch_bounds__(MSM_T)
     }
   }
   __syncthreads();
-  // accumulate: thread t owns the contiguous slice [lo, hi) of the sorted list
+  // accumulate: thread t owns the contiguous slice [lo, hi) of the sorted list.  ONE flat loop over the
+  // slice (every lane of the warp executes the same number of point additions); a change of bucket only
+  // triggers a short, predicated flush.  (Looping run by run made the warp pay max-over-lanes per run.)
   {
     const int lo = (int)(((long long)tid * N) / MSM_T), hi = (int)(((long long)(tid + 1) * N) / MSM_T);
     if (lo < hi) {
-      // bucket containing position lo: largest b with off[b] <= lo
-      int b = 1;
+      int b;  // bucket containing position lo: largest b with off[b] <= lo
       {
         int l = 1, r = MSM_NB;
         while (l < r) {
@@ -230,39 +231,43 @@ __global__ void __launch_bounds__(MSM_T)
         }
         b = l;
       }
-      int pos = lo;
-      while (pos < hi) {
-        while (sm.off[b + 1] <= pos) b++;  // skip exhausted / empty buckets
-        const int bend = sm.off[b + 1];
-        const int run_end = bend < hi ? bend : hi;
-        pt_ext acc = pt_identity();
-        // software pipeline: the next point's 96 B are in flight while the current addition runs
-        uint16_t e = sm.list[pos];
-        // local column c -> generator index c * col_mul + col_add (col_mul = #GPUs when one proof is sharded
-        // by the low index bits: this rank owns the columns congruent to its rank)
-        pt_niels nn = ld_niels(tw + (size_t)(c_begin + (e & 0x7fff)) * col_mul + col_add);
-        for (int p = pos; p < run_end; p++) {
-          const uint16_t ecur = e;
-          const pt_niels ncur = nn;
-          if (p + 1 < run_end) {
-            e = sm.list[p + 1];
-            nn = ld_niels(tw + (size_t)(c_begin + (e & 0x7fff)) * col_mul + col_add);
-          }
-          // P - Q = P + (-Q): negating an affine-niels point is a swap and one negation
-          acc = pt_madd(acc, (ecur & 0x8000) ? niels_neg(ncur) : ncur);
-        }
-        const bool complete = (pos == sm.off[b]) && (run_end == bend);
+      while (sm.off[b + 1] <= lo) b++;  // skip empty buckets that share the offset
+      auto flush = [&](int bb, int start, int end, const pt_ext& acc) {
+        const bool complete = (start == sm.off[bb]) && (end == sm.off[bb + 1]);
         if (complete) {
-          sm_store_pt(sm.bucket, MSM_NB + 1, b, acc);
-        } else if (pos == lo) {
+          sm_store_pt(sm.bucket, MSM_NB + 1, bb, acc);
+        } else if (start == lo) {
           sm_store_pt(sm.pfirst, MSM_T, tid, acc);
-          sm.pf_b[tid] = b;
+          sm.pf_b[tid] = bb;
         } else {
           sm_store_pt(sm.plast, MSM_T, tid, acc);
-          sm.pl_b[tid] = b;
+          sm.pl_b[tid] = bb;
         }
-        pos = run_end;
+      };
+      pt_ext acc = pt_identity();
+      int run_start = lo;
+      // software pipeline: the next point's 96 B are in flight while the current addition runs.
+      // local column c -> generator index c * col_mul + col_add (col_mul = #GPUs when one proof is sharded
+      // by the low index bits: this rank owns the columns congruent to its rank)
+      uint16_t e = sm.list[lo];
+      pt_niels nn = ld_niels(tw + (size_t)(c_begin + (e & 0x7fff)) * col_mul + col_add);
+      for (int p = lo; p < hi; p++) {
+        const uint16_t ecur = e;
+        const pt_niels ncur = nn;
+        if (p + 1 < hi) {
+          e = sm.list[p + 1];
+          nn = ld_niels(tw + (size_t)(c_begin + (e & 0x7fff)) * col_mul + col_add);
+        }
+        if (p >= sm.off[b + 1]) {  // the bucket is exhausted (it received >= 1 point): flush, move on
+          flush(b, run_start, p, acc);
+          acc = pt_identity();
+          run_start = p;
+          do { b++; } while (sm.off[b + 1] <= p);
+        }
+        // P - Q = P + (-Q): negating an affine-niels point is a swap and one negation
+        acc = pt_madd(acc, (ecur & 0x8000) ? niels_neg(ncur) : ncur);
       }
+      flush(b, run_start, hi, acc);
     }
   }
   __syncthreads();

@@ -75,6 +75,10 @@ void orc_f_op(int which, int op, const uint64_t* a, const uint64_t* b, uint64_t*
 void orc_f_from_u64(int which, uint64_t v, uint64_t* out) {
   if (which == 0) stfr(out, Fr::from_u64(v)); else stfq(out, Fq::from_u64(v));
 }
+void orc_fr_from_u64_batch(const uint64_t* in, size_t n, uint64_t* out) {
+#pragma omp parallel for
+  for (size_t i = 0; i < n; i++) stfr(out + 4 * i, Fr::from_u64(in[i]));
+}
 void orc_f_to_canonical(int which, const uint64_t* a, uint64_t* out) {
   BigInt4 b = which == 0 ? ldfr(a).into_bigint() : ldfq(a).into_bigint();
   memcpy(out, b.l, 32);

@@ -20,13 +20,14 @@ for log_n in range(16, max_log + 1, 2):
     n = 1 << log_n
     bases = np.ascontiguousarray(np.tile(pool[:8192], (n // 8192, 1)))
     for name, bits in (("full-253", 253), ("small-16", 16)):
-        raw = rng.integers(0, 2**63, size=(n, 4), dtype=np.uint64)
-        if bits <= 16:
-            raw[:, 1:] = 0
-            raw[:, 0] &= 0xFFFF
-        else:
-            raw[:, 3] &= (1 << 59) - 1  # < 2^251 < l : already canonical; treat the limbs as Montgomery residues
-        sc = np.ascontiguousarray(raw)
+        if bits <= 16:  # Montgomery form of small integers (F::from(u64))
+            small = rng.integers(0, 1 << bits, size=n, dtype=np.uint64)
+            sc = np.zeros((n, 4), dtype=np.uint64)
+            ol.lib().orc_fr_from_u64_batch(P(small), sz(n), P(sc))
+        else:  # limbs < 2^251 < l read as Montgomery residues: uniform full-width field elements
+            raw = rng.integers(0, 2**63, size=(n, 4), dtype=np.uint64)
+            raw[:, 3] &= (1 << 59) - 1
+            sc = np.ascontiguousarray(raw)
         lb.msm(ctx, bases[:1024], sc[:1024])  # warm-up
         t = time.time(); got = lb.msm(ctx, bases, sc); dt = time.time() - t
         cpu_ms, same = float("nan"), "-"
