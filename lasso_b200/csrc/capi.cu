@@ -118,8 +118,10 @@ int lasso_sumcheck_round_arbitrary(lasso_ctx* h, int strategy, int C, int log_M,
   DBuf<fr_t> d(c, (size_t)np * len);
   for (int k = 0; k < np; k++)
     LB_CUDA_CHECK(cudaMemcpyAsync(d.p + (size_t)k * len, polys[k], len * 32, cudaMemcpyHostToDevice, c->st));
-  launch_sumcheck_eval_arbitrary(S, d.p, len, len / 2, c->d_partial, c->d_small, c->st);
-  g_launches += 2;
+  Finalize f = c->fin_begin();
+  f.mapped = nullptr;  // plain device result + copy on this entry point
+  launch_sumcheck_eval_arbitrary(S, d.p, len, len / 2, f, c->st);
+  g_launches += 1;
   c->d2h(evals_out, c->d_small, (size_t)npts * 32);
   return 0;
   LB_CATCH
@@ -142,8 +144,10 @@ int lasso_sumcheck_round_cubic(lasso_ctx* h, int n_circuits, const uint64_t* con
   LB_CUDA_CHECK(cudaMemcpyAsync(dC.p, Ceq, len * 32, cudaMemcpyHostToDevice, c->st));
   LB_CUDA_CHECK(cudaMemcpyAsync(pA.p, hA.data(), n_circuits * sizeof(fr_t*), cudaMemcpyHostToDevice, c->st));
   LB_CUDA_CHECK(cudaMemcpyAsync(pB.p, hB.data(), n_circuits * sizeof(fr_t*), cudaMemcpyHostToDevice, c->st));
-  launch_sumcheck_eval_cubic(pA.p, pB.p, dC.p, n_circuits, len / 2, c->d_partial, c->d_small, c->st);
-  g_launches += 2;
+  Finalize f = c->fin_begin();
+  f.mapped = nullptr;
+  launch_sumcheck_eval_cubic(pA.p, pB.p, dC.p, n_circuits, len / 2, f, c->st);
+  g_launches += 1;
   c->d2h(out, c->d_small, (size_t)n_circuits * 3 * 32);
   return 0;
   LB_CATCH

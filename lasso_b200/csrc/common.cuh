@@ -92,6 +92,65 @@ __device__ __forceinline__ void block_sum_fr(fr_t (&v)[NV], fr_t* scratch) {
   }
   __syncthreads();
 }
+
+// ---- single-launch reduction + publication of a round message ---------------------------------------------
+// Every CTA stores its partial sums, takes a ticket, and the LAST CTA to finish adds the partials of all
+// values, writes the results to device memory and (optionally) straight into mapped pinned host memory,
+// then raises a sequence flag the host is spinning on.  One kernel per sumcheck round instead of
+// eval + reduce + copy: the rounds of the grand-product ladder are pure launch/sync latency.
+struct Finalize {
+  fr_t* partial;      // scratch: [nvals][blocks_per_val]
+  unsigned* counter;  // device ticket counter: 0 on entry, reset to 0 by the last CTA
+  fr_t* out_dev;      // nvals results (always written)
+  uint32_t* mapped;   // optional mapped host buffer: payload words [0, 8*nvals), flag at word 1024
+  uint32_t seq;       // flag value to publish
+};
+__device__ __forceinline__ fr_t ld_fr_cg(const fr_t* p) {  // bypass L1: written by other CTAs of this launch
+  fr_t r;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]) : "l"(p));
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"((const char*)p + 16));
+  return r;
+}
+// vals[0..NV) are valid in thread 0 of the CTA; they belong to value indices v0 .. v0+NV, partial slot bidx.
+template <int NV>
+__device__ __forceinline__ void finalize_block(const Finalize& f, const fr_t (&vals)[NV], int v0, int bidx,
+                                               int blocks_per_val, int nvals_total, int total_blocks) {
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int t = 0; t < NV; t++) f.partial[(size_t)(v0 + t) * blocks_per_val + bidx] = vals[t];
+    __threadfence();
+    unsigned ticket = atomicAdd(f.counter, 1u);
+    s_last = (ticket == (unsigned)total_blocks - 1u);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int v = warp; v < nvals_total; v += nwarps) {
+    fr_t acc = fr_zero();
+    for (int i = lane; i < blocks_per_val; i += 32) acc = fr_add(acc, ld_fr_cg(f.partial + (size_t)v * blocks_per_val + i));
+    acc = warp_sum_fr(acc);
+    if (lane == 0) {
+      f.out_dev[v] = acc;
+      if (f.mapped) {
+#pragma unroll
+        for (int l = 0; l < 8; l++) f.mapped[8 * v + l] = acc.v[l];
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *f.counter = 0;
+    if (f.mapped) {
+      __threadfence_system();
+      *((volatile uint32_t*)(f.mapped + 1024)) = f.seq;
+    }
+  }
+}
 #endif
 
 }  // namespace lb

@@ -48,20 +48,20 @@ void launch_eq_evals(const FrVec& r, int ell, fr_t* out, fr_t* scratch, cudaStre
 
 // ---- K2: primary sumcheck round evaluation (sumcheck.rs:179-237) ----
 // polys = (alpha+1) arrays of length 2*half at base + k*stride (the last one is eq).
-// Writes deg+1 field elements to out (device).  partial: scratch of (deg+1)*max_blocks elements.
-void launch_sumcheck_eval_arbitrary(const Strategy& S, const fr_t* base, size_t stride, size_t half, fr_t* partial,
-                                    fr_t* out, cudaStream_t st);
+// One launch: the last CTA reduces the block partials and publishes the deg+1 results (see Finalize).
+void launch_sumcheck_eval_arbitrary(const Strategy& S, const fr_t* base, size_t stride, size_t half, const Finalize& fin,
+                                    cudaStream_t st);
 int sumcheck_max_blocks();
 
 // ---- K3: batched cubic round evaluation (sumcheck.rs:49-93) ----
 // A, B: ncirc device pointers each to 2*half elements; Ceq: 2*half elements. out = ncirc x 3 (e0,e2,e3).
 void launch_sumcheck_eval_cubic(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Ceq, int ncirc, size_t half,
-                                fr_t* partial, fr_t* out, cudaStream_t st);
+                                const Finalize& fin, cudaStream_t st);
 
 // fused: bind A_k, B_k (in place) and eq (Cin -> Cout) with r, then evaluate the next round on the bound
-// values; h = bound length (>= 2).  Returns the number of kernels launched.
-int launch_sumcheck_bind_eval_cubic(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Cin, fr_t* Cout, int ncirc, size_t h,
-                                    const fr_t& r, fr_t* partial, fr_t* out, cudaStream_t st);
+// values; h = bound length (>= 2).
+void launch_sumcheck_bind_eval_cubic(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Cin, fr_t* Cout, int ncirc, size_t h,
+                                     const fr_t& r, const Finalize& fin, cudaStream_t st);
 
 // ---- K5: subtables (subtables/*.rs) ----
 // tables_fr: nsub x M Montgomery elements; tables_u32: nsub x M raw values

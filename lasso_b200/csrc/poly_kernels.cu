@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kThreads) reduce_partials_kernel(const fr_t* p
 // degree 2 -> evaluation points t = 0, 1, 2 with P(t) = lo + t (hi - lo) built incrementally.
 // Reads 2 * 32 B per polynomial per index pair (64 B/pair/poly algorithmic).
 __global__ void __launch_bounds__(kThreads)
-    sc_eval_linear_kernel(const fr_t* base, size_t stride, int alpha, size_t half, FrVec w, fr_t* partial) {
+    sc_eval_linear_kernel(const fr_t* base, size_t stride, int alpha, size_t half, FrVec w, Finalize fin) {
   __shared__ fr_t scratch[3 * kThreads / 32];
   fr_t acc[3] = {fr_zero(), fr_zero(), fr_zero()};
   const fr_t* eq = base + (size_t)alpha * stride;
@@ -162,10 +162,7 @@ __global__ void __launch_bounds__(kThreads)
     acc[2] = fr_add(acc[2], fr_mul(c2, q2));
   }
   block_sum_fr<3>(acc, scratch);
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int t = 0; t < 3; t++) partial[(size_t)t * gridDim.x + blockIdx.x] = acc[t];
-  }
+  finalize_block<3>(fin, acc, 0, blockIdx.x, gridDim.x, 3, gridDim.x);
 }
 
 // LT strategy (lt.rs:60-69): g = sum_i LT_i prod_{j<i} EQ_j, memories ordered LT_0, EQ_0, LT_1, ...
@@ -173,7 +170,7 @@ __global__ void __launch_bounds__(kThreads)
 // so only two polynomials' values are live at a time.
 template <int C>
 __global__ void __launch_bounds__(128)
-    sc_eval_lt_kernel(const fr_t* base, size_t stride, size_t half, fr_t* partial) {
+    sc_eval_lt_kernel(const fr_t* base, size_t stride, size_t half, Finalize fin) {
   constexpr int NP = C + 2;  // degree C+1
   __shared__ fr_t scratch[NP * 128 / 32];
   fr_t acc[NP];
@@ -208,10 +205,7 @@ __global__ void __launch_bounds__(128)
     }
   }
   block_sum_fr<NP>(acc, scratch);
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int t = 0; t < NP; t++) partial[(size_t)t * gridDim.x + blockIdx.x] = acc[t];
-  }
+  finalize_block<NP>(fin, acc, 0, blockIdx.x, gridDim.x, NP, gridDim.x);
 }
 
 static FrVec linear_weights(const Strategy& S) {
@@ -222,29 +216,27 @@ static FrVec linear_weights(const Strategy& S) {
 }
 
 template <int C>
-static void launch_lt(const fr_t* base, size_t stride, size_t half, fr_t* partial, int blocks, cudaStream_t st) {
-  sc_eval_lt_kernel<C><<<blocks, 128, 0, st>>>(base, stride, half, partial);
+static void launch_lt(const fr_t* base, size_t stride, size_t half, const Finalize& fin, int blocks, cudaStream_t st) {
+  sc_eval_lt_kernel<C><<<blocks, 128, 0, st>>>(base, stride, half, fin);
 }
 
-void launch_sumcheck_eval_arbitrary(const Strategy& S, const fr_t* base, size_t stride, size_t half, fr_t* partial,
-                                    fr_t* out, cudaStream_t st) {
-  int npts = S.sumcheck_poly_degree() + 1;
+void launch_sumcheck_eval_arbitrary(const Strategy& S, const fr_t* base, size_t stride, size_t half, const Finalize& fin,
+                                    cudaStream_t st) {
   int blocks;
   if (S.kind == STRAT_LT) {
     blocks = grid_for(half, 128, kMaxBlocks);
     switch (S.C) {
-      case 1: launch_lt<1>(base, stride, half, partial, blocks, st); break;
-      case 2: launch_lt<2>(base, stride, half, partial, blocks, st); break;
-      case 3: launch_lt<3>(base, stride, half, partial, blocks, st); break;
-      case 4: launch_lt<4>(base, stride, half, partial, blocks, st); break;
-      case 8: launch_lt<8>(base, stride, half, partial, blocks, st); break;
+      case 1: launch_lt<1>(base, stride, half, fin, blocks, st); break;
+      case 2: launch_lt<2>(base, stride, half, fin, blocks, st); break;
+      case 3: launch_lt<3>(base, stride, half, fin, blocks, st); break;
+      case 4: launch_lt<4>(base, stride, half, fin, blocks, st); break;
+      case 8: launch_lt<8>(base, stride, half, fin, blocks, st); break;
       default: throw std::runtime_error("LT strategy: unsupported C (1,2,3,4,8 are built)");
     }
   } else {
     blocks = grid_for(half);
-    sc_eval_linear_kernel<<<blocks, kThreads, 0, st>>>(base, stride, S.num_memories(), half, linear_weights(S), partial);
+    sc_eval_linear_kernel<<<blocks, kThreads, 0, st>>>(base, stride, S.num_memories(), half, linear_weights(S), fin);
   }
-  reduce_partials_kernel<<<npts, kThreads, 0, st>>>(partial, blocks, out);
 }
 
 // subtables/mod.rs:186-216: sum_k eq[k] * g(E_1[k], ..., E_alpha[k]) over the whole hypercube
@@ -290,7 +282,7 @@ void launch_sumcheck_claim(const Strategy& S, const fr_t* base, size_t stride, s
 // ------------------------------------------------------------------------------------ K3
 // sumcheck.rs:49-93: per circuit (e0, e2, e3) = sum_i A B C at t = 0, 2, 3.
 __global__ void __launch_bounds__(kThreads)
-    sc_eval_cubic_kernel(fr_t* const* A, fr_t* const* B, const fr_t* Ceq, size_t half, fr_t* partial) {
+    sc_eval_cubic_kernel(fr_t* const* A, fr_t* const* B, const fr_t* Ceq, size_t half, Finalize fin) {
   __shared__ fr_t scratch[3 * kThreads / 32];
   const fr_t* a = A[blockIdx.y];
   const fr_t* b = B[blockIdx.y];
@@ -307,12 +299,8 @@ __global__ void __launch_bounds__(kThreads)
     acc[2] = fr_add(acc[2], fr_mul(fr_mul(a3, b3), c3));
   }
   block_sum_fr<3>(acc, scratch);
-  if (threadIdx.x == 0) {
-    // layout [circuit][t][block] so one reduce CTA handles one (circuit, t)
-#pragma unroll
-    for (int t = 0; t < 3; t++)
-      partial[((size_t)blockIdx.y * 3 + t) * gridDim.x + blockIdx.x] = acc[t];
-  }
+  // value index = circuit*3 + t
+  finalize_block<3>(fin, acc, blockIdx.y * 3, blockIdx.x, gridDim.x, 3 * gridDim.y, gridDim.x * gridDim.y);
 }
 // Fused round: bind every A_k, B_k (in place) and the shared eq polynomial (Cin -> Cout, ping-pong: it is
 // read by all circuits) with the challenge of round j, and evaluate round j+1 on the bound values in the
@@ -321,7 +309,7 @@ __global__ void __launch_bounds__(kThreads)
 // h = number of bound outputs per polynomial (current length / 2), must be >= 2.
 __global__ void __launch_bounds__(kThreads)
     sc_bind_eval_cubic_kernel(fr_t* const* A, fr_t* const* B, const fr_t* Cin, fr_t* Cout, size_t h, fr_t r,
-                              fr_t* partial, fr_t* out_direct) {
+                              Finalize fin) {
   __shared__ fr_t scratch[3 * kThreads / 32];
   fr_t* a = A[blockIdx.y];
   fr_t* b = B[blockIdx.y];
@@ -357,37 +345,24 @@ __global__ void __launch_bounds__(kThreads)
     acc[2] = fr_add(acc[2], fr_mul(fr_mul(a3, b3), c3));
   }
   block_sum_fr<3>(acc, scratch);
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int t = 0; t < 3; t++) {
-      if (gridDim.x == 1)
-        out_direct[(size_t)blockIdx.y * 3 + t] = acc[t];
-      else
-        partial[((size_t)blockIdx.y * 3 + t) * gridDim.x + blockIdx.x] = acc[t];
-    }
-  }
+  finalize_block<3>(fin, acc, blockIdx.y * 3, blockIdx.x, gridDim.x, 3 * gridDim.y, gridDim.x * gridDim.y);
 }
-// returns the number of kernels launched
-int launch_sumcheck_bind_eval_cubic(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Cin, fr_t* Cout, int ncirc, size_t h,
-                                    const fr_t& r, fr_t* partial, fr_t* out, cudaStream_t st) {
+void launch_sumcheck_bind_eval_cubic(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Cin, fr_t* Cout, int ncirc, size_t h,
+                                     const fr_t& r, const Finalize& fin, cudaStream_t st) {
   size_t q = h / 2;
   int per = kMaxBlocks / ncirc;
   if (per < 1) per = 1;
   int bx = grid_for(q, kThreads, per);
   dim3 grid(bx, ncirc);
-  sc_bind_eval_cubic_kernel<<<grid, kThreads, 0, st>>>(d_A, d_B, Cin, Cout, h, r, partial, out);
-  if (bx == 1) return 1;
-  reduce_partials_kernel<<<ncirc * 3, kThreads, 0, st>>>(partial, bx, out);
-  return 2;
+  sc_bind_eval_cubic_kernel<<<grid, kThreads, 0, st>>>(d_A, d_B, Cin, Cout, h, r, fin);
 }
 void launch_sumcheck_eval_cubic(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Ceq, int ncirc, size_t half,
-                                fr_t* partial, fr_t* out, cudaStream_t st) {
+                                const Finalize& fin, cudaStream_t st) {
   int per = kMaxBlocks / ncirc;
   if (per < 1) per = 1;
   int bx = grid_for(half, kThreads, per);
   dim3 grid(bx, ncirc);
-  sc_eval_cubic_kernel<<<grid, kThreads, 0, st>>>(d_A, d_B, Ceq, half, partial);
-  reduce_partials_kernel<<<ncirc * 3, kThreads, 0, st>>>(partial, bx, out);
+  sc_eval_cubic_kernel<<<grid, kThreads, 0, st>>>(d_A, d_B, Ceq, half, fin);
 }
 
 // ------------------------------------------------------------------------------------ K5

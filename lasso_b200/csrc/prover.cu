@@ -39,6 +39,19 @@ void Ctx::d2h_small(void* dst, const void* src, size_t bytes) {
   const uint32_t seq = ++mapped_seq;
   publish_kernel<<<1, 128, 0, st>>>((const uint32_t*)src, (int)((bytes + 3) / 4), d_mapped, seq);
   g_launches += 1;
+  wait_flag(seq);
+  memcpy(dst, (const void*)h_mapped, bytes);
+}
+void Ctx::fin_wait(const Finalize& f, fr_t* dst, int count) {
+  if (f.mapped) {
+    wait_flag(f.seq);
+    memcpy(dst, (const void*)h_mapped, (size_t)count * sizeof(fr_t));
+    return;
+  }
+  comm_allreduce_fr(this, d_small, count);
+  d2h(dst, d_small, (size_t)count * sizeof(fr_t));
+}
+void Ctx::wait_flag(uint32_t seq) {
   volatile uint32_t* flag = h_mapped + 1024;
   auto t0 = std::chrono::steady_clock::now();
   unsigned spins = 0;
@@ -53,7 +66,6 @@ void Ctx::d2h_small(void* dst, const void* src, size_t bytes) {
     }
   }
   __sync_synchronize();
-  memcpy(dst, (const void*)h_mapped, bytes);
 }
 Ctx* ctx_create(int device) {
   int count = 0;
@@ -77,6 +89,7 @@ Ctx* ctx_create(int device) {
   LB_CUDA_CHECK(cudaMalloc((void**)&c->d_small, c->small_elems * sizeof(fr_t)));
   LB_CUDA_CHECK(cudaMalloc((void**)&c->d_eq_scratch, (size_t)(4096 + (1 << 17) + 4096) * sizeof(fr_t)));
   LB_CUDA_CHECK(cudaMalloc((void**)&c->d_flag, 64));
+  LB_CUDA_CHECK(cudaMemset(c->d_flag, 0, 64));
   {
     const char* nm = getenv("LASSO_B200_NO_MAPPED");
     if (!(nm && nm[0] == '1')) {
@@ -462,12 +475,19 @@ static SumcheckProof prove_arbitrary(Ctx* c, const Strategy& S, fr_t* base, size
     }
     if (len <= 1) break;
     size_t half = len / 2;
-    launch_sumcheck_eval_arbitrary(S, base, stride, half, c->d_partial, c->d_small, c->st);
-    g_launches += 2;
-    if (sharded)
-      reduce_to_host(c, c->d_small, npts, evals.data());
-    else
-      c->d2h(evals.data(), c->d_small, (size_t)npts * sizeof(fr_t));
+    if (sharded) {
+      Finalize f = c->fin_begin();
+      launch_sumcheck_eval_arbitrary(S, base, stride, half, f, c->st);
+      c->fin_wait(f, evals.data(), npts);
+    } else {  // replicated tail of a sharded proof, or a single GPU: no cross-rank sum
+      Finalize f = c->fin_begin();
+      launch_sumcheck_eval_arbitrary(S, base, stride, half, f, c->st);
+      if (f.mapped)
+        c->fin_wait(f, evals.data(), npts);
+      else
+        c->d2h(evals.data(), c->d_small, (size_t)npts * sizeof(fr_t));
+    }
+    g_launches += 1;
     std::vector<fr_t> coeffs = unipoly_from_evals(evals);
     unipoly_append(coeffs, transcript);
     fr_t r_j = transcript.challenge_scalar("challenge_nextround");
@@ -589,6 +609,7 @@ static GPAProof prove_gpa(Ctx* c, std::vector<Circuit*>& circuits, std::vector<f
     fr_t* Ccur = eqbuf.p;
     fr_t* Cnext = eqbuf2.p;
     bool have_evals = false;
+    Finalize fz = c->fin_begin();
     for (;;) {
       if (sharded && cur == 1) {  // all-gather the G-element remainders; the tail rounds run replicated
         comm_gather_heads(c, d_AB.p, nullptr, 0, 2 * ncirc, tail.p);
@@ -606,12 +627,13 @@ static GPAProof prove_gpa(Ctx* c, std::vector<Circuit*>& circuits, std::vector<f
       }
       if (cur <= 1) break;
       if (!have_evals) {  // first round of a phase; later rounds come out of the fused bind+eval kernel
-        launch_sumcheck_eval_cubic(d_A.p, d_B.p, Ccur, ncirc, cur / 2, c->d_partial, c->d_small, c->st);
-        g_launches += 2;
+        fz = c->fin_begin();
+        launch_sumcheck_eval_cubic(d_A.p, d_B.p, Ccur, ncirc, cur / 2, fz, c->st);
+        g_launches += 1;
       }
       size_t half = cur / 2;
-      if (sharded)
-        reduce_to_host(c, c->d_small, 3 * ncirc, ev.data());
+      if (sharded || fz.mapped)
+        c->fin_wait(fz, ev.data(), 3 * ncirc);
       else
         c->d2h(ev.data(), c->d_small, ev.size() * sizeof(fr_t));
       fr_t c0 = fr_zero(), c2 = fr_zero(), c3 = fr_zero();
@@ -627,8 +649,9 @@ static GPAProof prove_gpa(Ctx* c, std::vector<Circuit*>& circuits, std::vector<f
       rand_prod.push_back(r_j);
       if (half > 1) {
         // bind with r_j and evaluate the next round in one pass (sumcheck.rs:116-120 + 63-89)
-        g_launches += launch_sumcheck_bind_eval_cubic(d_A.p, d_B.p, Ccur, Cnext, ncirc, half, r_j, c->d_partial,
-                                                      c->d_small, c->st);
+        fz = c->fin_begin();
+        launch_sumcheck_bind_eval_cubic(d_A.p, d_B.p, Ccur, Cnext, ncirc, half, r_j, fz, c->st);
+        g_launches += 1;
         std::swap(Ccur, Cnext);
         have_evals = true;
       } else {

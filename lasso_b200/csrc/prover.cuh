@@ -53,6 +53,23 @@ struct Ctx {
   uint32_t* d_mapped = nullptr;
   uint32_t mapped_seq = 0;
   void d2h_small(void* dst, const void* src, size_t bytes);  // prover.cu
+  void wait_flag(uint32_t seq);                               // prover.cu
+  // a round message produced by a single launch (common.cuh Finalize): results land in d_small and, on a single
+  // GPU, directly in the mapped host buffer
+  Finalize fin_begin() {
+    Finalize f;
+    f.partial = d_partial;
+    f.counter = d_flag + 4;
+    f.out_dev = d_small;
+    f.mapped = nullptr;
+    f.seq = 0;
+    if (h_mapped && world == 1) {
+      f.mapped = d_mapped;
+      f.seq = ++mapped_seq;
+    }
+    return f;
+  }
+  void fin_wait(const Finalize& f, fr_t* dst, int count);  // prover.cu (sums over ranks when sharded)
   // device -> host through the pinned buffer (small) or directly (large)
   void d2h(void* dst, const void* src, size_t bytes) {
     if (bytes <= 4096 && h_mapped) {
