@@ -280,7 +280,10 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"kernel": "bind_top_kernel (K1)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch of this exact shape, from the
+                         # ncu --set full capture in profiles/r01_bind_top_kernel_ncu_full.txt (671.1 MB + 295.5 MB)
+                         "traffic": 966613504,
                          "peak_source": peak_src, "ms_per_launch": ms,
                          "alg_bytes_per_launch": alg_bytes},
         }
