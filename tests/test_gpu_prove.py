@@ -19,6 +19,13 @@ CASES = [  # name, kind, C, log_m, log_r, lookups, same_index
     ("or_c2_ragged", 1, 2, 8, 0, 700, False),
     ("lt_c8", 3, 8, 8, 0, 1 << 9, False),
     ("range_c4", 4, 4, 16, 40, 1 << 10, False),
+    # edge shapes: non-power-of-two C (zero-padded merges), the smallest sizes, a single dimension of LT
+    ("xor_c3", 2, 3, 8, 0, 64, False),
+    ("and_s2", 0, 2, 4, 0, 2, False),
+    ("or_s4_ragged", 1, 4, 4, 0, 3, False),
+    ("lt_c1", 3, 1, 4, 0, 8, False),
+    ("range_c2_small_r", 4, 2, 8, 12, 16, False),
+    ("xor_c16_m16", 2, 16, 4, 0, 16, False),
 ]
 
 
@@ -59,6 +66,29 @@ def test_prove_matches_oracle(ctx, name, kind, C, log_m, log_r, n, same):
     nch = min(len(proof.challenges), len(ref["challenges"]))
     assert (proof.challenges[:nch] == ref["challenges"][:nch]).all(), "Fiat-Shamir challenges diverge"
     assert len(proof.challenges) == len(ref["challenges"])
+    assert proof.bytes == ref["proof"]
+
+
+def test_headline_config_full_size(ctx):
+    """BASELINE configs[1] at its FULL size — XOR, C=4, M=2^16, 2^20 lookups: commitment and proof bytes of the GPU
+    path equal the oracle's (which its own verifier accepts).  The oracle takes ~10-20 s on the box's host cores."""
+    import lasso_b200 as lb
+
+    C, log_m, n = 4, 16, 1 << 20
+    idx, r, seed, s = make_inputs(C, log_m, n, 2024, True)
+    S = lb.Strategy(lb.XOR, C, log_m)
+    need = lb.gens_points_needed(C, s, S.num_memories, log_m)
+    stream = np.ascontiguousarray(ol.generators(need))
+    gens = lb.SparsePolyCommitmentGens.new(ctx, b"gens_sparse_poly", C, s, S.num_memories, log_m, stream=stream)
+    dense = lb.DensifiedRepresentation.from_lookup_indices(ctx, idx, log_m)
+    commitment = dense.commit(gens)
+    proof = lb.SparsePolynomialEvaluationProof.prove(ctx, S, dense, r, gens, tape_seed=seed)
+    # size-independent sanity first: deterministic, and a different tape seed changes only the opening proofs
+    proof2 = lb.SparsePolynomialEvaluationProof.prove(ctx, S, dense, r, gens, tape_seed=seed)
+    assert proof2.bytes == proof.bytes
+    ref = ol.prove(lb.XOR, C, log_m, 0, idx, r, stream, seed, flags=1)
+    assert ref["rc"] == 0
+    assert commitment == ref["commitment"]
     assert proof.bytes == ref["proof"]
 
 
