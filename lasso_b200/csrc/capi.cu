@@ -101,7 +101,7 @@ int lasso_eq_evals(lasso_ctx* h, const uint64_t* r, int ell, uint64_t* out) {
   size_t n = (size_t)1 << ell;
   DBuf<fr_t> d(c, n);
   launch_eq_evals(rv, ell, d.p, c->d_eq_scratch, c->st);
-  g_launches += ell <= 11 ? 1 : 3;
+  g_launches += ell <= 11 ? 1 : (ell <= 22 ? 3 : 5);
   LB_CUDA_CHECK(cudaMemcpyAsync(out, d.p, n * 32, cudaMemcpyDeviceToHost, c->st));
   c->sync();
   return 0;

@@ -107,4 +107,11 @@ void launch_bullet_scalars(const fr_t* a, const fr_t* w, size_t n_loc, size_t m,
 void launch_scale_strided(const fr_t* in, fr_t* out, size_t n, size_t stride, size_t off, const fr_t& k, cudaStream_t st);
 void launch_scale(const fr_t* in, fr_t* out, size_t n, const fr_t& k, cudaStream_t st);
 
+// ---- densify on the GPU (densify_kernels.cu; densified.rs:33-56) ----
+bool densify_gpu_supported(size_t s, size_t log_m);
+size_t densify_chunk(size_t s);
+int launch_densify_dim(const uint32_t* d_idx, size_t n, size_t s, int C, int dim, size_t log_m, int G, int g,
+                       uint32_t* d_addr, uint32_t* d_P, uint32_t* dim_loc, uint32_t* read_loc, uint32_t* final_loc,
+                       cudaStream_t st);
+
 }  // namespace lb

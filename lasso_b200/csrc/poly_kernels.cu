@@ -105,17 +105,12 @@ void launch_eq_evals(const FrVec& r, int ell, fr_t* out, fr_t* scratch, cudaStre
   }
   int ell_lo = ell / 2 > 11 ? 11 : ell / 2;
   int ell_hi = ell - ell_lo;
-  if (ell_hi > 11) {  // very large tables: build hi recursively into the tail of `out` first
-    // 2^ell_hi entries fit in out; compute hi table there with a recursive outer product
+  if (ell_hi > 11) {
+    // > 2^22 entries: the high table (2^ell_hi <= 2^17 entries) is itself an outer product.  Build it in the
+    // tail of `out`, stage it in scratch (+4096) because the final pass overwrites that tail, then expand.
     fr_t* hi_tab = out + (((size_t)1 << ell) - ((size_t)1 << ell_hi));
-    FrVec rh = r;
-    launch_eq_evals(rh, ell_hi, hi_tab, scratch, st);  // uses scratch internally, finished before reuse below
+    launch_eq_evals(r, ell_hi, hi_tab, scratch, st);
     eq_small_kernel<<<1, 1024, 0, st>>>(r, ell_hi, ell_lo, scratch);
-    // the in-place hazard: out[i] for i near the end overlaps hi_tab.  Process through a copy of hi_tab
-    // is avoided by noting out index i reads hi_tab[i >> ell_lo]; the last 2^ell_hi outputs (which
-    // overwrite hi_tab) only need hi_tab entries >= 2^ell_hi - 2^(ell_hi-ell_lo), i.e. a hazard exists.
-    // Keep it simple and correct: stage hi_tab in scratch + 4096.
-    // (ell_hi <= 16 here since ell <= 28 and ell_lo = 11 -> up to 2^17 entries; callers size scratch.)
     cudaMemcpyAsync(scratch + 4096, hi_tab, sizeof(fr_t) << ell_hi, cudaMemcpyDeviceToDevice, st);
     size_t n = (size_t)1 << ell;
     eq_outer_kernel<<<grid_for(n), kThreads, 0, st>>>(scratch + 4096, scratch, ell_lo, n, out);

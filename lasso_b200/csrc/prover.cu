@@ -126,7 +126,7 @@ static FrVec to_frvec(const std::vector<fr_t>& v, size_t off, size_t n) {
 // eq(r) table on the device (eq_poly.rs:21-38)
 static void eq_evals_dev(Ctx* c, const std::vector<fr_t>& r, size_t off, size_t ell, fr_t* out) {
   launch_eq_evals(to_frvec(r, off, ell), (int)ell, out, c->d_eq_scratch, c->st);
-  g_launches += ell <= 11 ? 1 : 3;
+  g_launches += ell <= 11 ? 1 : (ell <= 22 ? 3 : 5);
 }
 
 // ---------------------------------------------------------------------------------------------- generators
@@ -307,7 +307,64 @@ Dense* densify(Ctx* c, const uint64_t* indices, size_t n, size_t C, size_t log_m
   d->m_loc = m / G;
   const size_t s_loc = d->s_loc, m_loc = d->m_loc;
   const size_t nl = ((size_t)1 << d->nv_l) / G, nm = ((size_t)1 << d->nv_m) / G;  // local lengths
-  // pinned, reused across calls: no per-call page faults, and the upload runs at full PCIe rate
+  {
+    const char* hd = getenv("LASSO_B200_HOST_DENSIFY");
+    const char* gd = getenv("LASSO_B200_GPU_DENSIFY");
+    // measured on B200 (profiles/README.md): the device path wins from 2^22 lookups up (53 vs 73 ms at 2^24) and
+    // whenever one proof is sharded (no replicated host scan); below that the 3 ms host scan + pinned upload wins
+    const bool want_gpu = (gd && gd[0] == '1') || s >= ((size_t)1 << 22) || G > 1;
+    if (densify_gpu_supported(s, log_m) && want_gpu && !(hd && hd[0] == '1')) {
+      // GPU path (densify_kernels.cu): upload the raw index matrix, derive dim / read / final on the device.
+      // When one proof is sharded every rank does this for the whole sequence and stores only its shard.
+      d->d_l_u32.alloc(c, nl);
+      d->d_m_u32.alloc(c, nm);
+      d->d_l_fr.alloc(c, nl);
+      d->d_m_fr.alloc(c, nm);
+      // narrow usize -> u32 (and range-check, densified.rs:46) while staging into pinned memory: half the
+      // PCIe bytes and a full-rate copy; a few host threads keep up with the link
+      uint32_t* stage = c->stage(n * C);
+      {
+        const size_t total = n * C, nthreads = total >= (1u << 20) ? 4 : 1;
+        std::vector<int> bad(nthreads, 0);
+        auto conv = [&](size_t t) {
+          size_t lo = total * t / nthreads, hi = total * (t + 1) / nthreads;
+          for (size_t k = lo; k < hi; k++) {
+            uint64_t a = indices[k];
+            if (a >= m) {
+              bad[t] = 1;
+              a = 0;
+            }
+            stage[k] = (uint32_t)a;
+          }
+        };
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < nthreads; t++) th.emplace_back(conv, t);
+        conv(0);
+        for (auto& t : th) t.join();
+        for (int bflag : bad)
+          if (bflag) {
+            *err = 3;
+            return nullptr;
+          }
+      }
+      DBuf<uint32_t> d_idx(c, n * C);
+      LB_CUDA_CHECK(cudaMemcpyAsync(d_idx.p, stage, n * C * sizeof(uint32_t), cudaMemcpyHostToDevice, c->st));
+      const size_t B = densify_chunk(s);
+      DBuf<uint32_t> d_addr(c, s), d_P(c, (s / B) * m);
+      if (nl > 2 * C * s_loc) LB_CUDA_CHECK(cudaMemsetAsync(d->d_l_u32.p + 2 * C * s_loc, 0, (nl - 2 * C * s_loc) * 4, c->st));
+      if (nm > C * m_loc) LB_CUDA_CHECK(cudaMemsetAsync(d->d_m_u32.p + C * m_loc, 0, (nm - C * m_loc) * 4, c->st));
+      for (size_t i = 0; i < C; i++)
+        g_launches += launch_densify_dim(d_idx.p, n, s, (int)C, (int)i, log_m, (int)G, (int)gr, d_addr.p, d_P.p,
+                                         d->d_l_u32.p + i * s_loc, d->d_l_u32.p + (C + i) * s_loc,
+                                         d->d_m_u32.p + i * m_loc, c->st);
+      launch_from_u32(d->d_l_u32.p, d->d_l_fr.p, nl, c->st);  // DensePolynomial::from_usize + merge
+      launch_from_u32(d->d_m_u32.p, d->d_m_fr.p, nm, c->st);
+      g_launches += 2;
+      c->sync();  // the pinned staging buffer is reused by the next call
+      return d.release();
+    }
+  }
+  // host path (memories larger than 2^16 cells): pinned staging, reused across calls: no per-call page faults, and the upload runs at full PCIe rate
   uint32_t* l_host = c->stage(nl + nm + (G > 1 ? (2 * s + m) * C : 0));
   uint32_t* m_host = l_host + nl;
   uint32_t* full = m_host + nm;  // G > 1: whole-sequence scratch (every rank runs the full scan, keeps its shard)

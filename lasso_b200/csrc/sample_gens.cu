@@ -106,8 +106,6 @@ void sample_generators(const std::string& label, size_t count, uint64_t* out_aff
   ChaCha20Stream rng(seed.data());
   const fq_t d = {{0x135978a3u, 0x75eb4dcau, 0x4141d8abu, 0x00700a4du, 0x7779e898u, 0x8cc74079u, 0x2b6ffe73u, 0x52036ceeu}};
   const fq_t sqrtm1 = {{0x4a0ea0b0u, 0xc4ee1b27u, 0xad2fe478u, 0x2f431806u, 0x3dfbd7a7u, 0x2b4d0099u, 0x4fc1df0bu, 0x2b832480u}};
-  const fq_t inv38 = fq_from_ark(fq_one());  // 38^-1
-  (void)inv38;
   size_t produced = 0;
   while (produced < count) {
     // Fq::rand: 4 x u64, keep 255 bits, reject >= q; the bits are the Montgomery representation

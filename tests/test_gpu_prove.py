@@ -109,6 +109,47 @@ def test_densified_fields(ctx):
     assert e.value.code == 3
 
 
+def test_gpu_densify_matches_host_scan(monkeypatch):
+    """densify_kernels.cu (chunk histogram + column scan + in-order warp ranking) against the host timestamp scan,
+    through the public fields of DensifiedRepresentation (densified.rs:8-18); skewed addresses included."""
+    import lasso_b200 as lb
+
+    rng = np.random.default_rng(77)
+    n, C, log_m = 5000, 3, 8
+    idx = rng.integers(0, 1 << log_m, size=(n, C), dtype=np.uint64)
+    idx[:, 1] = rng.integers(0, 3, size=n)          # heavy collisions: timestamps up to ~n/3
+    idx[100:400, 2] = 17                             # a long run of one address
+    fields = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("LASSO_B200_GPU_DENSIFY", mode)
+        monkeypatch.setenv("LASSO_B200_HOST_DENSIFY", "0" if mode == "1" else "1")
+        c = lb.Context(0)
+        d = lb.DensifiedRepresentation.from_lookup_indices(c, idx, log_m)
+        fields[mode] = (d.dim_usize.copy(), d.read.copy(), d.final.copy())
+        del d
+        c.close()
+    for a, b in zip(fields["1"], fields["0"]):
+        assert (a == b).all()
+    # and against a plain Python restatement of densified.rs:44-51
+    s = 8192
+    for i in range(C):
+        fin = [0] * (1 << log_m)
+        rd = []
+        for k in range(s):
+            a = int(idx[k, i]) if k < n else 0
+            rd.append(fin[a])
+            fin[a] += 1
+        assert ol.fr_ints(fields["1"][1][i][:64]) == rd[:64]
+        assert ol.fr_ints(fields["1"][2][i][:32]) == fin[:32]
+    with pytest.raises(lb.LassoError):
+        monkeypatch.setenv("LASSO_B200_GPU_DENSIFY", "1")
+        monkeypatch.setenv("LASSO_B200_HOST_DENSIFY", "0")
+        c = lb.Context(0)
+        bad = idx.copy()
+        bad[7, 0] = 1 << log_m
+        lb.DensifiedRepresentation.from_lookup_indices(c, bad, log_m)
+
+
 def test_prove_rejects_wrong_r_length(ctx):
     import lasso_b200 as lb
 
