@@ -36,7 +36,7 @@ def inputs(C, log_m, n, seed, same):
 
 def main():
     out = {"generator_label": "gens_sparse_poly", "cases": []}
-    gens = ol.generators(300)
+    gens = ol.generators(600)
     for name, kind, C, log_m, log_r, n, same, seed in CASES:
         idx, r, tape_seed, s = inputs(C, log_m, n, seed, same)
         res = ol.prove(kind, C, log_m, log_r, idx, r, gens, tape_seed, flags=1)
