@@ -38,7 +38,8 @@ static std::vector<Fr> ldvec(const uint64_t* p, size_t n) {
 __attribute__((constructor)) static void orc_malloc_tune() {
   mallopt(M_MMAP_MAX, 0);
   mallopt(M_TRIM_THRESHOLD, -1);
-  mallopt(M_ARENA_MAX, 1);
+  const char* am = getenv("ORACLE_ARENA_MAX");  // default 1: one shared heap that stays faulted-in
+  mallopt(M_ARENA_MAX, am ? atoi(am) : 1);
 }
 
 extern "C" {
