@@ -120,6 +120,11 @@ __global__ void transpose_gathered_kernel(const fr_t* gathered /*[G][npolys]*/, 
   int g = i / npolys, k = i % npolys;
   out[(size_t)k * world + g] = gathered[i];
 }
+// out[k] = ptrs[k][0] (or base[k*stride]): used to bring the 2*ncirc final claims of a layer to the host in one go
+void pack_heads(Ctx* c, fr_t* const* d_ptrs, const fr_t* base, size_t stride, int npolys, fr_t* d_out) {
+  pack_heads_kernel<<<(npolys + 127) / 128, 128, 0, c->st>>>(d_ptrs, base, stride, npolys, d_out);
+  g_launches += 1;
+}
 void comm_gather_heads(Ctx* c, fr_t* const* d_ptrs, const fr_t* base, size_t stride, int npolys, fr_t* d_out) {
   if ((size_t)npolys * (c->world + 1) > c->gather_elems) throw std::runtime_error("gather_heads: too many polynomials");
   fr_t* packed = c->d_gather + (size_t)npolys * c->world;

@@ -625,34 +625,52 @@ static GPAProof prove_gpa(Ctx* c, std::vector<Circuit*>& circuits, std::vector<f
   GPAProof out;
   const int ncirc = (int)circuits.size(), G = c->world;
   const size_t num_layers = circuits[0]->num_layers;
-  DBuf<fr_t*> d_A(c, ncirc), d_B(c, ncirc), d_AB(c, 2 * ncirc);
+  // pointer tables: slot L (< num_layers) = the arrays of layer L, slot num_layers = the replicated tail arrays;
+  // all of them are uploaded once, up front (no per-layer copy + sync)
+  const size_t nslots = num_layers + 1;
+  DBuf<fr_t*> d_ptrs(c, nslots * 4 * ncirc);
   const size_t eq_cap = std::max<size_t>(circuits[0]->N / 2 / G, (size_t)G);
   DBuf<fr_t> eqbuf(c, eq_cap), eqbuf2(c, std::max<size_t>(eq_cap / 2, 1));
   DBuf<fr_t> tail(c, (size_t)(2 * ncirc + 1) * G);  // replicated remainders of A_k, B_k, C (G elements each)
-  std::vector<fr_t*> hA(ncirc), hB(ncirc), hAB(2 * ncirc);
   std::vector<fr_t> rand;
   std::vector<fr_t> ev((size_t)ncirc * 3), fin((size_t)2 * ncirc);
-  auto upload_ptrs = [&]() {
-    for (int k = 0; k < ncirc; k++) {
-      hAB[2 * k] = hA[k];
-      hAB[2 * k + 1] = hB[k];
-    }
-    LB_CUDA_CHECK(cudaMemcpyAsync(d_A.p, hA.data(), ncirc * sizeof(fr_t*), cudaMemcpyHostToDevice, c->st));
-    LB_CUDA_CHECK(cudaMemcpyAsync(d_B.p, hB.data(), ncirc * sizeof(fr_t*), cudaMemcpyHostToDevice, c->st));
-    LB_CUDA_CHECK(cudaMemcpyAsync(d_AB.p, hAB.data(), 2 * ncirc * sizeof(fr_t*), cudaMemcpyHostToDevice, c->st));
-    c->sync();  // the host arrays are rewritten afterwards
-  };
-  for (size_t layer_id = num_layers; layer_id-- > 0;) {
+  // per slot: [A_0..A_{n-1} | B_0..B_{n-1} | A_0,B_0,A_1,B_1,...]
+  std::vector<fr_t*> table(nslots * 4 * ncirc);
+  auto slot_A = [&](size_t slot) { return d_ptrs.p + slot * 4 * ncirc; };
+  auto slot_B = [&](size_t slot) { return d_ptrs.p + slot * 4 * ncirc + ncirc; };
+  auto slot_AB = [&](size_t slot) { return d_ptrs.p + slot * 4 * ncirc + 2 * ncirc; };
+  auto layer_cur = [&](size_t layer_id, bool& replicated_layer) {
     const size_t len_g = circuits[0]->layer_len_global(layer_id);
-    bool sharded = G > 1 && circuits[0]->layer_is_sharded(layer_id);
-    const bool replicated_layer = G > 1 && !sharded;
-    // |A| = |B| = |C| = len/2 globally; per rank len/(2G) when sharded
-    size_t cur = replicated_layer ? len_g / 2 : len_g / 2 / (size_t)G;
+    replicated_layer = G > 1 && !circuits[0]->layer_is_sharded(layer_id);
+    return replicated_layer ? len_g / 2 : len_g / 2 / (size_t)G;  // |A| = |B| = |C| on this rank
+  };
+  for (size_t slot = 0; slot < nslots; slot++) {
     for (int k = 0; k < ncirc; k++) {
-      hA[k] = replicated_layer ? circuits[k]->layer_rep(layer_id) : circuits[k]->layer_local(layer_id);
-      hB[k] = hA[k] + cur;
+      fr_t *pa, *pb;
+      if (slot == num_layers) {
+        pa = tail.p + (size_t)(2 * k) * G;
+        pb = tail.p + (size_t)(2 * k + 1) * G;
+      } else {
+        bool rep;
+        size_t cur0 = layer_cur(slot, rep);
+        pa = rep ? circuits[k]->layer_rep(slot) : circuits[k]->layer_local(slot);
+        pb = pa + cur0;
+      }
+      table[slot * 4 * ncirc + k] = pa;
+      table[slot * 4 * ncirc + ncirc + k] = pb;
+      table[slot * 4 * ncirc + 2 * ncirc + 2 * k] = pa;
+      table[slot * 4 * ncirc + 2 * ncirc + 2 * k + 1] = pb;
     }
-    upload_ptrs();
+  }
+  LB_CUDA_CHECK(cudaMemcpyAsync(d_ptrs.p, table.data(), table.size() * sizeof(fr_t*), cudaMemcpyHostToDevice, c->st));
+  c->sync();
+  for (size_t layer_id = num_layers; layer_id-- > 0;) {
+    bool replicated_layer;
+    size_t cur = layer_cur(layer_id, replicated_layer);
+    bool sharded = G > 1 && !replicated_layer;
+    fr_t* const* dA = slot_A(layer_id);
+    fr_t* const* dB = slot_B(layer_id);
+    fr_t* const* dAB = slot_AB(layer_id);
     // poly_C = eq(rand), grand_product.rs:122
     if (sharded)
       eq_evals_shard(c, rand, 0, rand.size(), eqbuf.p);
@@ -669,13 +687,11 @@ static GPAProof prove_gpa(Ctx* c, std::vector<Circuit*>& circuits, std::vector<f
     Finalize fz = c->fin_begin();
     for (;;) {
       if (sharded && cur == 1) {  // all-gather the G-element remainders; the tail rounds run replicated
-        comm_gather_heads(c, d_AB.p, nullptr, 0, 2 * ncirc, tail.p);
+        comm_gather_heads(c, dAB, nullptr, 0, 2 * ncirc, tail.p);
         comm_gather_heads(c, nullptr, Ccur, 0, 1, tail.p + (size_t)2 * ncirc * G);
-        for (int k = 0; k < ncirc; k++) {
-          hA[k] = tail.p + (size_t)(2 * k) * G;
-          hB[k] = tail.p + (size_t)(2 * k + 1) * G;
-        }
-        upload_ptrs();
+        dA = slot_A(num_layers);
+        dB = slot_B(num_layers);
+        dAB = slot_AB(num_layers);
         Ccur = tail.p + (size_t)2 * ncirc * G;
         Cnext = eqbuf2.p;
         cur = (size_t)G;
@@ -685,14 +701,16 @@ static GPAProof prove_gpa(Ctx* c, std::vector<Circuit*>& circuits, std::vector<f
       if (cur <= 1) break;
       if (!have_evals) {  // first round of a phase; later rounds come out of the fused bind+eval kernel
         fz = c->fin_begin();
-        launch_sumcheck_eval_cubic(d_A.p, d_B.p, Ccur, ncirc, cur / 2, fz, c->st);
+        launch_sumcheck_eval_cubic(dA, dB, Ccur, ncirc, cur / 2, fz, c->st);
         g_launches += 1;
       }
       size_t half = cur / 2;
+      auto tp0 = std::chrono::steady_clock::now();
       if (sharded || fz.mapped)
         c->fin_wait(fz, ev.data(), 3 * ncirc);
       else
         c->d2h(ev.data(), c->d_small, ev.size() * sizeof(fr_t));
+      auto tp1 = std::chrono::steady_clock::now();
       fr_t c0 = fr_zero(), c2 = fr_zero(), c3 = fr_zero();
       for (int k = 0; k < ncirc; k++) {  // sumcheck.rs:95-97
         c0 = fr_add(c0, fr_mul(ev[3 * k], coeff_vec[k]));
@@ -704,30 +722,33 @@ static GPAProof prove_gpa(Ctx* c, std::vector<Circuit*>& circuits, std::vector<f
       unipoly_append(coeffs, transcript);
       fr_t r_j = transcript.challenge_scalar("challenge_nextround");
       rand_prod.push_back(r_j);
+      auto tp2 = std::chrono::steady_clock::now();
       if (half > 1) {
         // bind with r_j and evaluate the next round in one pass (sumcheck.rs:116-120 + 63-89)
         fz = c->fin_begin();
-        launch_sumcheck_bind_eval_cubic(d_A.p, d_B.p, Ccur, Cnext, ncirc, half, r_j, fz, c->st);
+        launch_sumcheck_bind_eval_cubic(dA, dB, Ccur, Cnext, ncirc, half, r_j, fz, c->st);
         g_launches += 1;
         std::swap(Ccur, Cnext);
         have_evals = true;
       } else {
-        launch_bind_top_ptrs(d_AB.p, 2 * ncirc, half, r_j, c->st);
+        launch_bind_top_ptrs(dAB, 2 * ncirc, half, r_j, c->st);
         launch_bind_top(Ccur, 0, 1, half, r_j, c->st);
         g_launches += 2;
         have_evals = false;
+      }
+      auto tp3 = std::chrono::steady_clock::now();
+      if (c->span_sync) {  // where a grand-product round goes: waiting for the device, host glue, launch call
+        c->spans["GPA.round wait"] += std::chrono::duration<double, std::milli>(tp1 - tp0).count();
+        c->spans["GPA.round host"] += std::chrono::duration<double, std::milli>(tp2 - tp1).count();
+        c->spans["GPA.round launch"] += std::chrono::duration<double, std::milli>(tp3 - tp2).count();
       }
       e = unipoly_evaluate(coeffs, r_j);
       lp.proof.push_back(unipoly_compress(coeffs));
       cur = half;
     }
-    // claims_prod = (A_k[0], B_k[0]); gather the 2*ncirc scalars
-    for (int k = 0; k < ncirc; k++) {
-      LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin + (size_t)(2 * k) * 32, hA[k], 32, cudaMemcpyDeviceToHost, c->st));
-      LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin + (size_t)(2 * k + 1) * 32, hB[k], 32, cudaMemcpyDeviceToHost, c->st));
-    }
-    c->sync();
-    memcpy(fin.data(), c->h_pin, fin.size() * 32);
+    // claims_prod = (A_k[0], B_k[0]): pack the 2*ncirc heads on the device, one small transfer
+    pack_heads(c, dAB, nullptr, 0, 2 * ncirc, c->d_small + 1024);
+    c->d2h(fin.data(), c->d_small + 1024, fin.size() * sizeof(fr_t));
     for (int k = 0; k < ncirc; k++) {
       lp.claims_prod_left.push_back(fin[2 * k]);
       lp.claims_prod_right.push_back(fin[2 * k + 1]);

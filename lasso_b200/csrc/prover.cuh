@@ -224,5 +224,6 @@ void comm_allreduce_fr(Ctx*, fr_t* d_buf, int count);
 // every rank holds one element per polynomial (ptrs[k][0], or base[k*stride] when ptrs == null);
 // d_out[k*G + g] <- rank g's element of polynomial k
 void comm_gather_heads(Ctx*, fr_t* const* d_ptrs, const fr_t* base, size_t stride, int npolys, fr_t* d_out);
+void pack_heads(Ctx*, fr_t* const* d_ptrs, const fr_t* base, size_t stride, int npolys, fr_t* d_out);
 
 }  // namespace lb
