@@ -85,7 +85,9 @@ int lasso_materialize_subtables(lasso_ctx*, int strategy, int C, int log_M, int 
 int lasso_gather_lookup_polys(lasso_ctx*, int strategy, int C, int log_M, int log_R, const uint64_t* const* nz,
                               size_t s, uint64_t* const* E_out);
 /* VariableBaseMSM::msm  msm/mod.rs:36-40 (bases: n affine points, scalars: n Fr) -> one extended point,
- * normalised (z = 1).  Same group element as the reference's msm_bigint_wnaf. */
+ * normalised (z = 1).  Same group element as the reference's msm_bigint_wnaf.  After lasso_ctx_init_comm this
+ * (and lasso_commit_rows) is collective: each rank passes ITS SHARD of the terms (any split), partial points are
+ * all-gathered over NCCL and added, every rank receives the full sum. */
 int lasso_msm(lasso_ctx*, const uint64_t* bases_affine, const uint64_t* scalars, size_t n, uint64_t out_xytz[16]);
 /* DensePolynomial::commit_inner  poly/dense_mlpoly.rs:109-128 (+ Commitments::batch_commit
  * poly/commitments.rs:84-93 with blind = 0): Z viewed as L_size rows of R_size; gens_affine holds the

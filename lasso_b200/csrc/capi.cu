@@ -212,8 +212,19 @@ static void msm_variable_base(Ctx* c, const uint64_t* bases_affine, size_t nbase
   if (nw > kMsmFullWindows) nw = kMsmFullWindows;
   DBuf<pt_ext> part(c, msm_partials_count((int)nrows, (int)ncols, nw));
   DBuf<fq_t> oe(c, nrows * 4);
-  launch_msm_rows(tab.p, nbases, 0, canon.p, 8, ncols, (int)nrows, (int)ncols, nw, 1, 0, part.p, oe.p, nullptr, nullptr, c->st);
-  g_launches += 4;
+  if (c->world == 1) {
+    launch_msm_rows(tab.p, nbases, 0, canon.p, 8, ncols, (int)nrows, (int)ncols, nw, 1, 0, part.p, oe.p, nullptr, nullptr, c->st);
+    g_launches += 4;
+  } else {
+    // collective: every rank passed ITS shard of the terms; partial points are all-gathered and added
+    // ("final bucket-sum reduce over NVLink" = gather-then-add, group addition is not an NCCL reduction)
+    DBuf<uint32_t> raw(c, (size_t)(c->world + 1) * nrows * 32);
+    uint32_t* mine = raw.p + (size_t)c->world * nrows * 32;
+    launch_msm_rows(tab.p, nbases, 0, canon.p, 8, ncols, (int)nrows, (int)ncols, nw, 1, 0, part.p, nullptr, nullptr, mine, c->st);
+    comm_allgather(c, mine, raw.p, nrows * 128);
+    launch_sum_raw_points(raw.p, c->world, (int)nrows, nullptr, nullptr, oe.p, c->st);
+    g_launches += 5;
+  }
   LB_CUDA_CHECK(cudaMemcpyAsync(out_ext, oe.p, nrows * 128, cudaMemcpyDeviceToHost, c->st));
   c->sync();
 }

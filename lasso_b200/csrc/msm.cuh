@@ -25,7 +25,8 @@ void launch_msm_rows(const pt_niels* table, size_t table_stride, int shifted, co
                      size_t row_stride, int nrows, int ncols, int nw, int col_mul, int col_add, pt_ext* partials,
                      fq_t* out_ext, uint32_t* out_comp, uint32_t* out_raw, cudaStream_t st);
 // raw[(k*nrows + row)*32 ..): (X,Y,Z,T) of source k; adds the nsrc sources per row (cross-GPU gather-then-add)
-void launch_sum_raw_points(const uint32_t* raw, int nsrc, int nrows, uint32_t* out_raw, uint32_t* out_comp, cudaStream_t st);
+void launch_sum_raw_points(const uint32_t* raw, int nsrc, int nrows, uint32_t* out_raw, uint32_t* out_comp, fq_t* out_ext,
+                           cudaStream_t st);
 void launch_combine_points(const fq_t* in_ext, int n, fq_t* out_ext, uint32_t* out_comp, cudaStream_t st);
 
 inline int msm_windows_for_bits(unsigned max_bits) {

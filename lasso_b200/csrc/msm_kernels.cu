@@ -461,7 +461,8 @@ void launch_msm_rows(const pt_niels* table, size_t table_stride, int shifted, co
 // (k < nsrc: the all-gathered per-rank partials, plus optionally a replicated tail term).  One warp-lane
 // per row adds the nsrc points; output raw again (few rows -> host normalisation) and/or compressed.
 __global__ void __launch_bounds__(64)
-    sum_raw_points_kernel(const uint32_t* raw, int nsrc, int nrows, uint32_t* out_raw, uint32_t* out_comp) {
+    sum_raw_points_kernel(const uint32_t* raw, int nsrc, int nrows, uint32_t* out_raw, uint32_t* out_comp,
+                          fq_t* out_ext) {
   int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= nrows) return;
   pt_ext acc = pt_identity();
@@ -486,17 +487,26 @@ __global__ void __launch_bounds__(64)
       out_raw[(size_t)row * 32 + 24 + l] = acc.T.v[l];
     }
   }
-  if (out_comp) {
+  if (out_comp || out_ext) {
     fq_t x, y;
     pt_to_affine_canonical(acc, x, y);
-    uint32_t c[8];
-    pt_compress_canonical(x, y, c);
+    if (out_comp) {
+      uint32_t c[8];
+      pt_compress_canonical(x, y, c);
 #pragma unroll
-    for (int l = 0; l < 8; l++) out_comp[(size_t)row * 8 + l] = c[l];
+      for (int l = 0; l < 8; l++) out_comp[(size_t)row * 8 + l] = c[l];
+    }
+    if (out_ext) {
+      out_ext[(size_t)row * 4 + 0] = fq_to_ark(x);
+      out_ext[(size_t)row * 4 + 1] = fq_to_ark(y);
+      out_ext[(size_t)row * 4 + 2] = fq_to_ark(fq_mul(x, y));
+      out_ext[(size_t)row * 4 + 3] = fq_to_ark(fq_one());
+    }
   }
 }
-void launch_sum_raw_points(const uint32_t* raw, int nsrc, int nrows, uint32_t* out_raw, uint32_t* out_comp, cudaStream_t st) {
-  sum_raw_points_kernel<<<(nrows + 63) / 64, 64, 0, st>>>(raw, nsrc, nrows, out_raw, out_comp);
+void launch_sum_raw_points(const uint32_t* raw, int nsrc, int nrows, uint32_t* out_raw, uint32_t* out_comp, fq_t* out_ext,
+                           cudaStream_t st) {
+  sum_raw_points_kernel<<<(nrows + 63) / 64, 64, 0, st>>>(raw, nsrc, nrows, out_raw, out_comp, out_ext);
 }
 
 // sum of a few extended points + normalisation (used to add a blind*h term or combine rows)

@@ -224,7 +224,7 @@ static std::vector<uint8_t> msm_rows(Ctx* c, const Gens& g, const void* d_scal, 
   if (few) {
     uint32_t xyzt[8 * 32];
     if (nsrc > 1) {
-      launch_sum_raw_points(raw.p, nsrc, nrows, mine, nullptr, c->st);
+      launch_sum_raw_points(raw.p, nsrc, nrows, mine, nullptr, nullptr, c->st);
       g_launches += 1;
       c->d2h(xyzt, mine, (size_t)nrows * 128);
     } else {
@@ -235,7 +235,7 @@ static std::vector<uint8_t> msm_rows(Ctx* c, const Gens& g, const void* d_scal, 
     return out;
   }
   DBuf<uint32_t> comp(c, (size_t)nrows * 8);
-  launch_sum_raw_points(raw.p, nsrc, nrows, nullptr, comp.p, c->st);
+  launch_sum_raw_points(raw.p, nsrc, nrows, nullptr, comp.p, nullptr, c->st);
   g_launches += 1;
   c->d2h(out.data(), comp.p, out.size());
   return out;

@@ -43,6 +43,19 @@ for kind, C, log_m, log_r, n, same in cases:
         print("case kind=%d C=%d log_m=%d n=%d world=%d: %s (%.1f ms, commit_ok=%s, first diverging challenge=%s)" % (
             kind, C, log_m, n, world, "OK" if good else "MISMATCH", dt * 1e3, com == ref["commitment"], first_bad), flush=True)
         ok = ok and good
+# collective MSM: each rank holds a shard of the terms; the sum over ranks must equal the oracle's MSM of all terms
+n_all = 3000
+rng = np.random.default_rng(99)
+bases_all = np.ascontiguousarray(ol.generators(9002)[:n_all])
+sc_all = ol.rand_fr(rng, n_all)
+lo, hi = n_all * rank // world, n_all * (rank + 1) // world
+got = lb.msm(ctx, np.ascontiguousarray(bases_all[lo:hi]), np.ascontiguousarray(sc_all[lo:hi]))
+if rank == 0:
+    ref = np.zeros(16, dtype=np.uint64)
+    ol.lib().orc_msm(ol.P(bases_all), ol.P(sc_all), ol.sz(n_all), 1, ol.P(ref))
+    same = ol.lib().orc_point_eq(ol.P(got), ol.P(ref)) == 1
+    print("collective msm over %d ranks: %s" % (world, "OK" if same else "MISMATCH"), flush=True)
+    ok = ok and same
 dist.barrier()
 dist.destroy_process_group()
 if rank == 0:
