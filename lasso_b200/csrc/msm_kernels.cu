@@ -219,8 +219,11 @@ __global__ void __launch_bounds__(MSM_T)
   // accumulate: thread t owns the contiguous slice [lo, hi) of the sorted list.  ONE flat loop over the
   // slice (every lane of the warp executes the same number of point additions); a change of bucket only
   // triggers a short, predicated flush.  (Looping run by run made the warp pay max-over-lanes per run.)
+  // Slices: N >= T -> equal shares; N < T -> the first N threads take one entry each, so that the threads
+  // holding entries are always a contiguous range (the stitch below relies on it).
+  auto slice_lo = [&](int t) { return N >= MSM_T ? (int)(((long long)t * N) / MSM_T) : min(t, N); };
   {
-    const int lo = (int)(((long long)tid * N) / MSM_T), hi = (int)(((long long)(tid + 1) * N) / MSM_T);
+    const int lo = slice_lo(tid), hi = slice_lo(tid + 1);
     if (lo < hi) {
       int b;  // bucket containing position lo: largest b with off[b] <= lo
       {
@@ -270,17 +273,36 @@ __global__ void __launch_bounds__(MSM_T)
       flush(b, run_start, hi, acc);
     }
   }
+  // stitch partial runs into their buckets.  A bucket that is not wholly inside one thread's slice was split
+  // over a CONTIGUOUS range of threads [t_lo, t_hi]: t_lo holds its tail partial (plast) for the bucket — or a
+  // head partial if the bucket starts exactly at its slice — and every later thread of the range a head
+  // partial (pfirst).  Step 1: segmented suffix reduction of the head partials keyed by bucket (log steps,
+  // stops as soon as no run is longer than the stride: one step for uniform digits, 7 for a window whose
+  // digits all fall into one bucket — a serial walk there cost up to 127 additions on one lane while the
+  // other warps waited at the barrier).  Step 2: the owner of a bucket adds <= 2 values.
   __syncthreads();
-  // stitch partial runs into their buckets: thread t owns bucket t+1.  A bucket that is not wholly
-  // inside one thread's slice was split over a CONTIGUOUS range of threads [t_lo, t_hi], each holding
-  // exactly one partial for it, so the owner walks just that range (typically 2-3 threads) instead of
-  // scanning all 128 slots — scanning made every warp execute ~64 divergent point additions.
   {
+    const int myk = sm.pf_b[tid];  // written by this thread (or 0)
+    pt_ext mine;
+    if (myk) mine = sm_load_pt(sm.pfirst, MSM_T, tid);
+    for (int d = 1; d < MSM_T; d <<= 1) {
+      const bool work = myk && (tid + d < MSM_T) && sm.pf_b[tid + d] == myk;
+      if (!__syncthreads_or(work)) break;  // barrier: the previous step's stores are visible
+      pt_ext other;
+      if (work) other = sm_load_pt(sm.pfirst, MSM_T, tid + d);
+      __syncthreads();
+      if (work) {
+        mine = pt_add(mine, other);
+        sm_store_pt(sm.pfirst, MSM_T, tid, mine);
+      }
+    }
+    // (loop exit is always through a barrier or after the last step's store: sync before the owners read)
+    __syncthreads();
     const int b = tid + 1;
     const int s0 = sm.off[b], s1 = sm.off[b + 1];
     if (s1 > s0) {
-      auto slice_lo = [&](int t) { return (int)(((long long)t * N) / MSM_T); };
       auto thread_of = [&](int pos) {
+        if (N < MSM_T) return pos;
         int t = (int)(((long long)pos * MSM_T) / N);
         if (t > MSM_T - 1) t = MSM_T - 1;
         while (t + 1 < MSM_T && slice_lo(t + 1) <= pos) t++;
@@ -289,13 +311,11 @@ __global__ void __launch_bounds__(MSM_T)
       };
       const int t_lo = thread_of(s0), t_hi = thread_of(s1 - 1);
       if (t_lo != t_hi) {
-        pt_ext acc = pt_identity();
-        for (int t = t_lo; t <= t_hi; t++) {
-          if (sm.pf_b[t] == b)
-            acc = pt_add(acc, sm_load_pt(sm.pfirst, MSM_T, t));
-          else if (sm.pl_b[t] == b)
-            acc = pt_add(acc, sm_load_pt(sm.plast, MSM_T, t));
-        }
+        const bool has_l = sm.pl_b[t_lo] == b;
+        const int t_f = t_lo + (has_l ? 1 : 0);
+        const bool has_f = t_f <= t_hi && sm.pf_b[t_f] == b;
+        pt_ext acc = has_l ? sm_load_pt(sm.plast, MSM_T, t_lo) : sm_load_pt(sm.pfirst, MSM_T, t_f);
+        if (has_l && has_f) acc = pt_add(acc, sm_load_pt(sm.pfirst, MSM_T, t_f));
         sm_store_pt(sm.bucket, MSM_NB + 1, b, acc);
       }
     }
