@@ -9,14 +9,16 @@
 //     (s + 0x80..80, then byte w minus 128): digits are independent per window, no carry chain;
 //   * the generators are expanded once into a table T[w][j] = 2^(8w) G_j in affine-niels form
 //     (96 B/point), so every window of a row lands in ONE bucket set and no doublings are needed;
-//   * one CTA per (window, row, column-chunk): counting sort of the chunk's digits in shared memory,
-//     then every thread adds an equal-sized contiguous slice of the sorted list (robust against
-//     skewed digits, e.g. 0/1-valued LT tables), bucket partials are stitched, and the weighted
-//     bucket sum  sum_b b*B_b  is a suffix scan + tree reduction over the 128 buckets;
-//   * a finish kernel adds the per-(window, chunk) partials of a row, normalises (one Fq inversion
-//     per row) and emits arkworks-layout points + compressed bytes.
+//   * one CTA per (row, column-chunk), ALL windows: counting sort of the chunk's (column, window)
+//     digits in shared memory, then every thread adds an equal-sized contiguous slice of the sorted
+//     list (robust against skewed digits, e.g. 0/1-valued LT tables), split buckets are stitched by
+//     a segmented log-step reduction, and the weighted bucket sum  sum_b b*B_b  is a suffix scan +
+//     tree reduction over the 128 buckets — once per CTA, not once per window;
+//   * a finish kernel adds the per-chunk partials of a row, normalises (one Fq inversion per row)
+//     and emits arkworks-layout points + compressed bytes.
 // For bases without a precomputed table (variable-base lasso_msm) the same kernels run with the
-// single window-0 table and the finish kernel does the 8-doubling Horner combination instead.
+// single window-0 table, one CTA per (window, row, chunk), and the finish kernel does the 8-doubling
+// Horner combination instead.
 // Integer-ALU bound (7 Fq muls per bucket add), not HBM bound: reported as point-adds/s.
 #if defined(__CUDACC__)
 #define LB_FQ_MUL_ATTR static __host__ __device__ __noinline__
@@ -111,29 +113,32 @@ void launch_canonicalize(const fr_t* in, fr_t* out, size_t n, unsigned* d_max_bi
   canonicalize_kernel<<<(unsigned)b, 256, 0, st>>>(in, out, n, d_max_bits);
 }
 
-// signed digit of window w (c = 8): byte w of (s + 0x80..80) minus 128
+// signed digits (c = 8): byte w of (s + 0x80..80) minus 128.  MsmDigits biases the scalar once; digit(w) with a
+// compile-time w (the window loops are fully unrolled) is a shift and a mask.
 template <int SL>
-__device__ __forceinline__ int msm_digit(const uint32_t* s, int w);
+struct MsmDigits;
 template <>
-__device__ __forceinline__ int msm_digit<1>(const uint32_t* s, int w) {
-  uint64_t v = (uint64_t)s[0] + 0x8080808080ull;
-  return (int)((v >> (8 * w)) & 0xff) - 128;
-}
+struct MsmDigits<1> {
+  static constexpr int kMaxWindows = 5;
+  uint64_t v;
+  __device__ __forceinline__ explicit MsmDigits(const uint32_t* s) : v((uint64_t)s[0] + 0x8080808080ull) {}
+  __device__ __forceinline__ int digit(int w) const { return (int)((v >> (8 * w)) & 0xff) - 128; }
+};
 template <>
-__device__ __forceinline__ int msm_digit<8>(const uint32_t* s, int w) {
-  // add 0x80808080 to every limb with carry, only as far as limb w/4
-  uint32_t carry = 0, limb = 0;
-  int top = w >> 2;
+struct MsmDigits<8> {
+  static constexpr int kMaxWindows = 32;
+  uint32_t b[8];
+  __device__ __forceinline__ explicit MsmDigits(const uint32_t* s) {
+    uint32_t carry = 0;
 #pragma unroll
-  for (int l = 0; l < 8; l++) {
-    if (l <= top) {
+    for (int l = 0; l < 8; l++) {
       uint64_t t = (uint64_t)s[l] + 0x80808080u + carry;
-      limb = (uint32_t)t;
+      b[l] = (uint32_t)t;
       carry = (uint32_t)(t >> 32);
     }
   }
-  return (int)((limb >> (8 * (w & 3))) & 0xff) - 128;
-}
+  __device__ __forceinline__ int digit(int w) const { return (int)((b[w >> 2] >> (8 * (w & 3))) & 0xff) - 128; }
+};
 
 // ---------------------------------------------------------------- the bucket kernel
 struct MsmSmem {
@@ -150,15 +155,21 @@ struct MsmSmem {
 template <int SL>
 __global__ void __launch_bounds__(MSM_T)
     msm_bucket_kernel(const pt_niels* table, size_t table_stride, int shifted, const uint32_t* scalars,
-                      size_t row_stride /*in scalars*/, int ncols, int chunk_cols, int col_mul, int col_add,
-                      pt_ext* partials) {
+                      size_t row_stride /*in scalars*/, int ncols, int chunk_cols, int nw, int wpc, int col_mul,
+                      int col_add, pt_ext* partials) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   MsmSmem& sm = *reinterpret_cast<MsmSmem*>(smem_raw);
-  const int w = blockIdx.x, row = blockIdx.y, chunk = blockIdx.z, tid = threadIdx.x;
+  // this CTA: windows [w0, w1) of the columns [c_begin, c_end) of `row`.  With a shifted table every window
+  // has the same bucket weights, so all of them share ONE bucket set (wpc = nw): one weighted bucket sum per
+  // CTA instead of one per window.  Without it (variable-base) wpc = 1 and the finish kernel does the Horner.
+  const int wg = blockIdx.x, row = blockIdx.y, chunk = blockIdx.z, tid = threadIdx.x;
+  const int w0 = wg * wpc, w1 = min(nw, w0 + wpc), nwin = w1 - w0;
   const int c_begin = chunk * chunk_cols;
   const int c_end = min(ncols, c_begin + chunk_cols);
-  const pt_niels* tw = shifted ? table + (size_t)w * table_stride : table;
+  const size_t wstride = shifted ? table_stride : 0;
+  const pt_niels* tw = table + (size_t)w0 * wstride;
   const uint32_t* srow = scalars + ((size_t)row * row_stride) * SL;
+  constexpr int MAXW = MsmDigits<SL>::kMaxWindows;
 
   for (int b = tid; b < MSM_NB + 2; b += MSM_T) sm.cnt[b] = 0;
   sm.pf_b[tid] = 0;
@@ -169,8 +180,14 @@ __global__ void __launch_bounds__(MSM_T)
     uint32_t s[SL];
 #pragma unroll
     for (int l = 0; l < SL; l++) s[l] = srow[(size_t)c * SL + l];
-    int d = msm_digit<SL>(s, w);
-    if (d) atomicAdd(&sm.cnt[d < 0 ? -d : d], 1);
+    const MsmDigits<SL> dg(s);
+#pragma unroll
+    for (int w = 0; w < MAXW; w++) {
+      if (w >= w0 && w < w1) {
+        int d = dg.digit(w);
+        if (d) atomicAdd(&sm.cnt[d < 0 ? -d : d], 1);
+      }
+    }
   }
   __syncthreads();
   // exclusive scan over buckets 1..128 (one warp, 4 buckets per lane)
@@ -201,18 +218,24 @@ __global__ void __launch_bounds__(MSM_T)
   __syncthreads();
   const int N = sm.off[MSM_NB + 1];
   if (N == 0) {
-    if (tid == 0) partials[((size_t)row * gridDim.x + w) * gridDim.z + chunk] = pt_identity();
+    if (tid == 0) partials[((size_t)row * gridDim.x + wg) * gridDim.z + chunk] = pt_identity();
     return;
   }
-  // pass 2: scatter (column-in-chunk | sign) into the sorted list
+  // pass 2: scatter ((column-in-chunk * nwin + window-in-group) | sign) into the sorted list
   for (int c = c_begin + tid; c < c_end; c += MSM_T) {
     uint32_t s[SL];
 #pragma unroll
     for (int l = 0; l < SL; l++) s[l] = srow[(size_t)c * SL + l];
-    int d = msm_digit<SL>(s, w);
-    if (d) {
-      int pos = atomicAdd(&sm.cur[d < 0 ? -d : d], 1);
-      sm.list[pos] = (uint16_t)((c - c_begin) | (d < 0 ? 0x8000 : 0));
+    const MsmDigits<SL> dg(s);
+#pragma unroll
+    for (int w = 0; w < MAXW; w++) {
+      if (w >= w0 && w < w1) {
+        int d = dg.digit(w);
+        if (d) {
+          int pos = atomicAdd(&sm.cur[d < 0 ? -d : d], 1);
+          sm.list[pos] = (uint16_t)(((c - c_begin) * nwin + (w - w0)) | (d < 0 ? 0x8000 : 0));
+        }
+      }
     }
   }
   __syncthreads();
@@ -252,14 +275,18 @@ __global__ void __launch_bounds__(MSM_T)
       // software pipeline: the next point's 96 B are in flight while the current addition runs.
       // local column c -> generator index c * col_mul + col_add (col_mul = #GPUs when one proof is sharded
       // by the low index bits: this rank owns the columns congruent to its rank)
+      auto entry_ptr = [&](uint16_t ee) {
+        const int idx = ee & 0x7fff, cl = idx / nwin, wl = idx - cl * nwin;
+        return tw + (size_t)wl * wstride + (size_t)(c_begin + cl) * col_mul + col_add;
+      };
       uint16_t e = sm.list[lo];
-      pt_niels nn = ld_niels(tw + (size_t)(c_begin + (e & 0x7fff)) * col_mul + col_add);
+      pt_niels nn = ld_niels(entry_ptr(e));
       for (int p = lo; p < hi; p++) {
         const uint16_t ecur = e;
         const pt_niels ncur = nn;
         if (p + 1 < hi) {
           e = sm.list[p + 1];
-          nn = ld_niels(tw + (size_t)(c_begin + (e & 0x7fff)) * col_mul + col_add);
+          nn = ld_niels(entry_ptr(e));
         }
         if (p >= sm.off[b + 1]) {  // the bucket is exhausted (it received >= 1 point): flush, move on
           flush(b, run_start, p, acc);
@@ -348,7 +375,7 @@ __global__ void __launch_bounds__(MSM_T)
       inA = !inA;
       __syncthreads();
     }
-    if (tid == 0) partials[((size_t)row * gridDim.x + w) * gridDim.z + chunk] = mine;
+    if (tid == 0) partials[((size_t)row * gridDim.x + wg) * gridDim.z + chunk] = mine;
   }
 }
 
@@ -428,22 +455,37 @@ __global__ void __launch_bounds__(32)
   }
 }
 
-// Column-chunk size: whole rows per CTA when there are many rows; with only a few rows (Bulletproofs
-// rounds) split the columns so that at least ~2 CTAs per SM exist.
-static int msm_chunk_cols(int nrows, int ncols, int nw) {
-  long long ctas = (long long)nrows * nw;
+// Launch geometry.  wpc = windows per CTA (all of them over a shifted table), ngroups = window groups,
+// chunk_cols = columns per CTA: at most MSM_CHUNK list entries (columns x windows) per CTA; with only a few
+// rows (Bulletproofs rounds) the columns are split further so that about one CTA per SM exists.
+struct MsmGeom {
+  int wpc, ngroups, chunk_cols, nchunks;
+};
+static MsmGeom msm_geometry(int nrows, int ncols, int nw, int shifted) {
+  MsmGeom g;
+  g.wpc = shifted ? nw : 1;
+  g.ngroups = (nw + g.wpc - 1) / g.wpc;
+  int cap = MSM_CHUNK / g.wpc;  // columns whose digits fit the sorted list
+  if (cap < 1) cap = 1;
+  long long ctas = (long long)nrows * g.ngroups;
   int want = (int)((1LL * kNumSMs + ctas - 1) / ctas);  // chunks needed for ~1 CTA per SM
   int chunk = want > 1 ? (ncols + want - 1) / want : ncols;
-  if (chunk < 256) chunk = 256;
-  if (chunk > MSM_CHUNK) chunk = MSM_CHUNK;
+  int floor_cols = 1024 / g.wpc;  // keep >= ~1k entries per CTA: the bucket reduction is a fixed 14 steps
+  if (floor_cols < 8) floor_cols = 8;
+  if (chunk < floor_cols) chunk = floor_cols;
+  if (chunk > cap) chunk = cap;
   if (chunk > ncols) chunk = ncols;
   if (chunk < 1) chunk = 1;
-  return chunk;
+  g.chunk_cols = chunk;
+  g.nchunks = (ncols + chunk - 1) / chunk;
+  if (g.nchunks < 1) g.nchunks = 1;
+  return g;
 }
-size_t msm_partials_count(int nrows, int ncols, int nw) {
-  int chunk_cols = msm_chunk_cols(nrows, ncols, nw);
-  int nchunks = (ncols + chunk_cols - 1) / chunk_cols;
-  return (size_t)nrows * nw * nchunks;
+size_t msm_partials_count(int nrows, int ncols, int nw) {  // upper bound over both table kinds
+  if (nw < 1) nw = 1;
+  MsmGeom a = msm_geometry(nrows, ncols, nw, 0), b = msm_geometry(nrows, ncols, nw, 1);
+  size_t ca = (size_t)a.ngroups * a.nchunks, cb = (size_t)b.ngroups * b.nchunks;
+  return (size_t)nrows * (ca > cb ? ca : cb);
 }
 
 void launch_msm_rows(const pt_niels* table, size_t table_stride, int shifted, const void* scalars, int scalar_limbs,
@@ -451,9 +493,8 @@ void launch_msm_rows(const pt_niels* table, size_t table_stride, int shifted, co
                      fq_t* out_ext, uint32_t* out_comp, uint32_t* out_raw, cudaStream_t st) {
   if (nrows <= 0) return;
   if (nw < 1) nw = 1;
-  int chunk_cols = msm_chunk_cols(nrows, ncols, nw);
-  int nchunks = (ncols + chunk_cols - 1) / chunk_cols;
-  if (nchunks < 1) nchunks = 1;
+  const MsmGeom g = msm_geometry(nrows, ncols, nw, shifted);
+  const int nchunks = g.nchunks, chunk_cols = g.chunk_cols;
   static bool attr_set = false;
   if (!attr_set) {
     LB_CUDA_CHECK(cudaFuncSetAttribute(msm_bucket_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MsmSmem)));
@@ -463,18 +504,18 @@ void launch_msm_rows(const pt_niels* table, size_t table_stride, int shifted, co
   // gridDim.y is limited to 65535 rows per launch
   for (int r0 = 0; r0 < nrows; r0 += 65535) {
     int nr = nrows - r0 < 65535 ? nrows - r0 : 65535;
-    dim3 grid(nw, nr, nchunks);
-    pt_ext* part = partials + (size_t)r0 * nw * nchunks;
+    dim3 grid(g.ngroups, nr, nchunks);
+    pt_ext* part = partials + (size_t)r0 * g.ngroups * nchunks;
     if (scalar_limbs == 1)
       msm_bucket_kernel<1><<<grid, MSM_T, sizeof(MsmSmem), st>>>(
           table, table_stride, shifted, (const uint32_t*)scalars + (size_t)r0 * row_stride, row_stride, ncols,
-          chunk_cols, col_mul, col_add, part);
+          chunk_cols, nw, g.wpc, col_mul, col_add, part);
     else
       msm_bucket_kernel<8><<<grid, MSM_T, sizeof(MsmSmem), st>>>(
           table, table_stride, shifted, (const uint32_t*)scalars + (size_t)r0 * row_stride * 8, row_stride, ncols,
-          chunk_cols, col_mul, col_add, part);
+          chunk_cols, nw, g.wpc, col_mul, col_add, part);
   }
-  msm_finish_kernel<<<nrows, 32, 0, st>>>(partials, nrows, nw, nchunks, shifted, out_ext, out_comp, out_raw);
+  msm_finish_kernel<<<nrows, 32, 0, st>>>(partials, nrows, g.ngroups, nchunks, shifted, out_ext, out_comp, out_raw);
 }
 
 // Cross-GPU "bucket-sum reduce": raw[(k * nrows + row) * 32 ..] = partial (X,Y,Z,T) of source k for `row`

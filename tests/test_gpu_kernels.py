@@ -157,6 +157,34 @@ def test_msm_vs_oracle(ctx, n, bits):
         lb.msm(ctx, bases, S[:-1] if n > 1 else np.zeros((0, 4), dtype=np.uint64))  # Err(min_len)
 
 
+@pytest.mark.parametrize("n,vals", [(3000, [5]), (2000, [1, 2, 3]), (700, [128, 129, 0x8080]), (130, [1]),
+                                    (6000, [ol.L_FR - 1, 1])])
+def test_msm_skewed_digits(ctx, n, vals):
+    """Every digit of a window in one (or a few) buckets: the split-bucket stitch runs all its log steps."""
+    import lasso_b200 as lb
+
+    bases = np.ascontiguousarray(ol.generators(9002)[:n])
+    S = ol.fr_array([vals[i % len(vals)] for i in range(n)])
+    ref = np.zeros(16, dtype=np.uint64)
+    orc().orc_msm(P(bases), P(S), sz(n), 1, P(ref))
+    got = lb.msm(ctx, bases, S)
+    assert (got[:8] == _affine_of(ref)).all()
+
+
+@pytest.mark.parametrize("L,R,vals", [(8, 2048, [1]), (4, 4096, [0, 1, 255, 256, 65535]), (2, 8192, [7, 1 << 19])])
+def test_commit_rows_skewed(ctx, L, R, vals):
+    """Many rows over shared bases, skewed small scalars (variable-base path; the fixed-base path is covered end to end)."""
+    import lasso_b200 as lb
+
+    gens = np.ascontiguousarray(ol.generators(9002)[: R + 1])
+    Z = ol.fr_array([vals[(i * 7 + i // R) % len(vals)] for i in range(L * R)])
+    ref = np.zeros((L, 16), dtype=np.uint64)
+    orc().orc_commit_rows(P(gens), P(Z), sz(L), sz(R), P(ref))
+    got = lb.commit_rows(ctx, gens, Z, L, R)
+    for i in range(L):
+        assert (got[i][:8] == _affine_of(ref[i])).all()
+
+
 def test_msm_all_zero_and_identity(ctx):
     import lasso_b200 as lb
 
