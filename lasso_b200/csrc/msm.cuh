@@ -21,9 +21,12 @@ size_t msm_partials_count(int nrows, int ncols, int nw);
 // out_comp = nrows x 32 bytes ark-serialize compressed; out_raw = nrows x 128 B un-normalised (X,Y,Z,T)
 // internal limbs for host-side normalisation (host_fq64.hpp) or the cross-GPU gather-then-add.
 // Local column c uses generator index c*col_mul + col_add.
+// mapped != null (nrows <= 8): the un-normalised rows are also written to mapped pinned host memory (32 words per
+// row) and the sequence flag at word 1024 is set to `seq` — no separate copy kernel, the host spins on the flag.
 void launch_msm_rows(const pt_niels* table, size_t table_stride, int shifted, const void* scalars, int scalar_limbs,
                      size_t row_stride, int nrows, int ncols, int nw, int col_mul, int col_add, pt_ext* partials,
-                     fq_t* out_ext, uint32_t* out_comp, uint32_t* out_raw, cudaStream_t st);
+                     fq_t* out_ext, uint32_t* out_comp, uint32_t* out_raw, cudaStream_t st, uint32_t* mapped = nullptr,
+                     uint32_t seq = 0);
 // raw[(k*nrows + row)*32 ..): (X,Y,Z,T) of source k; adds the nsrc sources per row (cross-GPU gather-then-add)
 void launch_sum_raw_points(const uint32_t* raw, int nsrc, int nrows, uint32_t* out_raw, uint32_t* out_comp, fq_t* out_ext,
                            cudaStream_t st);

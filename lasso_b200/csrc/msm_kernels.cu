@@ -402,56 +402,77 @@ __device__ __forceinline__ pt_ext ld_pt(const pt_ext* p) {
 // One warp per row.  out_ext: (x,y,t,z=1) arkworks Montgomery limbs; out_comp: 32 B compressed;
 // out_raw: un-normalised (X, Y, Z, T) internal limbs, 128 B/row — for host-side normalisation (a couple of
 // rows: one inversion is a 265-step serial chain) or for the cross-GPU gather-then-add of partial points.
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(256)
     msm_finish_kernel(const pt_ext* partials, int nrows, int nw, int nchunks, int shifted, fq_t* out_ext,
-                      uint32_t* out_comp, uint32_t* out_raw) {
-  const int row = blockIdx.x, lane = threadIdx.x;
-  if (row >= nrows) return;
-  const pt_ext* p = partials + (size_t)row * nw * nchunks;
-  pt_ext acc = pt_identity();
-  if (shifted) {
-    const int total = nw * nchunks;
-    for (int i = lane; i < total; i += 32) acc = pt_add(acc, ld_pt(p + i));
-    if (total > 1) {
+                      uint32_t* out_comp, uint32_t* out_raw, uint32_t* mapped, uint32_t seq) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row < nrows) {
+    const pt_ext* p = partials + (size_t)row * nw * nchunks;
+    pt_ext acc = pt_identity();
+    if (shifted) {
+      const int total = nw * nchunks;
+      for (int i = lane; i < total; i += 32) acc = pt_add(acc, ld_pt(p + i));
+      if (total > 1) {
 #pragma unroll 1
-      for (int d = 16; d >= 1; d >>= 1) {
-        pt_ext o = shfl_down_pt(acc, d);
-        acc = pt_add(acc, o);
+        for (int d = 16; d >= 1; d >>= 1) {
+          pt_ext o = shfl_down_pt(acc, d);
+          acc = pt_add(acc, o);
+        }
+      }
+    } else if (lane == 0) {
+      // msm/mod.rs:150-163: total = sum_w 2^(8w) W_w, high to low with 8 doublings per window
+      for (int w = nw - 1; w >= 0; w--) {
+        if (w != nw - 1)
+          for (int k = 0; k < 8; k++) acc = pt_dbl(acc);
+        for (int c = 0; c < nchunks; c++) acc = pt_add(acc, ld_pt(p + (size_t)w * nchunks + c));
       }
     }
-  } else if (lane == 0) {
-    // msm/mod.rs:150-163: total = sum_w 2^(8w) W_w, high to low with 8 doublings per window
-    for (int w = nw - 1; w >= 0; w--) {
-      if (w != nw - 1)
-        for (int k = 0; k < 8; k++) acc = pt_dbl(acc);
-      for (int c = 0; c < nchunks; c++) acc = pt_add(acc, ld_pt(p + (size_t)w * nchunks + c));
+    if (lane == 0) {
+      if (out_raw) {
+#pragma unroll
+        for (int l = 0; l < 8; l++) {
+          out_raw[(size_t)row * 32 + l] = acc.X.v[l];
+          out_raw[(size_t)row * 32 + 8 + l] = acc.Y.v[l];
+          out_raw[(size_t)row * 32 + 16 + l] = acc.Z.v[l];
+          out_raw[(size_t)row * 32 + 24 + l] = acc.T.v[l];
+        }
+      }
+      if (mapped) {  // straight into mapped pinned host memory: the host is spinning on the flag below
+#pragma unroll
+        for (int l = 0; l < 8; l++) {
+          mapped[row * 32 + l] = acc.X.v[l];
+          mapped[row * 32 + 8 + l] = acc.Y.v[l];
+          mapped[row * 32 + 16 + l] = acc.Z.v[l];
+          mapped[row * 32 + 24 + l] = acc.T.v[l];
+        }
+        __threadfence_system();
+      }
+      if (out_comp || out_ext) {
+        fq_t x, y;
+        pt_to_affine_canonical(acc, x, y);
+        if (out_comp) {
+          uint32_t c[8];
+          pt_compress_canonical(x, y, c);
+#pragma unroll
+          for (int l = 0; l < 8; l++) out_comp[(size_t)row * 8 + l] = c[l];
+        }
+        if (out_ext) {
+          fq_t one = fq_one();
+          out_ext[(size_t)row * 4 + 0] = fq_to_ark(x);
+          out_ext[(size_t)row * 4 + 1] = fq_to_ark(y);
+          out_ext[(size_t)row * 4 + 2] = fq_to_ark(fq_mul(x, y));
+          out_ext[(size_t)row * 4 + 3] = fq_to_ark(one);
+        }
+      }
     }
   }
-  if (lane != 0) return;
-  if (out_raw) {
-#pragma unroll
-    for (int l = 0; l < 8; l++) {
-      out_raw[(size_t)row * 32 + l] = acc.X.v[l];
-      out_raw[(size_t)row * 32 + 8 + l] = acc.Y.v[l];
-      out_raw[(size_t)row * 32 + 16 + l] = acc.Z.v[l];
-      out_raw[(size_t)row * 32 + 24 + l] = acc.T.v[l];
+  if (mapped) {  // single-CTA launch (nrows <= 8): publish once every row is written
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      *((volatile uint32_t*)(mapped + 1024)) = seq;
     }
-  }
-  if (!out_comp && !out_ext) return;
-  fq_t x, y;
-  pt_to_affine_canonical(acc, x, y);
-  if (out_comp) {
-    uint32_t c[8];
-    pt_compress_canonical(x, y, c);
-#pragma unroll
-    for (int l = 0; l < 8; l++) out_comp[(size_t)row * 8 + l] = c[l];
-  }
-  if (out_ext) {
-    fq_t one = fq_one();
-    out_ext[(size_t)row * 4 + 0] = fq_to_ark(x);
-    out_ext[(size_t)row * 4 + 1] = fq_to_ark(y);
-    out_ext[(size_t)row * 4 + 2] = fq_to_ark(fq_mul(x, y));
-    out_ext[(size_t)row * 4 + 3] = fq_to_ark(one);
   }
 }
 
@@ -490,9 +511,11 @@ size_t msm_partials_count(int nrows, int ncols, int nw) {  // upper bound over b
 
 void launch_msm_rows(const pt_niels* table, size_t table_stride, int shifted, const void* scalars, int scalar_limbs,
                      size_t row_stride, int nrows, int ncols, int nw, int col_mul, int col_add, pt_ext* partials,
-                     fq_t* out_ext, uint32_t* out_comp, uint32_t* out_raw, cudaStream_t st) {
+                     fq_t* out_ext, uint32_t* out_comp, uint32_t* out_raw, cudaStream_t st, uint32_t* mapped,
+                     uint32_t seq) {
   if (nrows <= 0) return;
   if (nw < 1) nw = 1;
+  if (mapped && nrows > 8) throw std::runtime_error("msm: mapped publication is for <= 8 rows");
   const MsmGeom g = msm_geometry(nrows, ncols, nw, shifted);
   const int nchunks = g.nchunks, chunk_cols = g.chunk_cols;
   static bool attr_set = false;
@@ -515,7 +538,12 @@ void launch_msm_rows(const pt_niels* table, size_t table_stride, int shifted, co
           table, table_stride, shifted, (const uint32_t*)scalars + (size_t)r0 * row_stride * 8, row_stride, ncols,
           chunk_cols, nw, g.wpc, col_mul, col_add, part);
   }
-  msm_finish_kernel<<<nrows, 32, 0, st>>>(partials, nrows, g.ngroups, nchunks, shifted, out_ext, out_comp, out_raw);
+  if (mapped)
+    msm_finish_kernel<<<1, 32 * nrows, 0, st>>>(partials, nrows, g.ngroups, nchunks, shifted, out_ext, out_comp, out_raw,
+                                                mapped, seq);
+  else
+    msm_finish_kernel<<<nrows, 32, 0, st>>>(partials, nrows, g.ngroups, nchunks, shifted, out_ext, out_comp, out_raw,
+                                            nullptr, 0);
 }
 
 // Cross-GPU "bucket-sum reduce": raw[(k * nrows + row) * 32 ..] = partial (X,Y,Z,T) of source k for `row`

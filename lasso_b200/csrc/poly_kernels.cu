@@ -591,6 +591,107 @@ void launch_bullet_scalars(const fr_t* a, const fr_t* w, size_t n_loc, size_t m,
                            fr_t* sR, cudaStream_t st) {
   bullet_scalars_kernel<<<grid_for(n_loc), kThreads, 0, st>>>(a, w, n_loc, m, G, g, a_rep, sL, sR);
 }
+// One Bulletproofs round's scalar side in ONE launch (single GPU): fold a, b with the previous round's
+// challenge (bullet.rs:127-130), expand the generator weights, form the L / R scalars of the unfolded
+// generators in canonical form, and (last CTA, Finalize ticket) the cross inner products c_L, c_R
+// (bullet.rs:78-79) + blinds as the two tail columns (Q, h).  Replaces fold_ab + expand_weights + cross_ip +
+// reduce + bullet_scalars + set_tail + canonicalize: seven launches of a few microseconds each on the
+// critical path of every round.
+//   a_in, b_in : length 2m when fold != 0 (folded here into a_out, b_out of length m), else length m
+//   w_in       : n/(2m) weights when fold != 0 (expanded into w_out, n/m weights), else n/m weights
+//   s_out      : 2 rows x (n + 2) canonical scalars: row 0 = L, row 1 = R; columns n, n+1 = (c, blind)
+// Thread j <-> generator column j = t*m + pos.  h = m/2:  L[j] = a'[pos-h] w'[t] (pos >= h),
+// R[j] = a'[pos+h] w'[t] (pos < h).  Threads j < h also own the pair (pos, pos+h) of a', b'.
+__global__ void __launch_bounds__(kThreads)
+    bullet_round_kernel(const fr_t* a_in, const fr_t* b_in, const fr_t* w_in, fr_t* a_out, fr_t* b_out, fr_t* w_out,
+                        size_t n, size_t m, int fold, fr_t u, fr_t uinv, fr_t blind_L, fr_t blind_R, fr_t* s_out,
+                        fr_t* partial, unsigned* counter) {
+  __shared__ fr_t scratch[2 * kThreads / 32];
+  __shared__ int s_last;
+  const size_t h = m / 2, stride = n + 2;
+  const int lg_m = 63 - __clzll((long long)m);
+  fr_t acc[2] = {fr_zero(), fr_zero()};
+  auto folded_a = [&](size_t i) {
+    return fold ? fr_add(fr_mul(ld_fr(a_in + i), u), fr_mul(uinv, ld_fr(a_in + m + i))) : ld_fr(a_in + i);
+  };
+  auto folded_b = [&](size_t i) {
+    return fold ? fr_add(fr_mul(ld_fr(b_in + i), uinv), fr_mul(u, ld_fr(b_in + m + i))) : ld_fr(b_in + i);
+  };
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) {
+    const size_t t = j >> lg_m, pos = j & (m - 1);  // m is a power of two
+    fr_t wt = fold ? fr_mul(ld_fr(w_in + (t >> 1)), (t & 1) ? u : uinv) : ld_fr(w_in + t);
+    if (pos == 0 && fold) st_fr(w_out + t, wt);
+    const bool is_l = pos >= h;
+    const size_t idx = is_l ? pos - h : pos + h;
+    const fr_t ai = folded_a(idx);
+    const fr_t sc = fr_to_canonical(fr_mul(ai, wt));
+    st_fr(s_out + j, is_l ? sc : fr_zero());
+    st_fr(s_out + stride + j, is_l ? fr_zero() : sc);
+    if (t == 0 && pos < h) {  // owner of the pair (pos, pos + h): ai = a'[pos + h]
+      const fr_t alo = folded_a(pos), blo = folded_b(pos), bhi = folded_b(idx);
+      if (fold) {
+        st_fr(a_out + pos, alo);
+        st_fr(a_out + idx, ai);
+        st_fr(b_out + pos, blo);
+        st_fr(b_out + idx, bhi);
+      }
+      acc[0] = fr_mul(alo, bhi);  // c_L = <a_lo, b_hi>
+      acc[1] = fr_mul(ai, blo);   // c_R = <a_hi, b_lo>
+    }
+  }
+  block_sum_fr<2>(acc, scratch);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = acc[0];
+    partial[gridDim.x + blockIdx.x] = acc[1];
+    __threadfence();
+    s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp < 2) {
+    fr_t v = fr_zero();
+    for (unsigned i = lane; i < gridDim.x; i += 32) v = fr_add(v, ld_fr_cg(partial + (size_t)warp * gridDim.x + i));
+    v = warp_sum_fr(v);
+    if (lane == 0) {
+      st_fr(s_out + (size_t)warp * stride + n, fr_to_canonical(v));
+      st_fr(s_out + (size_t)warp * stride + n + 1, fr_to_canonical(warp == 0 ? blind_L : blind_R));
+    }
+  }
+  if (threadIdx.x == 0) *counter = 0;
+}
+void launch_bullet_round(const fr_t* a_in, const fr_t* b_in, const fr_t* w_in, fr_t* a_out, fr_t* b_out, fr_t* w_out, size_t n,
+                         size_t m, int fold, const fr_t& u, const fr_t& uinv, const fr_t& blind_L, const fr_t& blind_R,
+                         fr_t* s_out, fr_t* partial, unsigned* counter, cudaStream_t st) {
+  unsigned blocks = (unsigned)((n + kThreads - 1) / kThreads);
+  bullet_round_kernel<<<blocks, kThreads, 0, st>>>(a_in, b_in, w_in, a_out, b_out, w_out, n, m, fold, u, uinv, blind_L,
+                                                   blind_R, s_out, partial, counter);
+}
+// Two MSM rows over the n + 2 generators (G_0..G_{n-1}, Q, h) in canonical form:
+//   row 0 = (k * v[0..n), t00, t01)    row 1 = (0 .. 0, t10, t11)
+// i.e. (Cx, Cy) of dot_product.rs:192-197 and (delta, beta) of dot_product.rs:219-230 as ONE two-row MSM.
+__global__ void __launch_bounds__(kThreads)
+    two_row_scalars_kernel(const fr_t* v, int scale, fr_t k, fr_t t00, fr_t t01, fr_t t10, fr_t t11, size_t n, fr_t* out) {
+  const size_t stride = n + 2;
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < stride; j += (size_t)gridDim.x * blockDim.x) {
+    fr_t r0, r1 = fr_zero();
+    if (j < n) {
+      fr_t x = ld_fr(v + j);
+      r0 = fr_to_canonical(scale ? fr_mul(x, k) : x);
+    } else {
+      r0 = fr_to_canonical(j == n ? t00 : t01);
+      r1 = fr_to_canonical(j == n ? t10 : t11);
+    }
+    st_fr(out + j, r0);
+    st_fr(out + stride + j, r1);
+  }
+}
+void launch_two_row_scalars(const fr_t* v, int scale, const fr_t& k, const fr_t& t00, const fr_t& t01, const fr_t& t10,
+                            const fr_t& t11, size_t n, fr_t* out, cudaStream_t st) {
+  two_row_scalars_kernel<<<grid_for(n + 2), kThreads, 0, st>>>(v, scale, k, t00, t01, t10, t11, n, out);
+}
 // out[i] = in[i*stride + off] * k
 __global__ void __launch_bounds__(kThreads)
     scale_strided_kernel(const fr_t* in, fr_t* out, size_t n, size_t stride, size_t off, fr_t k) {

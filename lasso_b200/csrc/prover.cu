@@ -98,6 +98,7 @@ Ctx* ctx_create(int device) {
       LB_CUDA_CHECK(cudaHostGetDevicePointer((void**)&c->d_mapped, c->h_mapped, 0));
     }
   }
+  LB_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming));
   const char* sp = getenv("LASSO_B200_SPANS");
   c->span_sync = sp && sp[0] == '1';
   return c.release();
@@ -110,6 +111,7 @@ void ctx_destroy(Ctx* c) {
   cudaFree(c->d_small);
   cudaFree(c->d_eq_scratch);
   cudaFree(c->d_flag);
+  if (c->ev_aux) cudaEventDestroy(c->ev_aux);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->h_mapped) cudaFreeHost(c->h_mapped);
   cudaFreeHost(c->h_pin);
@@ -839,32 +841,35 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
   std::vector<fr_t> v1 = tape.random_vector("blinds_vec_1", 2 * lg_n);
   std::vector<fr_t> v2 = tape.random_vector("blinds_vec_2", 2 * lg_n);
   DotProductProofLogBytes out;
-  // Cx = batch_commit(x_vec, blind_x = 0) ; Cy = y*Q + 0*h
-  std::vector<uint8_t> Cx = msm_rows_fr(c, g, a.p, 1, (int)n_loc);
-  transcript.append_point_compressed("Cx", Cx.data());
+  const bool fast = G == 1 && c->h_mapped != nullptr && n * 32 <= c->h_pin_bytes;  // single-GPU pipeline below
   DBuf<fr_t> two(c, 4);
-  set_elems_kernel<<<1, 32, 0, c->st>>>(two.p, Zr, fr_zero());
-  g_launches += 1;
-  std::vector<uint8_t> Cy = msm_replicated_fr(c, g, two.p, 2, n);
-  transcript.append_point_compressed("Cy", Cy.data());
-  {  // append_scalars(b"a", a_vec): canonical bytes straight from the device (all ranks need the whole vector)
-    DBuf<fr_t> canon(c, n_loc), all(c, G > 1 ? n : 0);
-    launch_canonicalize(b.p, canon.p, n_loc, c->d_flag, c->st);
+  if (!fast) {
+    // Cx = batch_commit(x_vec, blind_x = 0) ; Cy = y*Q + 0*h
+    std::vector<uint8_t> Cx = msm_rows_fr(c, g, a.p, 1, (int)n_loc);
+    transcript.append_point_compressed("Cx", Cx.data());
+    set_elems_kernel<<<1, 32, 0, c->st>>>(two.p, Zr, fr_zero());
     g_launches += 1;
-    std::vector<uint8_t> bytes(n * 32);
-    if (G == 1) {
-      c->d2h(bytes.data(), canon.p, bytes.size());
-    } else {
-      comm_allgather(c, canon.p, all.p, n_loc * 32);
-      std::vector<uint8_t> tmp(n * 32);
-      c->d2h(tmp.data(), all.p, tmp.size());
-      for (int q = 0; q < G; q++)  // rank q's local column j' is global column j'*G + q
-        for (size_t j = 0; j < n_loc; j++) memcpy(&bytes[(j * G + q) * 32], &tmp[((size_t)q * n_loc + j) * 32], 32);
+    std::vector<uint8_t> Cy = msm_replicated_fr(c, g, two.p, 2, n);
+    transcript.append_point_compressed("Cy", Cy.data());
+    {  // append_scalars(b"a", a_vec): canonical bytes straight from the device (all ranks need the whole vector)
+      DBuf<fr_t> canon(c, n_loc), all(c, G > 1 ? n : 0);
+      launch_canonicalize(b.p, canon.p, n_loc, c->d_flag, c->st);
+      g_launches += 1;
+      std::vector<uint8_t> bytes(n * 32);
+      if (G == 1) {
+        c->d2h(bytes.data(), canon.p, bytes.size());
+      } else {
+        comm_allgather(c, canon.p, all.p, n_loc * 32);
+        std::vector<uint8_t> tmp(n * 32);
+        c->d2h(tmp.data(), all.p, tmp.size());
+        for (int q = 0; q < G; q++)  // rank q's local column j' is global column j'*G + q
+          for (size_t j = 0; j < n_loc; j++) memcpy(&bytes[(j * G + q) * 32], &tmp[((size_t)q * n_loc + j) * 32], 32);
+      }
+      transcript.append_scalars_bytes("a", bytes.data(), n);
     }
-    transcript.append_scalars_bytes("a", bytes.data(), n);
   }
   // ---- BulletReductionProof::prove with unfolded generators (see file header)
-  sp1.reset(new SpanTimer(c, "PE.3 bullet rounds"));
+  if (!fast) sp1.reset(new SpanTimer(c, "PE.3 bullet rounds"));
   fr_t blind_fin = fr_zero();  // blind_Gamma = blind_x + blind_y = 0
   const size_t ncols_main = G == 1 ? n + 2 : n_loc;  // single GPU: Q and h ride along as columns n, n+1
   DBuf<fr_t> W0(c, n), W1(c, n), sLR(c, 2 * ncols_main), tailsc(c, 4);
@@ -876,6 +881,82 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
   fr_t* sR = sLR.p + ncols_main;
   fr_t* av = a.p;  // current a / b vectors: sharded while m >= 2G, replicated afterwards
   fr_t* bv = b.p;
+  DBuf<fr_t> a_alt, b_alt;
+  if (fast) {
+    // Single GPU.  Per message ONE scalar kernel + the two MSM kernels, the finish kernel publishing straight to
+    // mapped host memory; the host part of a message (compression, Fiat-Shamir) overlaps the device work of the
+    // next one wherever the transcript allows it.
+    //   (Cx, Cy): rows (x_vec, 0, 0) and (0.., y, 0) of one two-row MSM        (dot_product.rs:192-197)
+    //   round k : fold with u_{k-1}, weights, L/R scalars, c_L, c_R -> two-row MSM   (bullet.rs:73-134)
+    auto read_two_points = [&](uint32_t seq, uint8_t* comp64) {
+      c->wait_flag(seq);
+      uint32_t xyzt[64];
+      memcpy(xyzt, (const void*)c->h_mapped, sizeof(xyzt));
+      h64::compress_xyz(xyzt, comp64);
+      h64::compress_xyz(xyzt + 32, comp64 + 32);
+    };
+    a_alt.alloc(c, n);
+    b_alt.alloc(c, n);
+    fr_t *an = a_alt.p, *bn = b_alt.p;
+    DBuf<pt_ext> part(c, msm_partials_count(2, (int)(n + 2), kMsmFullWindows));
+    DBuf<fr_t> canon(c, n);
+    auto two_row_msm = [&]() {
+      const uint32_t seq = ++c->mapped_seq;
+      launch_msm_rows(g.d_table.p, g.n_points, 1, sLR.p, 8, n + 2, 2, (int)(n + 2), kMsmFullWindows, 1, 0, part.p, nullptr,
+                      nullptr, nullptr, c->st, c->d_mapped, seq);
+      g_launches += 2;
+      return seq;
+    };
+    launch_two_row_scalars(av, 0, fr_one(), fr_zero(), fr_zero(), Zr, fr_zero(), n, sLR.p, c->st);
+    uint32_t seq = two_row_msm();
+    // a_vec of the transcript = canonical bytes of b; the copy is waited for only when it is appended
+    launch_canonicalize(bv, canon.p, n, c->d_flag, c->st);
+    LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin, canon.p, n * 32, cudaMemcpyDeviceToHost, c->st));
+    LB_CUDA_CHECK(cudaEventRecord(c->ev_aux, c->st));
+    g_launches += 2;
+    uint8_t CxCy[64];
+    read_two_points(seq, CxCy);
+    fr_t u = fr_one(), u_inv = fr_one();
+    int fold = 0;
+    size_t m = n;  // vector length entering the round (after the fold with the previous challenge)
+    auto launch_round = [&](size_t round) {
+      launch_bullet_round(av, bv, W, an, bn, Wn, n, m, fold, u, u_inv, v1[round], v2[round], sLR.p, c->d_partial,
+                          c->d_flag + 4, c->st);
+      g_launches += 1;
+      if (fold) {
+        std::swap(av, an);
+        std::swap(bv, bn);
+        std::swap(W, Wn);
+      }
+      return two_row_msm();
+    };
+    if (m != 1) seq = launch_round(0);  // round 0 needs no challenge: it runs while the host absorbs Cx, Cy, a
+    transcript.append_point_compressed("Cx", CxCy);
+    transcript.append_point_compressed("Cy", CxCy + 32);
+    LB_CUDA_CHECK(cudaEventSynchronize(c->ev_aux));
+    transcript.append_scalars_bytes("a", c->h_pin, n);
+    sp1.reset(new SpanTimer(c, "PE.3 bullet rounds"));
+    for (size_t round = 0; m != 1; round++) {
+      uint8_t LR[64];
+      read_two_points(seq, LR);
+      transcript.append_point_compressed("L", LR);
+      transcript.append_point_compressed("R", LR + 32);
+      u = transcript.challenge_scalar("u");
+      u_inv = fr_inv(u);
+      fold = 1;
+      m /= 2;
+      if (m != 1) seq = launch_round(round + 1);
+      blind_fin = fr_add(blind_fin, fr_add(fr_mul(fr_mul(v1[round], u), u), fr_mul(fr_mul(v2[round], u_inv), u_inv)));
+      out.L_vec.insert(out.L_vec.end(), LR, LR + 32);
+      out.R_vec.insert(out.R_vec.end(), LR + 32, LR + 64);
+    }
+    if (fold) {  // the last challenge: a, b -> one element each, weights -> n (bullet.rs:127-134)
+      launch_fold_ab(av, bv, 1, u, u_inv, c->st);
+      launch_expand_weights(W, Wn, n / 2, u, u_inv, c->st);
+      g_launches += 2;
+      std::swap(W, Wn);
+    }
+  } else {
   bool sharded = G > 1;
   size_t m = n, nw_count = 1;  // current (global) vector length, number of weights
   for (size_t round = 0; m != 1; round++) {
@@ -917,35 +998,58 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
     out.R_vec.insert(out.R_vec.end(), LR.begin() + 32, LR.begin() + 64);
     m = h;
   }
+  }
   sp1.reset(new SpanTimer(c, "PE.4 delta,beta"));
   fr_t ab[2];
-  LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin, av, 32, cudaMemcpyDeviceToHost, c->st));
-  LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin + 32, bv, 32, cudaMemcpyDeviceToHost, c->st));
-  c->sync();
-  memcpy(ab, c->h_pin, 64);
+  if (fast) {
+    // delta = d * g_hat + r_delta * h with g_hat = sum_j W[j] G_j (dot_product.rs:219-227) and
+    // beta = d * Q + r_beta * h (dot_product.rs:229-230) as the two rows of one MSM
+    launch_two_row_scalars(W, 1, d, fr_zero(), r_delta, d, r_beta, n, sLR.p, c->st);
+    const uint32_t seq = ++c->mapped_seq;
+    DBuf<pt_ext> part(c, msm_partials_count(2, (int)(n + 2), kMsmFullWindows));
+    launch_msm_rows(g.d_table.p, g.n_points, 1, sLR.p, 8, n + 2, 2, (int)(n + 2), kMsmFullWindows, 1, 0, part.p, nullptr,
+                    nullptr, nullptr, c->st, c->d_mapped, seq);
+    LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin, av, 32, cudaMemcpyDeviceToHost, c->st));
+    LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin + 32, bv, 32, cudaMemcpyDeviceToHost, c->st));
+    g_launches += 3;
+    c->wait_flag(seq);
+    uint32_t xyzt[64];
+    memcpy(xyzt, (const void*)c->h_mapped, sizeof(xyzt));
+    h64::compress_xyz(xyzt, out.delta);
+    h64::compress_xyz(xyzt + 32, out.beta);
+    c->sync();
+    memcpy(ab, c->h_pin, 64);
+    transcript.append_point_compressed("delta", out.delta);
+    transcript.append_point_compressed("beta", out.beta);
+  } else {
+    LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin, av, 32, cudaMemcpyDeviceToHost, c->st));
+    LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin + 32, bv, 32, cudaMemcpyDeviceToHost, c->st));
+    c->sync();
+    memcpy(ab, c->h_pin, 64);
+    // delta = d * g_hat + r_delta * h with g_hat = sum_j W[j] G_j  (dot_product.rs:219-227)
+    std::vector<uint8_t> delta;
+    if (G == 1) {
+      launch_scale(W, sL, n, d, c->st);
+      set_elems_kernel<<<1, 32, 0, c->st>>>(sL + n, fr_zero(), r_delta);
+      g_launches += 2;
+      delta = msm_rows_fr(c, g, sL, 1, (int)(n + 2));
+    } else {
+      launch_scale_strided(W, sL, n_loc, (size_t)G, (size_t)gr, d, c->st);
+      set_elems_kernel<<<1, 32, 0, c->st>>>(tailsc.p, fr_zero(), r_delta);
+      g_launches += 2;
+      delta = msm_rows_fr(c, g, sL, 1, (int)n_loc, tailsc.p, 2, n);
+    }
+    memcpy(out.delta, delta.data(), 32);
+    transcript.append_point_compressed("delta", out.delta);
+    // beta = d * Q + r_beta * h  (dot_product.rs:229-230)
+    set_elems_kernel<<<1, 32, 0, c->st>>>(two.p, d, r_beta);
+    g_launches += 1;
+    std::vector<uint8_t> beta = msm_replicated_fr(c, g, two.p, 2, n);
+    memcpy(out.beta, beta.data(), 32);
+    transcript.append_point_compressed("beta", out.beta);
+  }
   fr_t x_hat = ab[0], a_hat = ab[1], rhat_Gamma = blind_fin;
   fr_t y_hat = fr_mul(x_hat, a_hat);
-  // delta = d * g_hat + r_delta * h with g_hat = sum_j W[j] G_j  (dot_product.rs:219-227)
-  std::vector<uint8_t> delta;
-  if (G == 1) {
-    launch_scale(W, sL, n, d, c->st);
-    set_elems_kernel<<<1, 32, 0, c->st>>>(sL + n, fr_zero(), r_delta);
-    g_launches += 2;
-    delta = msm_rows_fr(c, g, sL, 1, (int)(n + 2));
-  } else {
-    launch_scale_strided(W, sL, n_loc, (size_t)G, (size_t)gr, d, c->st);
-    set_elems_kernel<<<1, 32, 0, c->st>>>(tailsc.p, fr_zero(), r_delta);
-    g_launches += 2;
-    delta = msm_rows_fr(c, g, sL, 1, (int)n_loc, tailsc.p, 2, n);
-  }
-  memcpy(out.delta, delta.data(), 32);
-  transcript.append_point_compressed("delta", out.delta);
-  // beta = d * Q + r_beta * h  (dot_product.rs:229-230)
-  set_elems_kernel<<<1, 32, 0, c->st>>>(two.p, d, r_beta);
-  g_launches += 1;
-  std::vector<uint8_t> beta = msm_replicated_fr(c, g, two.p, 2, n);
-  memcpy(out.beta, beta.data(), 32);
-  transcript.append_point_compressed("beta", out.beta);
   fr_t cc = transcript.challenge_scalar("c");
   out.z1 = fr_add(d, fr_mul(cc, y_hat));
   out.z2 = fr_add(fr_mul(a_hat, fr_add(fr_mul(cc, rhat_Gamma), r_beta)), r_delta);

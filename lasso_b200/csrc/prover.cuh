@@ -52,6 +52,7 @@ struct Ctx {
   uint32_t* h_mapped = nullptr;  // [0..1024) payload words, [1024] flag
   uint32_t* d_mapped = nullptr;
   uint32_t mapped_seq = 0;
+  cudaEvent_t ev_aux = nullptr;  // marks a device->host copy that overlaps later launches on the same stream
   void d2h_small(void* dst, const void* src, size_t bytes);  // prover.cu
   void wait_flag(uint32_t seq);                               // prover.cu
   // a round message produced by a single launch (common.cuh Finalize): results land in d_small and, on a single
