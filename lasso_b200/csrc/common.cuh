@@ -95,15 +95,20 @@ __device__ __forceinline__ void block_sum_fr(fr_t (&v)[NV], fr_t* scratch) {
 
 // ---- single-launch reduction + publication of a round message ---------------------------------------------
 // Every CTA stores its partial sums, takes a ticket, and the LAST CTA to finish adds the partials of all
-// values, writes the results to device memory and (optionally) straight into mapped pinned host memory,
-// then raises a sequence flag the host is spinning on.  One kernel per sumcheck round instead of
-// eval + reduce + copy: the rounds of the grand-product ladder are pure launch/sync latency.
+// values, writes the results to device memory and (optionally) straight into mapped pinned host memory the
+// host is spinning on.  One kernel per sumcheck round instead of eval + reduce + copy: the rounds of the
+// grand-product ladder are pure launch/sync latency.
+//
+// Publication needs no flag and no system-scope fence (each costs microseconds per round): an Fr element is
+// < 2^253, so bits 29..31 of its last word are free.  Every published element carries a 3-bit tag there and
+// travels as ONE 32-byte store; the host waits until all `count` elements show the tag of this round, strips
+// it, and clears the slots (prover.cu Ctx::fin_wait).  Ordering between elements is irrelevant.
 struct Finalize {
   fr_t* partial;      // scratch: [nvals][blocks_per_val]
   unsigned* counter;  // device ticket counter: 0 on entry, reset to 0 by the last CTA
-  fr_t* out_dev;      // nvals results (always written)
-  uint32_t* mapped;   // optional mapped host buffer: payload words [0, 8*nvals), flag at word 1024
-  uint32_t seq;       // flag value to publish
+  fr_t* out_dev;      // nvals results (always written, untagged)
+  uint32_t* mapped;   // optional mapped host buffer: element v at words [8v, 8v+8), tagged
+  uint32_t tag;       // 1..7
 };
 __device__ __forceinline__ fr_t ld_fr_cg(const fr_t* p) {  // bypass L1: written by other CTAs of this launch
   fr_t r;
@@ -113,11 +118,50 @@ __device__ __forceinline__ fr_t ld_fr_cg(const fr_t* p) {  // bypass L1: written
                : "l"((const char*)p + 16));
   return r;
 }
+// result v of a round: device copy + tagged host copy
+__device__ __forceinline__ void finalize_publish(const Finalize& f, int v, const fr_t& val) {
+  f.out_dev[v] = val;
+  if (f.mapped) {
+    fr_t t = val;
+    t.v[7] |= f.tag << 29;
+    st_fr((fr_t*)f.mapped + v, t);
+  }
+}
+// the LAST CTA of a launch (all threads): add the partials of every value and publish
+__device__ __forceinline__ void finalize_last_stage(const Finalize& f, int blocks_per_val, int nvals_total) {
+  __threadfence();
+  // groups of gsz = 2^k >= min(32, blocks_per_val) lanes add the partials of one value each
+  int gsz = 1;
+  while (gsz < blocks_per_val && gsz < 32) gsz <<= 1;
+  const int lane_g = threadIdx.x & (gsz - 1), ngroups = blockDim.x / gsz;
+  for (int base = 0; base < nvals_total; base += ngroups) {  // uniform trip count: full-warp shuffles inside
+    const int v = base + threadIdx.x / gsz;
+    const bool ok = v < nvals_total;
+    fr_t acc = fr_zero();
+    if (ok)
+      for (int i = lane_g; i < blocks_per_val; i += gsz) acc = fr_add(acc, ld_fr_cg(f.partial + (size_t)v * blocks_per_val + i));
+    for (int d = gsz >> 1; d > 0; d >>= 1) {
+      fr_t o;
+#pragma unroll
+      for (int l = 0; l < 8; l++) o.v[l] = __shfl_down_sync(0xffffffffu, acc.v[l], d, gsz);
+      acc = fr_add(acc, o);
+    }
+    if (ok && lane_g == 0) finalize_publish(f, v, acc);
+  }
+  if (threadIdx.x == 0) *f.counter = 0;
+}
 // vals[0..NV) are valid in thread 0 of the CTA; they belong to value indices v0 .. v0+NV, partial slot bidx.
 template <int NV>
 __device__ __forceinline__ void finalize_block(const Finalize& f, const fr_t (&vals)[NV], int v0, int bidx,
                                                int blocks_per_val, int nvals_total, int total_blocks) {
   __shared__ int s_last;
+  if (total_blocks == 1) {  // single CTA: nothing to combine
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int t = 0; t < NV; t++) finalize_publish(f, v0 + t, vals[t]);
+    }
+    return;
+  }
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int t = 0; t < NV; t++) f.partial[(size_t)(v0 + t) * blocks_per_val + bidx] = vals[t];
@@ -127,30 +171,9 @@ __device__ __forceinline__ void finalize_block(const Finalize& f, const fr_t (&v
   }
   __syncthreads();
   if (!s_last) return;
-  __threadfence();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int v = warp; v < nvals_total; v += nwarps) {
-    fr_t acc = fr_zero();
-    for (int i = lane; i < blocks_per_val; i += 32) acc = fr_add(acc, ld_fr_cg(f.partial + (size_t)v * blocks_per_val + i));
-    acc = warp_sum_fr(acc);
-    if (lane == 0) {
-      f.out_dev[v] = acc;
-      if (f.mapped) {
-#pragma unroll
-        for (int l = 0; l < 8; l++) f.mapped[8 * v + l] = acc.v[l];
-      }
-    }
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    *f.counter = 0;
-    if (f.mapped) {
-      __threadfence_system();
-      *((volatile uint32_t*)(f.mapped + 1024)) = f.seq;
-    }
-  }
+  finalize_last_stage(f, blocks_per_val, nvals_total);
 }
+
 #endif
 
 }  // namespace lb

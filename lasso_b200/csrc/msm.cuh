@@ -21,8 +21,10 @@ size_t msm_partials_count(int nrows, int ncols, int nw);
 // out_comp = nrows x 32 bytes ark-serialize compressed; out_raw = nrows x 128 B un-normalised (X,Y,Z,T)
 // internal limbs for host-side normalisation (host_fq64.hpp) or the cross-GPU gather-then-add.
 // Local column c uses generator index c*col_mul + col_add.
-// mapped != null (nrows <= 8): the un-normalised rows are also written to mapped pinned host memory (32 words per
-// row) and the sequence flag at word 1024 is set to `seq` — no separate copy kernel, the host spins on the flag.
+// mapped != null (nrows <= 8), fixed-base table, no other output: the rows go to mapped pinned host memory as
+// TAGGED canonical coordinates — element 3*row + {0,1,2} = X, Y, Z with bit 255 set, one 32-byte store each; the
+// host waits for the tags and clears them (prover.cu Ctx::wait_points).  `seq` is unused on that path.
+// Otherwise with mapped != null: raw rows at 32 words each + the sequence flag at word 1024 = seq.
 void launch_msm_rows(const pt_niels* table, size_t table_stride, int shifted, const void* scalars, int scalar_limbs,
                      size_t row_stride, int nrows, int ncols, int nw, int col_mul, int col_add, pt_ext* partials,
                      fq_t* out_ext, uint32_t* out_comp, uint32_t* out_raw, cudaStream_t st, uint32_t* mapped = nullptr,

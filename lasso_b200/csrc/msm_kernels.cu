@@ -476,6 +476,97 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---------------------------------------------------------------- quad-lane point addition
+// The latency of one extended addition on one thread is 9 dependent Fq multiplications (~2.6 us on a lone
+// warp); the short MSMs of the opening proofs (two rows, a few thousand terms) are nothing but a chain of
+// ~30 of them.  Here the FOUR lanes of a quad hold X, Y, Z, T of the accumulator (role = lane & 3) and run
+// the 4-way parallel form of add-2008-hwcd-3 (Hisil et al. sect. 4.2): A, B, D, C side by side, then
+// E*F, G*H, F*G, E*H side by side -> 2 multiplication levels (+1 on the T lane for 2d*T2), the coordinates
+// exchanged with quad shuffles.  `q` = X2, Y2, Z2, T2 of the other point (global or shared memory).
+__device__ __forceinline__ fq_t shfl_fq(unsigned mask, const fq_t& v, int src_lane) {
+  fq_t r;
+#pragma unroll
+  for (int l = 0; l < 8; l++) r.v[l] = __shfl_sync(mask, v.v[l], src_lane);
+  return r;
+}
+__device__ __forceinline__ fq_t quad_add(unsigned mask, int lane, const fq_t& mine, const fq_t* q) {
+  const int role = lane & 3, qb = lane & ~3;
+  const fq_t partner = shfl_fq(mask, mine, lane ^ 1);  // X <-> Y (Z <-> T unused)
+  fq_t s1, m;
+  if (role == 0) {
+    s1 = fq_sub(partner, mine);  // Y1 - X1
+    m = fq_sub(q[1], q[0]);
+  } else if (role == 1) {
+    s1 = fq_add(mine, partner);  // Y1 + X1
+    m = fq_add(q[1], q[0]);
+  } else if (role == 2) {
+    s1 = mine;
+    m = fq_dbl(q[2]);  // D = Z1 * 2 Z2
+  } else {
+    s1 = mine;
+    m = fq_mul(q[3], fq_d2());  // C = T1 * (2d T2)
+  }
+  const fq_t v = fq_mul(s1, m);                   // A, B, D, C
+  const fq_t o = shfl_fq(mask, v, lane ^ 1);      // B, A, C, D
+  fq_t p1, p2 = fq_zero();
+  if (role == 0) p1 = fq_sub(o, v);               // E = B - A
+  else if (role == 1) p1 = fq_add(v, o);          // H = B + A
+  else if (role == 2) { p1 = fq_sub(v, o); p2 = fq_add(v, o); }  // F = D - C, G = D + C
+  else p1 = fq_add(o, v);                         // G
+  // lane 0 <- F (lane 2), lane 1 <- G (lane 3), lane 3 <- E (lane 0); lane 2 has G itself
+  const int src_a = qb + (role == 0 ? 2 : role == 1 ? 3 : role == 2 ? 2 : 0);
+  fq_t a = shfl_fq(mask, p1, src_a);
+  const fq_t b = shfl_fq(mask, p1, qb + 1);       // H, for lane 3
+  if (role == 2) a = p2;
+  // X3 = E F, Y3 = H G, Z3 = F G, T3 = E H
+  return fq_mul(role == 3 ? a : p1, role == 3 ? b : a);
+}
+// Finish for a handful of rows over a shifted table (the rounds of the opening proofs): ONE CTA, 32 quads
+// per row; each quad adds its share of the row's partials, then a 5-level tree through shared memory.
+// The result (X, Y, Z canonical) goes to mapped host memory, one tagged 32-byte store per coordinate (bit
+// 255 is free below q): no flag, no system fence (see common.cuh Finalize).
+__global__ void __launch_bounds__(1024)
+    msm_finish_quad_kernel(const pt_ext* partials, int nrows, int P, uint32_t* out_raw, uint32_t* tagged) {
+  __shared__ fq_t sm_pt[8 * 32 * 4];
+  const int tid = threadIdx.x, lane = tid & 31, role = tid & 3;
+  const int row = tid >> 7, qr = (tid & 127) >> 2;  // blockDim = 128 * nrows
+  const fq_t* prow = reinterpret_cast<const fq_t*>(partials + (size_t)row * P);
+  fq_t mine = (role == 1 || role == 2) ? fq_one() : fq_zero();  // identity (0, 1, 1, 0)
+  for (int i0 = 0; i0 < P; i0 += 32) {  // uniform trip count: the quad shuffles use the full-warp mask
+    const int i = i0 + qr;
+    if (i0 == 0) {
+      if (i < P) mine = ld_fq(prow + 4 * (size_t)i + role);
+    } else {
+      fq_t r = quad_add(0xffffffffu, lane, mine, prow + 4 * (size_t)(i < P ? i : 0));
+      if (i < P) mine = r;
+    }
+  }
+  fq_t* slot = sm_pt + ((size_t)row * 32 + qr) * 4;
+  slot[role] = mine;
+  __syncthreads();
+  for (int d = 16; d >= 1; d >>= 1) {
+    fq_t r = mine;
+    if (qr < d) r = quad_add(d >= 8 ? 0xffffffffu : (0xfu << (lane & ~3)), lane, mine, slot + 4 * d);
+    __syncthreads();
+    if (qr < d) {
+      mine = r;
+      slot[role] = mine;
+    }
+    __syncthreads();
+  }
+  if (qr == 0 && role < 3) {
+    if (out_raw) {
+#pragma unroll
+      for (int l = 0; l < 8; l++) out_raw[(size_t)row * 32 + role * 8 + l] = mine.v[l];
+    }
+    if (tagged) {
+      fq_t c = fq_canonical(mine);
+      c.v[7] |= 0x80000000u;
+      st_fq(reinterpret_cast<fq_t*>(tagged) + row * 3 + role, c);
+    }
+  }
+}
+
 // Launch geometry.  wpc = windows per CTA (all of them over a shifted table), ngroups = window groups,
 // chunk_cols = columns per CTA: at most MSM_CHUNK list entries (columns x windows) per CTA; with only a few
 // rows (Bulletproofs rounds) the columns are split further so that about one CTA per SM exists.
@@ -538,7 +629,9 @@ void launch_msm_rows(const pt_niels* table, size_t table_stride, int shifted, co
           table, table_stride, shifted, (const uint32_t*)scalars + (size_t)r0 * row_stride * 8, row_stride, ncols,
           chunk_cols, nw, g.wpc, col_mul, col_add, part);
   }
-  if (mapped)
+  if (mapped && shifted && !out_ext && !out_comp)
+    msm_finish_quad_kernel<<<1, 128 * nrows, 0, st>>>(partials, nrows, g.ngroups * nchunks, out_raw, mapped);
+  else if (mapped)
     msm_finish_kernel<<<1, 32 * nrows, 0, st>>>(partials, nrows, g.ngroups, nchunks, shifted, out_ext, out_comp, out_raw,
                                                 mapped, seq);
   else

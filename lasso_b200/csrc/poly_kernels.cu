@@ -342,9 +342,119 @@ __global__ void __launch_bounds__(kThreads)
   block_sum_fr<3>(acc, scratch);
   finalize_block<3>(fin, acc, blockIdx.y * 3, blockIdx.x, gridDim.x, 3 * gridDim.y, gridDim.x * gridDim.y);
 }
+// Latency-oriented variant of the two kernels above for the small and medium rounds (most of the ~300 rounds of
+// a grand-product argument move a few KB: what the host waits for is the dependent chain inside one thread,
+// 12 field multiplications ~ 4.5 us on a lone warp).  FOUR lanes per (circuit k, pair index i):
+//   lane 0 / 1 / 2 binds its side (A_k / B_k / eq) at i and i+q (2 multiplications, do_bind != 0) and forms
+//   the side's values at t = 0, 2, 3; three quad shuffles hand lane t the three factors of its evaluation
+//   point, which it multiplies (2 multiplications): 4 dependent multiplications instead of 12.
+// Sums over i: xor-shuffles inside the warp, shared memory across warps, then either a direct tagged
+// publication (single CTA: no ticket, no fence) or the usual Finalize last-CTA stage.
+//   do_bind = 1: arrays hold 4q elements, pairs (i, i+2q) are bound with r into (i), then evaluated as (i, i+q)
+//   do_bind = 0: arrays hold 2q elements, evaluated as (i, i+q)               (q a power of two)
+__global__ void __launch_bounds__(1024)
+    sc_cubic_quad_kernel(fr_t* const* A, fr_t* const* B, const fr_t* Cin, fr_t* Cout, size_t q, int lg_q, int do_bind,
+                         fr_t r, int ncirc, Finalize fin) {
+  __shared__ fr_t s_part[256 * 3];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, role = tid & 3, lane = tid & 31;
+  const int upb = blockDim.x >> 2;  // (circuit, pair) units per CTA
+  const size_t U = (size_t)blockIdx.x * upb + (tid >> 2), total = (size_t)ncirc << lg_q;
+  const bool valid = U < total;
+  const int k = valid ? (int)(U >> lg_q) : 0;
+  const size_t i = U & (q - 1), h = 2 * q;
+  fr_t x0 = fr_zero(), x1 = fr_zero();
+  if (valid && role < 3) {
+    fr_t* src = role == 0 ? A[k] : role == 1 ? B[k] : const_cast<fr_t*>(Cin);
+    if (do_bind) {
+      fr_t lo = ld_fr(src + i), hi = ld_fr(src + i + h);
+      x0 = fr_add(lo, fr_mul(r, fr_sub(hi, lo)));
+      lo = ld_fr(src + i + q);
+      hi = ld_fr(src + i + q + h);
+      x1 = fr_add(lo, fr_mul(r, fr_sub(hi, lo)));
+      fr_t* dst = role == 2 ? (k == 0 ? Cout : nullptr) : src;
+      if (dst) {
+        st_fr(dst + i, x0);
+        st_fr(dst + i + q, x1);
+      }
+    } else {
+      x0 = ld_fr(src + i);
+      x1 = ld_fr(src + i + q);
+    }
+  }
+  // this side at t = 0, 2, 3
+  fr_t e0 = x0, d = fr_sub(x1, x0), e2 = fr_add(x1, d), e3 = fr_add(e2, d);
+  // round j: side s offers its value at t = (s + j) % 3; lane t reads side (t - j) mod 3 -> that side at t
+  fr_t P;
+  const int qbase = lane & ~3;
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const int sel = (role + j) % 3;
+    const fr_t offer = sel == 0 ? e0 : (sel == 1 ? e2 : e3);
+    const int src_lane = qbase + (role + 3 - j) % 3;
+    fr_t got;
+#pragma unroll
+    for (int l = 0; l < 8; l++) got.v[l] = __shfl_sync(0xffffffffu, offer.v[l], src_lane);
+    P = j == 0 ? got : fr_mul(P, got);
+  }
+  if (!valid || role == 3) P = fr_zero();
+  // sum over the pair indices of a circuit: gq = min(q, 8) consecutive units of a warp belong to one circuit
+  const int gq = q < 8 ? (int)q : 8;
+  for (int off = 1; off < gq; off <<= 1) {
+    fr_t o;
+#pragma unroll
+    for (int l = 0; l < 8; l++) o.v[l] = __shfl_xor_sync(0xffffffffu, P.v[l], off * 4);
+    P = fr_add(P, o);
+  }
+  const int unit = tid >> 2;
+  if ((unit & (gq - 1)) == 0 && role < 3) s_part[(unit / gq) * 3 + role] = P;
+  __syncthreads();
+  // block outputs: cpb circuits x 3 values, each the sum of gpc group partials
+  const int cpb = q >= (size_t)upb ? 1 : upb >> lg_q;
+  const int gpc = (int)((q >= (size_t)upb ? (size_t)upb : q) / gq);
+  const int bpv = q >= (size_t)upb ? (int)(q / upb) : 1;  // CTAs per circuit
+  int v = -1;
+  fr_t val = fr_zero();
+  if (tid < cpb * 3) {
+    const int cl = tid / 3, t = tid - 3 * cl;
+    const int kk = q >= (size_t)upb ? (int)(blockIdx.x / bpv) : (int)blockIdx.x * cpb + cl;
+    if (kk < ncirc) {
+      for (int w = 0; w < gpc; w++) val = fr_add(val, s_part[(cl * gpc + w) * 3 + t]);
+      v = kk * 3 + t;
+    }
+  }
+  if (gridDim.x == 1) {
+    if (v >= 0) finalize_publish(fin, v, val);
+    return;
+  }
+  if (v >= 0) {
+    fin.partial[(size_t)v * bpv + (blockIdx.x % bpv)] = val;
+    __threadfence();
+  }
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(fin.counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  finalize_last_stage(fin, bpv, 3 * ncirc);
+}
+static constexpr size_t kQuadMaxQ = 2048;  // beyond this the rounds are throughput-bound: thread-per-pair kernels
+static void launch_cubic_quad(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Cin, fr_t* Cout, int ncirc, size_t q,
+                              int do_bind, const fr_t& r, const Finalize& fin, cudaStream_t st) {
+  int lg_q = 0;
+  while (((size_t)1 << lg_q) < q) lg_q++;
+  const size_t threads = 4 * (size_t)ncirc * q;
+  if (threads <= 1024) {
+    unsigned t = (unsigned)((threads + 31) / 32 * 32);
+    sc_cubic_quad_kernel<<<1, t, 0, st>>>(d_A, d_B, Cin, Cout, q, lg_q, do_bind, r, ncirc, fin);
+  } else {
+    unsigned blocks = (unsigned)(((size_t)ncirc * q + 63) / 64);
+    sc_cubic_quad_kernel<<<blocks, 256, 0, st>>>(d_A, d_B, Cin, Cout, q, lg_q, do_bind, r, ncirc, fin);
+  }
+}
 void launch_sumcheck_bind_eval_cubic(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Cin, fr_t* Cout, int ncirc, size_t h,
                                      const fr_t& r, const Finalize& fin, cudaStream_t st) {
   size_t q = h / 2;
+  if (q <= kQuadMaxQ && (q & (q - 1)) == 0) return launch_cubic_quad(d_A, d_B, Cin, Cout, ncirc, q, 1, r, fin, st);
   int per = kMaxBlocks / ncirc;
   if (per < 1) per = 1;
   int bx = grid_for(q, kThreads, per);
@@ -353,6 +463,8 @@ void launch_sumcheck_bind_eval_cubic(fr_t* const* d_A, fr_t* const* d_B, const f
 }
 void launch_sumcheck_eval_cubic(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Ceq, int ncirc, size_t half,
                                 const Finalize& fin, cudaStream_t st) {
+  if (half <= kQuadMaxQ && (half & (half - 1)) == 0)
+    return launch_cubic_quad(d_A, d_B, Ceq, nullptr, ncirc, half, 0, fr_zero(), fin, st);
   int per = kMaxBlocks / ncirc;
   if (per < 1) per = 1;
   int bx = grid_for(half, kThreads, per);

@@ -44,12 +44,53 @@ void Ctx::d2h_small(void* dst, const void* src, size_t bytes) {
 }
 void Ctx::fin_wait(const Finalize& f, fr_t* dst, int count) {
   if (f.mapped) {
-    wait_flag(f.seq);
-    memcpy(dst, (const void*)h_mapped, (size_t)count * sizeof(fr_t));
+    // every element arrives as one 32-byte store carrying the round's tag in bits 29..31 of its last word
+    if ((size_t)count > kTaggedElems) throw std::runtime_error("round message larger than the tagged buffer");
+    volatile uint32_t* w = h_mapped + kTaggedWord0;
+    auto t0 = std::chrono::steady_clock::now();
+    unsigned spins = 0;
+    for (int v = 0; v < count; v++) {
+      while ((w[8 * v + 7] >> 29) != f.tag) {
+        __builtin_ia32_pause();
+        if ((++spins & 0xffff) == 0) {  // surface kernel faults instead of spinning forever
+          double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+          if (dt > 0.5) LB_CUDA_CHECK(cudaStreamQuery(st) == cudaErrorNotReady ? cudaSuccess : cudaStreamSynchronize(st));
+          if (dt > 120.0) throw std::runtime_error("timeout waiting for a device result");
+        }
+      }
+    }
+    __sync_synchronize();
+    memcpy(dst, (const void*)w, (size_t)count * sizeof(fr_t));
+    for (int v = 0; v < count; v++) {
+      dst[v].v[7] &= 0x1fffffffu;
+      w[8 * v + 7] = 0;  // consumed: no stale tag can satisfy a later wait
+    }
     return;
   }
   comm_allreduce_fr(this, d_small, count);
   d2h(dst, d_small, (size_t)count * sizeof(fr_t));
+}
+void Ctx::wait_points(int npoints, uint32_t* xyz) {
+  volatile uint32_t* w = h_mapped + kTaggedWord0;
+  const int count = 3 * npoints;
+  auto t0 = std::chrono::steady_clock::now();
+  unsigned spins = 0;
+  for (int v = 0; v < count; v++) {
+    while ((w[8 * v + 7] >> 31) == 0) {
+      __builtin_ia32_pause();
+      if ((++spins & 0xffff) == 0) {
+        double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (dt > 0.5) LB_CUDA_CHECK(cudaStreamQuery(st) == cudaErrorNotReady ? cudaSuccess : cudaStreamSynchronize(st));
+        if (dt > 120.0) throw std::runtime_error("timeout waiting for a device result");
+      }
+    }
+  }
+  __sync_synchronize();
+  memcpy(xyz, (const void*)w, (size_t)count * 32);
+  for (int v = 0; v < count; v++) {
+    xyz[8 * v + 7] &= 0x7fffffffu;
+    w[8 * v + 7] = 0;
+  }
 }
 void Ctx::wait_flag(uint32_t seq) {
   volatile uint32_t* flag = h_mapped + 1024;
@@ -93,8 +134,8 @@ Ctx* ctx_create(int device) {
   {
     const char* nm = getenv("LASSO_B200_NO_MAPPED");
     if (!(nm && nm[0] == '1')) {
-      LB_CUDA_CHECK(cudaHostAlloc((void**)&c->h_mapped, 4096 + 64, cudaHostAllocMapped));
-      memset(c->h_mapped, 0, 4096 + 64);
+      LB_CUDA_CHECK(cudaHostAlloc((void**)&c->h_mapped, Ctx::kMappedBytes, cudaHostAllocMapped));
+      memset(c->h_mapped, 0, Ctx::kMappedBytes);
       LB_CUDA_CHECK(cudaHostGetDevicePointer((void**)&c->d_mapped, c->h_mapped, 0));
     }
   }
@@ -888,12 +929,11 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
     // next one wherever the transcript allows it.
     //   (Cx, Cy): rows (x_vec, 0, 0) and (0.., y, 0) of one two-row MSM        (dot_product.rs:192-197)
     //   round k : fold with u_{k-1}, weights, L/R scalars, c_L, c_R -> two-row MSM   (bullet.rs:73-134)
-    auto read_two_points = [&](uint32_t seq, uint8_t* comp64) {
-      c->wait_flag(seq);
-      uint32_t xyzt[64];
-      memcpy(xyzt, (const void*)c->h_mapped, sizeof(xyzt));
-      h64::compress_xyz(xyzt, comp64);
-      h64::compress_xyz(xyzt + 32, comp64 + 32);
+    auto read_two_points = [&](uint32_t, uint8_t* comp64) {
+      uint32_t xyz[48];
+      c->wait_points(2, xyz);
+      h64::compress_xyz(xyz, comp64);
+      h64::compress_xyz(xyz + 24, comp64 + 32);
     };
     a_alt.alloc(c, n);
     b_alt.alloc(c, n);
@@ -903,7 +943,7 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
     auto two_row_msm = [&]() {
       const uint32_t seq = ++c->mapped_seq;
       launch_msm_rows(g.d_table.p, g.n_points, 1, sLR.p, 8, n + 2, 2, (int)(n + 2), kMsmFullWindows, 1, 0, part.p, nullptr,
-                      nullptr, nullptr, c->st, c->d_mapped, seq);
+                      nullptr, nullptr, c->st, c->d_mapped + Ctx::kTaggedWord0, seq);
       g_launches += 2;
       return seq;
     };
@@ -1008,15 +1048,14 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
     const uint32_t seq = ++c->mapped_seq;
     DBuf<pt_ext> part(c, msm_partials_count(2, (int)(n + 2), kMsmFullWindows));
     launch_msm_rows(g.d_table.p, g.n_points, 1, sLR.p, 8, n + 2, 2, (int)(n + 2), kMsmFullWindows, 1, 0, part.p, nullptr,
-                    nullptr, nullptr, c->st, c->d_mapped, seq);
+                    nullptr, nullptr, c->st, c->d_mapped + Ctx::kTaggedWord0, seq);
     LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin, av, 32, cudaMemcpyDeviceToHost, c->st));
     LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin + 32, bv, 32, cudaMemcpyDeviceToHost, c->st));
     g_launches += 3;
-    c->wait_flag(seq);
-    uint32_t xyzt[64];
-    memcpy(xyzt, (const void*)c->h_mapped, sizeof(xyzt));
-    h64::compress_xyz(xyzt, out.delta);
-    h64::compress_xyz(xyzt + 32, out.beta);
+    uint32_t xyz[48];
+    c->wait_points(2, xyz);
+    h64::compress_xyz(xyz, out.delta);
+    h64::compress_xyz(xyz + 24, out.beta);
     c->sync();
     memcpy(ab, c->h_pin, 64);
     transcript.append_point_compressed("delta", out.delta);

@@ -52,6 +52,10 @@ struct Ctx {
   uint32_t* h_mapped = nullptr;  // [0..1024) payload words, [1024] flag
   uint32_t* d_mapped = nullptr;
   uint32_t mapped_seq = 0;
+  // tagged region of the mapped buffer (round messages of Fr elements, see common.cuh Finalize): words
+  // [kTaggedWord0, kTaggedWord0 + 8 * kTaggedElems); the flag-based payload [0, 1024) + flag word 1024 stay separate
+  static constexpr size_t kTaggedWord0 = 2048, kTaggedElems = 128, kMappedBytes = (2048 + 8 * 128) * 4;
+  uint32_t fin_seq = 0;
   cudaEvent_t ev_aux = nullptr;  // marks a device->host copy that overlaps later launches on the same stream
   void d2h_small(void* dst, const void* src, size_t bytes);  // prover.cu
   void wait_flag(uint32_t seq);                               // prover.cu
@@ -63,14 +67,16 @@ struct Ctx {
     f.counter = d_flag + 4;
     f.out_dev = d_small;
     f.mapped = nullptr;
-    f.seq = 0;
+    f.tag = 0;
     if (h_mapped && world == 1) {
-      f.mapped = d_mapped;
-      f.seq = ++mapped_seq;
+      f.mapped = d_mapped + kTaggedWord0;
+      f.tag = 1 + (fin_seq++ % 7);
     }
     return f;
   }
   void fin_wait(const Finalize& f, fr_t* dst, int count);  // prover.cu (sums over ranks when sharded)
+  // npoints x (X, Y, Z) canonical Fq limbs published by msm_finish_quad_kernel (tag = bit 255 of each coordinate)
+  void wait_points(int npoints, uint32_t* xyz /* npoints x 24 words */);
   // device -> host through the pinned buffer (small) or directly (large)
   void d2h(void* dst, const void* src, size_t bytes) {
     if (bytes <= 4096 && h_mapped) {
