@@ -104,7 +104,7 @@ void launch_expand_weights(const fr_t* w, fr_t* w_out, size_t n_in, const fr_t& 
 // scalars for the L / R MSMs over the ORIGINAL generators: see prover.cu
 void launch_bullet_round(const fr_t* a_in, const fr_t* b_in, const fr_t* w_in, fr_t* a_out, fr_t* b_out, fr_t* w_out, size_t n,
                          size_t m, int fold, const fr_t& u, const fr_t& uinv, const fr_t& blind_L, const fr_t& blind_R,
-                         fr_t* s_out, fr_t* partial, unsigned* counter, cudaStream_t st);
+                         fr_t* s_out, uint32_t* cols_out, fr_t* partial, unsigned* counter, cudaStream_t st);
 void launch_two_row_scalars(const fr_t* v, int scale, const fr_t& k, const fr_t& t00, const fr_t& t01, const fr_t& t10,
                             const fr_t& t11, size_t n, fr_t* out, cudaStream_t st);
 void launch_bullet_scalars(const fr_t* a, const fr_t* w, size_t n_loc, size_t m, int G, int g, int a_rep, fr_t* sL,

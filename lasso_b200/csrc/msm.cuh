@@ -32,6 +32,14 @@ void launch_msm_rows(const pt_niels* table, size_t table_stride, int shifted, co
 // raw[(k*nrows + row)*32 ..): (X,Y,Z,T) of source k; adds the nsrc sources per row (cross-GPU gather-then-add)
 void launch_sum_raw_points(const uint32_t* raw, int nsrc, int nrows, uint32_t* out_raw, uint32_t* out_comp, fq_t* out_ext,
                            cudaStream_t st);
+// multiples table M[w][j][d-1] = d * 2^(8w) * G_j (d = 1..128) of the first npts generators, from the window table T
+void launch_build_multiples(const pt_niels* T, size_t table_stride, size_t npts, int nwindows, pt_niels* M, cudaStream_t st);
+// bucket-free MSM of nrows <= 8 short rows over M (msm_kernels.cu): scalars = nrows x len canonical integers,
+// cols = generator index per term (null: term k uses generator k); partials: nrows x msm_direct_chunks(len);
+// tagged: mapped host memory, 3 coordinates per row (see launch_msm_rows)
+int msm_direct_chunks(int len);
+void launch_msm_direct(const pt_niels* M, size_t npts, const uint32_t* scalars, const uint32_t* cols, int nrows, int len,
+                       pt_ext* partials, uint32_t* out_raw, uint32_t* tagged, cudaStream_t st);
 void launch_combine_points(const fq_t* in_ext, int n, fq_t* out_ext, uint32_t* out_comp, cudaStream_t st);
 
 inline int msm_windows_for_bits(unsigned max_bits) {

@@ -489,8 +489,23 @@ __device__ __forceinline__ fq_t shfl_fq(unsigned mask, const fq_t& v, int src_la
   for (int l = 0; l < 8; l++) r.v[l] = __shfl_sync(mask, v.v[l], src_lane);
   return r;
 }
-__device__ __forceinline__ fq_t quad_add(unsigned mask, int lane, const fq_t& mine, const fq_t* q) {
+// second half of the 4-way addition: v = (A, B, D, C) on the four lanes -> (X3, Y3, Z3, T3)
+__device__ __forceinline__ fq_t quad_tail(unsigned mask, int lane, const fq_t& v) {  // v = A, B, D, C
   const int role = lane & 3, qb = lane & ~3;
+  const fq_t o = shfl_fq(mask, v, lane ^ 1);  // B, A, C, D
+  fq_t p1, p2 = fq_zero();
+  if (role == 0) p1 = fq_sub(o, v);           // E = B - A
+  else if (role == 1) p1 = fq_add(v, o);      // H = B + A
+  else if (role == 2) { p1 = fq_sub(v, o); p2 = fq_add(v, o); }  // F = D - C, G = D + C
+  else p1 = fq_add(o, v);                     // G
+  const int src_a = qb + (role == 0 ? 2 : role == 1 ? 3 : role == 2 ? 2 : 0);
+  fq_t a = shfl_fq(mask, p1, src_a);
+  const fq_t b = shfl_fq(mask, p1, qb + 1);
+  if (role == 2) a = p2;
+  return fq_mul(role == 3 ? a : p1, role == 3 ? b : a);  // X3 = E F, Y3 = H G, Z3 = F G, T3 = E H
+}
+__device__ __forceinline__ fq_t quad_add(unsigned mask, int lane, const fq_t& mine, const fq_t* q) {
+  const int role = lane & 3;
   const fq_t partner = shfl_fq(mask, mine, lane ^ 1);  // X <-> Y (Z <-> T unused)
   fq_t s1, m;
   if (role == 0) {
@@ -506,20 +521,7 @@ __device__ __forceinline__ fq_t quad_add(unsigned mask, int lane, const fq_t& mi
     s1 = mine;
     m = fq_mul(q[3], fq_d2());  // C = T1 * (2d T2)
   }
-  const fq_t v = fq_mul(s1, m);                   // A, B, D, C
-  const fq_t o = shfl_fq(mask, v, lane ^ 1);      // B, A, C, D
-  fq_t p1, p2 = fq_zero();
-  if (role == 0) p1 = fq_sub(o, v);               // E = B - A
-  else if (role == 1) p1 = fq_add(v, o);          // H = B + A
-  else if (role == 2) { p1 = fq_sub(v, o); p2 = fq_add(v, o); }  // F = D - C, G = D + C
-  else p1 = fq_add(o, v);                         // G
-  // lane 0 <- F (lane 2), lane 1 <- G (lane 3), lane 3 <- E (lane 0); lane 2 has G itself
-  const int src_a = qb + (role == 0 ? 2 : role == 1 ? 3 : role == 2 ? 2 : 0);
-  fq_t a = shfl_fq(mask, p1, src_a);
-  const fq_t b = shfl_fq(mask, p1, qb + 1);       // H, for lane 3
-  if (role == 2) a = p2;
-  // X3 = E F, Y3 = H G, Z3 = F G, T3 = E H
-  return fq_mul(role == 3 ? a : p1, role == 3 ? b : a);
+  return quad_tail(mask, lane, fq_mul(s1, m));  // A, B, D, C -> X3, Y3, Z3, T3
 }
 // Finish for a handful of rows over a shifted table (the rounds of the opening proofs): ONE CTA, 32 quads
 // per row; each quad adds its share of the row's partials, then a 5-level tree through shared memory.
@@ -565,6 +567,140 @@ __global__ void __launch_bounds__(1024)
       st_fq(reinterpret_cast<fq_t*>(tagged) + row * 3 + role, c);
     }
   }
+}
+
+// ---------------------------------------------------------------- bucket-free MSM over a multiples table
+// The MSMs of the opening proofs are short (two rows of ~1-8 K terms) and sit on the critical path ~50 times
+// per proof: the bucket method spends most of its ~100 us on the fixed 14-step weighted bucket sum.  180 GB of
+// HBM buy a shortcut: for the first `npts` generators (the ones the openings use) keep every digit multiple
+//   M[w][j][d-1] = d * 2^(8w) * G_j,  d = 1..128, affine-niels (96 B): 32 * npts * 128 * 96 B (0.8 GB at
+//   npts = 2050, the 2^20-lookup configuration),
+// so a term is ONE table entry per window and the MSM is a plain sum of (terms x 32) points: quads of lanes
+// (quad_add above) add ~4 entries each, a shared-memory tree adds the 128 quads of a CTA, and the quad finish
+// kernel adds the CTAs of a row.  No sort, no buckets, no doublings; depth ~ 4 mixed + 7 + 7 full additions
+// at quad-lane latency.
+// Built once per generator set: thread (w, j) walks d = 1..128 (one mixed addition each) and normalises.
+__global__ void __launch_bounds__(128)
+    multiples_table_kernel(const pt_niels* T, size_t table_stride, size_t npts, int nwindows, pt_niels* M) {
+  const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= (size_t)nwindows * npts) return;
+  const size_t w = id / npts, j = id - w * npts;
+  const pt_niels base = ld_niels(T + w * table_stride + j);
+  pt_niels* out = M + id * 128;
+  st_niels(out, base);
+  pt_ext acc = pt_from_niels(base);
+  for (int d = 2; d <= 128; d++) {
+    acc = pt_madd(acc, base);
+    const fq_t zi = fq_inv(acc.Z);
+    st_niels(out + (d - 1), niels_from_affine(fq_mul(acc.X, zi), fq_mul(acc.Y, zi)));
+  }
+}
+void launch_build_multiples(const pt_niels* T, size_t table_stride, size_t npts, int nwindows, pt_niels* M, cudaStream_t st) {
+  const size_t n = (size_t)nwindows * npts;
+  multiples_table_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(T, table_stride, npts, nwindows, M);
+}
+
+// mixed quad addition: the quad's accumulator + one affine-niels entry; lane 0 / 1 / 3 hold the entry's
+// (y-x | y+x) / (y+x | y-x) / (+-2dxy) already selected for the sign of the digit
+__device__ __forceinline__ fq_t quad_madd(unsigned mask, int lane, const fq_t& mine, const fq_t& operand) {
+  const int role = lane & 3;
+  const fq_t partner = shfl_fq(mask, mine, lane ^ 1);
+  fq_t v;
+  if (role == 0) v = fq_mul(fq_sub(partner, mine), operand);       // A = (Y1 - X1)(y2 - x2)
+  else if (role == 1) v = fq_mul(fq_add(mine, partner), operand);  // B = (Y1 + X1)(y2 + x2)
+  else if (role == 2) v = fq_dbl(mine);                            // D = 2 Z1
+  else v = fq_mul(mine, operand);                                  // C = T1 * 2d x2 y2
+  return quad_tail(mask, lane, v);
+}
+
+static constexpr int MSMD_T = 512;  // 128 quads
+// scalars: nrows x len canonical 256-bit integers; cols (may be null = identity): generator index of each term.
+// CTA (chunk, row) takes the terms k = chunk (mod nchunks): an odd nchunks spreads any power-of-two pattern of
+// zero scalars evenly.  Quad (w, sub): window w of the terms chunk + nchunks * (sub + 4 i).
+__global__ void __launch_bounds__(MSMD_T)
+    msm_direct_kernel(const pt_niels* M, size_t npts, const uint32_t* scalars, const uint32_t* cols, int len, pt_ext* partials) {
+  __shared__ fq_t sm_pt[128 * 4];
+  const int tid = threadIdx.x, lane = tid & 31, role = tid & 3, quad = tid >> 2;
+  const int w = quad & 31, sub = quad >> 5;
+  const int chunk = blockIdx.x, nchunks = gridDim.x, row = blockIdx.y;
+  const uint32_t* srow = scalars + (size_t)row * len * 8;
+  const uint32_t* crow = cols ? cols + (size_t)row * len : nullptr;
+  fq_t mine = (role == 1 || role == 2) ? fq_one() : fq_zero();  // identity (0, 1, 1, 0)
+  // operand of an entry for this lane; digit 0 -> the identity entry (1, 1, 0): the control flow stays uniform
+  auto fetch = [&](int k, fq_t& op) -> bool {
+    uint32_t sw[8];
+    uint32_t any = 0;
+#pragma unroll
+    for (int l = 0; l < 8; l++) {
+      sw[l] = srow[(size_t)k * 8 + l];
+      any |= sw[l];
+    }
+    if (any == 0) return false;  // zero scalar: the same for the whole warp (all its quads share k)
+    const MsmDigits<8> dg(sw);
+    uint32_t limb = 0;
+#pragma unroll
+    for (int l = 0; l < 8; l++) limb = (l == (w >> 2)) ? dg.b[l] : limb;
+    const int d = (int)((limb >> (8 * (w & 3))) & 0xff) - 128;
+    const int ad = d < 0 ? -d : d;
+    op = role == 3 ? fq_zero() : fq_one();
+    if (ad != 0 && role != 2) {
+      const size_t col = crow ? crow[k] : (size_t)k;
+      const pt_niels* e = M + ((size_t)w * npts + col) * 128 + (ad - 1);
+      const bool neg = d < 0;
+      if (role == 0) op = ld_fq(neg ? &e->yplusx : &e->yminusx);
+      else if (role == 1) op = ld_fq(neg ? &e->yminusx : &e->yplusx);
+      else {
+        op = ld_fq(&e->t2d);
+        if (neg) op = fq_neg(op);
+      }
+    }
+    return true;
+  };
+  const int step = nchunks * 4;
+  int k = chunk + nchunks * sub;
+  fq_t op, op_next;
+  bool have = k < len ? fetch(k, op) : false;
+  while (k < len) {  // uniform per warp: its 8 quads share sub, hence k
+    const int kn = k + step;
+    const bool have_next = kn < len ? fetch(kn, op_next) : false;  // next entry in flight during this addition
+    if (have) mine = quad_madd(0xffffffffu, lane, mine, op);
+    op = op_next;
+    have = have_next;
+    k = kn;
+  }
+  // tree over the 128 quads
+  fq_t* slot = sm_pt + quad * 4;
+  slot[role] = mine;
+  __syncthreads();
+  for (int d = 64; d >= 1; d >>= 1) {
+    fq_t r = mine;
+    if (quad < d) r = quad_add(d >= 8 ? 0xffffffffu : (0xfu << (lane & ~3)), lane, mine, slot + 4 * d);
+    __syncthreads();
+    if (quad < d) {
+      mine = r;
+      slot[role] = mine;
+    }
+    __syncthreads();
+  }
+  if (quad == 0) {
+    fq_t* out = reinterpret_cast<fq_t*>(partials + (size_t)row * nchunks + chunk);
+    st_fq(out + role, mine);
+  }
+}
+// nrows (<= 8) short MSMs over the multiples table; result published like launch_msm_rows(..., mapped)
+int msm_direct_chunks(int len) {
+  int c = (len * kMsmFullWindows + 128 * 4 - 1) / (128 * 4);  // ~4 entries per quad
+  if (c > 73) c = 73;
+  if (c < 1) c = 1;
+  return c | 1;
+}
+void launch_msm_direct(const pt_niels* M, size_t npts, const uint32_t* scalars, const uint32_t* cols, int nrows, int len,
+                       pt_ext* partials, uint32_t* out_raw, uint32_t* tagged, cudaStream_t st) {
+  if (nrows < 1 || nrows > 8) throw std::runtime_error("msm_direct: 1..8 rows");
+  const int nchunks = msm_direct_chunks(len);
+  dim3 grid(nchunks, nrows);
+  msm_direct_kernel<<<grid, MSMD_T, 0, st>>>(M, npts, scalars, cols, len, partials);
+  msm_finish_quad_kernel<<<1, 128 * nrows, 0, st>>>(partials, nrows, nchunks, out_raw, tagged);
 }
 
 // Launch geometry.  wpc = windows per CTA (all of them over a shifted table), ngroups = window groups,

@@ -711,16 +711,19 @@ void launch_bullet_scalars(const fr_t* a, const fr_t* w, size_t n_loc, size_t m,
 // critical path of every round.
 //   a_in, b_in : length 2m when fold != 0 (folded here into a_out, b_out of length m), else length m
 //   w_in       : n/(2m) weights when fold != 0 (expanded into w_out, n/m weights), else n/m weights
-//   s_out      : 2 rows x (n + 2) canonical scalars: row 0 = L, row 1 = R; columns n, n+1 = (c, blind)
-// Thread j <-> generator column j = t*m + pos.  h = m/2:  L[j] = a'[pos-h] w'[t] (pos >= h),
-// R[j] = a'[pos+h] w'[t] (pos < h).  Threads j < h also own the pair (pos, pos+h) of a', b'.
+//   s_out      : 2 rows x (n/2 + 2) canonical scalars, row 0 = L, row 1 = R, with the generator index of every
+//                term in cols_out (same shape): each generator is in exactly one of L, R, so the rows are
+//                stored compacted; the last two terms of a row are (c, blind) on the generators n (Q), n+1 (h)
+// Thread j <-> generator column j = t*m + pos.  h = m/2:  L gets a'[pos-h] w'[t] G_j for pos >= h (term t*h +
+// pos-h), R gets a'[pos+h] w'[t] G_j for pos < h (term t*h + pos).  Threads j < h also own the pair (pos, pos+h)
+// of a', b'.
 __global__ void __launch_bounds__(kThreads)
     bullet_round_kernel(const fr_t* a_in, const fr_t* b_in, const fr_t* w_in, fr_t* a_out, fr_t* b_out, fr_t* w_out,
                         size_t n, size_t m, int fold, fr_t u, fr_t uinv, fr_t blind_L, fr_t blind_R, fr_t* s_out,
-                        fr_t* partial, unsigned* counter) {
+                        uint32_t* cols_out, fr_t* partial, unsigned* counter) {
   __shared__ fr_t scratch[2 * kThreads / 32];
   __shared__ int s_last;
-  const size_t h = m / 2, stride = n + 2;
+  const size_t h = m / 2, stride = n / 2 + 2;
   const int lg_m = 63 - __clzll((long long)m);
   fr_t acc[2] = {fr_zero(), fr_zero()};
   auto folded_a = [&](size_t i) {
@@ -738,8 +741,9 @@ __global__ void __launch_bounds__(kThreads)
     const size_t idx = is_l ? pos - h : pos + h;
     const fr_t ai = folded_a(idx);
     const fr_t sc = fr_to_canonical(fr_mul(ai, wt));
-    st_fr(s_out + j, is_l ? sc : fr_zero());
-    st_fr(s_out + stride + j, is_l ? fr_zero() : sc);
+    const size_t term = (is_l ? 0 : stride) + t * h + (is_l ? pos - h : pos);
+    st_fr(s_out + term, sc);
+    cols_out[term] = (uint32_t)j;
     if (t == 0 && pos < h) {  // owner of the pair (pos, pos + h): ai = a'[pos + h]
       const fr_t alo = folded_a(pos), blo = folded_b(pos), bhi = folded_b(idx);
       if (fold) {
@@ -768,18 +772,20 @@ __global__ void __launch_bounds__(kThreads)
     for (unsigned i = lane; i < gridDim.x; i += 32) v = fr_add(v, ld_fr_cg(partial + (size_t)warp * gridDim.x + i));
     v = warp_sum_fr(v);
     if (lane == 0) {
-      st_fr(s_out + (size_t)warp * stride + n, fr_to_canonical(v));
-      st_fr(s_out + (size_t)warp * stride + n + 1, fr_to_canonical(warp == 0 ? blind_L : blind_R));
+      st_fr(s_out + (size_t)warp * stride + n / 2, fr_to_canonical(v));
+      st_fr(s_out + (size_t)warp * stride + n / 2 + 1, fr_to_canonical(warp == 0 ? blind_L : blind_R));
+      cols_out[(size_t)warp * stride + n / 2] = (uint32_t)n;
+      cols_out[(size_t)warp * stride + n / 2 + 1] = (uint32_t)(n + 1);
     }
   }
   if (threadIdx.x == 0) *counter = 0;
 }
 void launch_bullet_round(const fr_t* a_in, const fr_t* b_in, const fr_t* w_in, fr_t* a_out, fr_t* b_out, fr_t* w_out, size_t n,
                          size_t m, int fold, const fr_t& u, const fr_t& uinv, const fr_t& blind_L, const fr_t& blind_R,
-                         fr_t* s_out, fr_t* partial, unsigned* counter, cudaStream_t st) {
+                         fr_t* s_out, uint32_t* cols_out, fr_t* partial, unsigned* counter, cudaStream_t st) {
   unsigned blocks = (unsigned)((n + kThreads - 1) / kThreads);
   bullet_round_kernel<<<blocks, kThreads, 0, st>>>(a_in, b_in, w_in, a_out, b_out, w_out, n, m, fold, u, uinv, blind_L,
-                                                   blind_R, s_out, partial, counter);
+                                                   blind_R, s_out, cols_out, partial, counter);
 }
 // Two MSM rows over the n + 2 generators (G_0..G_{n-1}, Q, h) in canonical form:
 //   row 0 = (k * v[0..n), t00, t01)    row 1 = (0 .. 0, t10, t11)

@@ -198,6 +198,18 @@ Gens* gens_create(Ctx* c, const uint64_t* stream_affine, size_t n_points, size_t
   g->d_table.alloc(c, (size_t)kMsmFullWindows * n_points);
   launch_build_table(g->d_bases_ark.p, n_points, g->d_table.p, n_points, kMsmFullWindows, c->st);
   g_launches += kMsmFullWindows;
+  {
+    // widest opening: R_size = 2^(nv - nv/2) generators + Q + h (dense_mlpoly.rs:301-316)
+    size_t nv = std::max(g->nv_l, std::max(g->nv_m, g->nv_d));
+    size_t nd = ((size_t)1 << (nv - nv / 2)) + 2;
+    const char* off = getenv("LASSO_B200_NO_MULTIPLES");
+    if (c->world == 1 && nd <= n_points && !(off && off[0] == '1')) {
+      g->n_direct = nd;
+      g->d_multiples.alloc(c, (size_t)kMsmFullWindows * nd * 128);
+      launch_build_multiples(g->d_table.p, n_points, nd, kMsmFullWindows, g->d_multiples.p, c->st);
+      g_launches += 1;
+    }
+  }
   c->sync();
   return g.release();
 }
@@ -882,7 +894,8 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
   std::vector<fr_t> v1 = tape.random_vector("blinds_vec_1", 2 * lg_n);
   std::vector<fr_t> v2 = tape.random_vector("blinds_vec_2", 2 * lg_n);
   DotProductProofLogBytes out;
-  const bool fast = G == 1 && c->h_mapped != nullptr && n * 32 <= c->h_pin_bytes;  // single-GPU pipeline below
+  // single-GPU pipeline below: needs the multiples table of the generators 0 .. n+1
+  const bool fast = G == 1 && c->h_mapped != nullptr && n * 32 <= c->h_pin_bytes && g.d_multiples.p && n + 2 <= g.n_direct;
   DBuf<fr_t> two(c, 4);
   if (!fast) {
     // Cx = batch_commit(x_vec, blind_x = 0) ; Cy = y*Q + 0*h
@@ -938,17 +951,18 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
     a_alt.alloc(c, n);
     b_alt.alloc(c, n);
     fr_t *an = a_alt.p, *bn = b_alt.p;
-    DBuf<pt_ext> part(c, msm_partials_count(2, (int)(n + 2), kMsmFullWindows));
+    DBuf<pt_ext> part(c, 2 * (size_t)msm_direct_chunks((int)(n + 2)));
     DBuf<fr_t> canon(c, n);
-    auto two_row_msm = [&]() {
-      const uint32_t seq = ++c->mapped_seq;
-      launch_msm_rows(g.d_table.p, g.n_points, 1, sLR.p, 8, n + 2, 2, (int)(n + 2), kMsmFullWindows, 1, 0, part.p, nullptr,
-                      nullptr, nullptr, c->st, c->d_mapped + Ctx::kTaggedWord0, seq);
+    DBuf<uint32_t> cols(c, 2 * (n / 2 + 2));
+    // two short rows over the multiples table; len terms per row, generator index per term in cols (or identity)
+    auto two_row_msm = [&](const uint32_t* d_cols, size_t len) {
+      launch_msm_direct(g.d_multiples.p, g.n_direct, (const uint32_t*)sLR.p, d_cols, 2, (int)len, part.p, nullptr,
+                        c->d_mapped + Ctx::kTaggedWord0, c->st);
       g_launches += 2;
-      return seq;
+      return 0u;
     };
     launch_two_row_scalars(av, 0, fr_one(), fr_zero(), fr_zero(), Zr, fr_zero(), n, sLR.p, c->st);
-    uint32_t seq = two_row_msm();
+    uint32_t seq = two_row_msm(nullptr, n + 2);
     // a_vec of the transcript = canonical bytes of b; the copy is waited for only when it is appended
     launch_canonicalize(bv, canon.p, n, c->d_flag, c->st);
     LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin, canon.p, n * 32, cudaMemcpyDeviceToHost, c->st));
@@ -960,7 +974,7 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
     int fold = 0;
     size_t m = n;  // vector length entering the round (after the fold with the previous challenge)
     auto launch_round = [&](size_t round) {
-      launch_bullet_round(av, bv, W, an, bn, Wn, n, m, fold, u, u_inv, v1[round], v2[round], sLR.p, c->d_partial,
+      launch_bullet_round(av, bv, W, an, bn, Wn, n, m, fold, u, u_inv, v1[round], v2[round], sLR.p, cols.p, c->d_partial,
                           c->d_flag + 4, c->st);
       g_launches += 1;
       if (fold) {
@@ -968,7 +982,7 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
         std::swap(bv, bn);
         std::swap(W, Wn);
       }
-      return two_row_msm();
+      return two_row_msm(cols.p, n / 2 + 2);
     };
     if (m != 1) seq = launch_round(0);  // round 0 needs no challenge: it runs while the host absorbs Cx, Cy, a
     transcript.append_point_compressed("Cx", CxCy);
@@ -1045,10 +1059,9 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
     // delta = d * g_hat + r_delta * h with g_hat = sum_j W[j] G_j (dot_product.rs:219-227) and
     // beta = d * Q + r_beta * h (dot_product.rs:229-230) as the two rows of one MSM
     launch_two_row_scalars(W, 1, d, fr_zero(), r_delta, d, r_beta, n, sLR.p, c->st);
-    const uint32_t seq = ++c->mapped_seq;
-    DBuf<pt_ext> part(c, msm_partials_count(2, (int)(n + 2), kMsmFullWindows));
-    launch_msm_rows(g.d_table.p, g.n_points, 1, sLR.p, 8, n + 2, 2, (int)(n + 2), kMsmFullWindows, 1, 0, part.p, nullptr,
-                    nullptr, nullptr, c->st, c->d_mapped + Ctx::kTaggedWord0, seq);
+    DBuf<pt_ext> part(c, 2 * (size_t)msm_direct_chunks((int)(n + 2)));
+    launch_msm_direct(g.d_multiples.p, g.n_direct, (const uint32_t*)sLR.p, nullptr, 2, (int)(n + 2), part.p, nullptr,
+                      c->d_mapped + Ctx::kTaggedWord0, c->st);
     LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin, av, 32, cudaMemcpyDeviceToHost, c->st));
     LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin + 32, bv, 32, cudaMemcpyDeviceToHost, c->st));
     g_launches += 3;

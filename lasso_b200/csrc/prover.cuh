@@ -157,6 +157,10 @@ struct Gens {
   size_t nv_l = 0, nv_m = 0, nv_d = 0;  // num_vars of the three committed polynomials
   DBuf<fq_t> d_bases_ark;               // n_points x (x, y)
   DBuf<pt_niels> d_table;               // kMsmFullWindows x n_points, T[w][j] = 2^(8w) G_j
+  // multiples M[w][j][d-1] = d * T[w][j] (d = 1..128) of the first n_direct generators: the bucket-free MSM of
+  // the opening proofs (msm_kernels.cu).  Single-GPU contexts only; empty -> the bucket MSM is used.
+  DBuf<pt_niels> d_multiples;
+  size_t n_direct = 0;
 };
 
 // DensifiedRepresentation<F, C> (lasso/densified.rs:8-18), device resident

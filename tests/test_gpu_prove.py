@@ -69,6 +69,25 @@ def test_prove_matches_oracle(ctx, name, kind, C, log_m, log_r, n, same):
     assert proof.bytes == ref["proof"]
 
 
+@pytest.mark.parametrize("name,kind,C,log_m,log_r,n,same", [CASES[0], CASES[3]])
+def test_prove_without_multiples_table(ctx, monkeypatch, name, kind, C, log_m, log_r, n, same):
+    """LASSO_B200_NO_MULTIPLES=1: the openings fall back to the bucket MSM + per-step kernels (the path a sharded
+    proof and memory-constrained setups use); bytes must not change."""
+    import lasso_b200 as lb
+
+    monkeypatch.setenv("LASSO_B200_NO_MULTIPLES", "1")
+    idx, r, seed, s = make_inputs(C, log_m, n, len(name), same)
+    S = lb.Strategy(kind, C, log_m, log_r)
+    need = lb.gens_points_needed(C, s, S.num_memories, log_m)
+    stream = np.ascontiguousarray(ol.generators(max(need, 300))[:need])
+    gens = lb.SparsePolyCommitmentGens.new(ctx, b"gens_sparse_poly", C, s, S.num_memories, log_m, stream=stream)
+    dense = lb.DensifiedRepresentation.from_lookup_indices(ctx, idx, log_m)
+    commitment = dense.commit(gens)
+    proof = lb.SparsePolynomialEvaluationProof.prove(ctx, S, dense, r, gens, tape_seed=seed)
+    ref = ol.prove(kind, C, log_m, log_r, idx, r, stream, seed, flags=1)
+    assert commitment == ref["commitment"] and proof.bytes == ref["proof"]
+
+
 def test_headline_config_full_size(ctx):
     """BASELINE configs[1] at its FULL size — XOR, C=4, M=2^16, 2^20 lookups: commitment and proof bytes of the GPU
     path equal the oracle's (which its own verifier accepts).  The oracle takes ~10-20 s on the box's host cores."""

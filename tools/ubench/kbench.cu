@@ -92,7 +92,7 @@ int main(int argc, char** argv) {
     for (size_t m : {n / 2, (size_t)64, (size_t)2}) {
       snprintf(nm, sizeof nm, "bullet_round n=%zu m=%zu fold=1", n, m);
       printf("%-52s %8.2f us\n", nm,
-             time_us([&] { launch_bullet_round(a0, b0, w0, a1, b1, w1, n, m, 1, r, r, r, r, sLR, partial, counter, st); }, 500, st));
+             time_us([&] { launch_bullet_round(a0, b0, w0, a1, b1, w1, n, m, 1, r, r, r, r, sLR, (uint32_t*)hB[5], partial, counter, st); }, 500, st));
     }
     // table for n+2 generators: any niels-shaped data works for timing (field ops are data-independent)
     pt_niels* table;
@@ -108,6 +108,31 @@ int main(int argc, char** argv) {
              launch_msm_rows(table, n + 2, 1, sLR, 8, n + 2, 2, (int)(n + 2), kMsmFullWindows, 1, 0, part, nullptr, nullptr, nullptr,
                              st, d_mapped, 7);
            }, 300, st));
+    {  // bucket-free MSM over the multiples table
+      pt_niels* M;
+      const size_t npts = n + 2;
+      if (cudaMalloc(&M, (size_t)kMsmFullWindows * npts * 128 * sizeof(pt_niels)) == cudaSuccess) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+        launch_build_multiples(table, n + 2, npts, kMsmFullWindows, M, st);
+        cudaEventRecord(e1, st);
+        cudaStreamSynchronize(st);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        snprintf(nm, sizeof nm, "build multiples table, %zu generators (%.0f MB)", npts, kMsmFullWindows * npts * 128 * 96 / 1e6);
+        printf("%-52s %8.2f ms\n", nm, ms);
+        // compact bullet-round shape: n/2 + 2 terms per row, all non-zero; identity columns
+        snprintf(nm, sizeof nm, "msm_direct 2 rows x %zu terms (direct+finish)", n / 2 + 2);
+        printf("%-52s %8.2f us\n", nm,
+               time_us([&] { launch_msm_direct(M, npts, (const uint32_t*)sLR, nullptr, 2, (int)(n / 2 + 2), part, nullptr, d_mapped, st); }, 300, st));
+        snprintf(nm, sizeof nm, "msm_direct 2 rows x %zu terms (direct+finish)", n + 2);
+        printf("%-52s %8.2f us\n", nm,
+               time_us([&] { launch_msm_direct(M, npts, (const uint32_t*)sLR, nullptr, 2, (int)(n + 2), part, nullptr, d_mapped, st); }, 300, st));
+        cudaFree(M);
+      }
+    }
     cudaFree(table);
     cudaFree(part);
   }
