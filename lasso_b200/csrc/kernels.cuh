@@ -94,6 +94,15 @@ void launch_gp_fingerprints_ops(const fr_t* dim_fr, const fr_t* E_fr, const fr_t
                                 cudaStream_t st);
 // product-tree layer (grand_product.rs:20-36): out[i] = in[i] * in[i + n_out], i < n_out
 void launch_product_layer(const fr_t* in, fr_t* out, size_t n_out, cudaStream_t st);
+// every product tree of one size N (contiguous layers, see poly_kernels.cu) + tagged publication of the two
+// top-layer elements of tree t as values 2*(slot0 + t) + {0, 1}
+struct TreePtrs {
+  fr_t* p[32];
+};
+void launch_product_trees(const TreePtrs& trees, int ntrees, size_t N, int slot0, const Finalize& fin, cudaStream_t st);
+int product_trees_launches(size_t N);
+// x_k[0] <- x_k[0] + r (x_k[1] - x_k[0]) for the n arrays x_k = d_AB[k]; results also published (Finalize)
+void launch_bind_heads(fr_t* const* d_AB, int n, const fr_t& r, const Finalize& fin, cudaStream_t st);
 // elementwise helpers for the Bulletproofs scalar folds (bullet.rs:125-130)
 // a[i] <- a[i]*u + uinv*a[i+h];  b[i] <- b[i]*uinv + u*b[i+h]
 void launch_fold_ab(fr_t* a, fr_t* b, size_t h, const fr_t& u, const fr_t& uinv, cudaStream_t st);

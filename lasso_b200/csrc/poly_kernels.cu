@@ -634,6 +634,60 @@ void launch_product_layer(const fr_t* in, fr_t* out, size_t n_out, cudaStream_t 
   product_layer_kernel<<<grid_for(n_out), kThreads, 0, st>>>(in, out, n_out);
 }
 
+// All product trees of one size at once (single GPU).  A tree is one contiguous array: layer 0 (N elements),
+// then layer 1 (N/2), ...; layer k+1[i] = layer k[i] * layer k[i + len/2].  One launch per layer for every
+// tree (blockIdx.y) while the layers are large, then ONE CTA per tree walks the remaining small layers with
+// a barrier in between and publishes the two elements of the top layer (grand_product.rs:60-65 `evaluate`)
+// as tagged values 2*slot0 + 2*tree + {0, 1}: ~16 launches per proof instead of ~270 + 16 small copies.
+__global__ void __launch_bounds__(kThreads) product_layers_kernel(TreePtrs trees, size_t in_off, size_t n_out) {
+  const fr_t* in = trees.p[blockIdx.y] + in_off;
+  fr_t* out = trees.p[blockIdx.y] + in_off + 2 * n_out;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (size_t)gridDim.x * blockDim.x)
+    st_fr(out + i, fr_mul(ld_fr(in + i), ld_fr(in + n_out + i)));
+}
+__global__ void __launch_bounds__(1024) product_tail_kernel(TreePtrs trees, size_t off, size_t len, int slot0, Finalize fin) {
+  fr_t* base = trees.p[blockIdx.x];
+  while (len > 2) {
+    const size_t n_out = len / 2;
+    for (size_t i = threadIdx.x; i < n_out; i += blockDim.x)
+      st_fr(base + off + len + i, fr_mul(ld_fr(base + off + i), ld_fr(base + off + n_out + i)));
+    __syncthreads();
+    off += len;
+    len = n_out;
+  }
+  if (threadIdx.x < 2) finalize_publish(fin, 2 * (slot0 + (int)blockIdx.x) + (int)threadIdx.x, ld_fr(base + off + threadIdx.x));
+}
+void launch_product_trees(const TreePtrs& trees, int ntrees, size_t N, int slot0, const Finalize& fin, cudaStream_t st) {
+  size_t off = 0, len = N;
+  while (len > 4096) {
+    const size_t n_out = len / 2;
+    dim3 grid(grid_for(n_out, kThreads, kMaxBlocks / ntrees + 1), ntrees);
+    product_layers_kernel<<<grid, kThreads, 0, st>>>(trees, off, n_out);
+    off += len;
+    len = n_out;
+  }
+  product_tail_kernel<<<ntrees, 1024, 0, st>>>(trees, off, len, slot0, fin);
+}
+int product_trees_launches(size_t N) {
+  int n = 1;
+  for (size_t len = N; len > 4096; len /= 2) n++;
+  return n;
+}
+// last round of a batched cubic sumcheck (one element pair left per array): bind the 2*ncirc heads with r in
+// place and publish them — they are the layer's claims (grand_product.rs:139-150)
+__global__ void bind_heads_kernel(fr_t* const* AB, int n, fr_t r, Finalize fin) {
+  const int k = threadIdx.x;
+  if (k >= n) return;
+  fr_t* x = AB[k];
+  const fr_t lo = ld_fr(x), hi = ld_fr(x + 1);
+  const fr_t v = fr_add(lo, fr_mul(r, fr_sub(hi, lo)));
+  st_fr(x, v);
+  finalize_publish(fin, k, v);
+}
+void launch_bind_heads(fr_t* const* d_AB, int n, const fr_t& r, const Finalize& fin, cudaStream_t st) {
+  bind_heads_kernel<<<1, (n + 31) / 32 * 32, 0, st>>>(d_AB, n, r, fin);
+}
+
 // ---- Bulletproofs scalar-side helpers (bullet.rs:73-134) ----
 __global__ void __launch_bounds__(kThreads) fold_ab_kernel(fr_t* a, fr_t* b, size_t h, fr_t u, fr_t uinv) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < h; i += (size_t)gridDim.x * blockDim.x) {

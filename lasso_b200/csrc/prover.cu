@@ -738,7 +738,7 @@ static GPAProof prove_gpa(Ctx* c, std::vector<Circuit*>& circuits, std::vector<f
     std::vector<fr_t> rand_prod;
     fr_t* Ccur = eqbuf.p;
     fr_t* Cnext = eqbuf2.p;
-    bool have_evals = false;
+    bool have_evals = false, heads_published = false;
     Finalize fz = c->fin_begin();
     for (;;) {
       if (sharded && cur == 1) {  // all-gather the G-element remainders; the tail rounds run replicated
@@ -785,6 +785,13 @@ static GPAProof prove_gpa(Ctx* c, std::vector<Circuit*>& circuits, std::vector<f
         g_launches += 1;
         std::swap(Ccur, Cnext);
         have_evals = true;
+      } else if (fz.mapped) {
+        // last round: bind the 2*ncirc heads and publish them (the layer's claims); eq is not needed any more
+        fz = c->fin_begin();
+        launch_bind_heads(dAB, 2 * ncirc, r_j, fz, c->st);
+        g_launches += 1;
+        have_evals = false;
+        heads_published = true;
       } else {
         launch_bind_top_ptrs(dAB, 2 * ncirc, half, r_j, c->st);
         launch_bind_top(Ccur, 0, 1, half, r_j, c->st);
@@ -801,9 +808,13 @@ static GPAProof prove_gpa(Ctx* c, std::vector<Circuit*>& circuits, std::vector<f
       lp.proof.push_back(unipoly_compress(coeffs));
       cur = half;
     }
-    // claims_prod = (A_k[0], B_k[0]): pack the 2*ncirc heads on the device, one small transfer
-    pack_heads(c, dAB, nullptr, 0, 2 * ncirc, c->d_small + 1024);
-    c->d2h(fin.data(), c->d_small + 1024, fin.size() * sizeof(fr_t));
+    // claims_prod = (A_k[0], B_k[0]): published by the last round's kernel, or packed on the device + one transfer
+    if (heads_published) {
+      c->fin_wait(fz, fin.data(), 2 * ncirc);
+    } else {
+      pack_heads(c, dAB, nullptr, 0, 2 * ncirc, c->d_small + 1024);
+      c->d2h(fin.data(), c->d_small + 1024, fin.size() * sizeof(fr_t));
+    }
     for (int k = 0; k < ncirc; k++) {
       lp.claims_prod_left.push_back(fin[2 * k]);
       lp.claims_prod_right.push_back(fin[2 * k + 1]);
@@ -1233,21 +1244,43 @@ std::vector<uint8_t> prove(Ctx* c, const Strategy& S, Dense& dense, const std::v
       launch_gp_fingerprints_ops(dense.dim(j), E.p + i * s_loc, dense.read(j), s_loc, gamma, tau, rd[i]->tree.p,
                                  wr[i]->tree.p, c->st);
       g_launches += 2;
-      build_tree(c, *init[i]);
-      build_tree(c, *fin[i]);
-      build_tree(c, *rd[i]);
-      build_tree(c, *wr[i]);
+    }
+    // all trees of a size at once + the top layers straight to the host (single GPU); else tree by tree
+    const bool batched = G == 1 && c->h_mapped && 2 * alpha <= 32;
+    std::vector<fr_t> tops(8 * alpha);
+    if (batched) {
+      TreePtrs tm, to;
+      for (size_t i = 0; i < alpha; i++) {
+        tm.p[2 * i] = init[i]->tree.p;
+        tm.p[2 * i + 1] = fin[i]->tree.p;
+        to.p[2 * i] = rd[i]->tree.p;
+        to.p[2 * i + 1] = wr[i]->tree.p;
+      }
+      Finalize f = c->fin_begin();
+      launch_product_trees(tm, (int)(2 * alpha), M, 0, f, c->st);
+      launch_product_trees(to, (int)(2 * alpha), s, (int)(2 * alpha), f, c->st);
+      g_launches += product_trees_launches(M) + product_trees_launches(s);
+      c->fin_wait(f, tops.data(), (int)(8 * alpha));
+    } else {
+      for (size_t i = 0; i < alpha; i++) {
+        build_tree(c, *init[i]);
+        build_tree(c, *fin[i]);
+        build_tree(c, *rd[i]);
+        build_tree(c, *wr[i]);
+      }
     }
     // ProductLayerProof::prove (memory_checking.rs:673-731)
     transcript.append_protocol_name("Lasso ProductLayerProof");
-    auto evaluate = [&](Circuit& ci) {  // grand_product.rs:60-65 (the top layer is replicated when G > 1)
+    auto evaluate = [&](Circuit& ci, size_t slot) {  // grand_product.rs:60-65 (the top layer is replicated when G > 1)
+      if (batched) return fr_mul(tops[2 * slot], tops[2 * slot + 1]);
       fr_t top[2];
       c->d2h(top, G == 1 ? ci.layer_local(ci.num_layers - 1) : ci.layer_rep(ci.num_layers - 1), 64);
       return fr_mul(top[0], top[1]);
     };
     std::vector<fr_t> claims_rw, claims_if;
     for (size_t i = 0; i < alpha; i++) {
-      fr_t hi = evaluate(*init[i]), hr = evaluate(*rd[i]), hw = evaluate(*wr[i]), hf = evaluate(*fin[i]);
+      fr_t hi = evaluate(*init[i], 2 * i), hr = evaluate(*rd[i], 2 * alpha + 2 * i),
+           hw = evaluate(*wr[i], 2 * alpha + 2 * i + 1), hf = evaluate(*fin[i], 2 * i + 1);
       if (!fr_eq(fr_mul(hi, hw), fr_mul(hr, hf))) throw std::runtime_error("multiset hash check failed (memory_checking.rs:689)");
       transcript.append_scalar("claim_hash_init", hi);
       transcript.append_scalar("claim_hash_read", hr);
