@@ -40,6 +40,10 @@ void launch_build_multiples(const pt_niels* T, size_t table_stride, size_t npts,
 int msm_direct_chunks(int len);
 void launch_msm_direct(const pt_niels* M, size_t npts, const uint32_t* scalars, const uint32_t* cols, int nrows, int len,
                        pt_ext* partials, uint32_t* out_raw, uint32_t* tagged, cudaStream_t st);
+// Hyrax row commitments of integer-valued polynomials as direct sums over the multiples table (no buckets)
+void launch_msm_rows_direct_u32(const pt_niels* M, size_t npts, const uint32_t* scalars, size_t row_stride, int nrows, int ncols,
+                                int nw, pt_ext* partials, fq_t* out_ext, uint32_t* out_comp, uint32_t* out_raw,
+                                cudaStream_t st);
 void launch_combine_points(const fq_t* in_ext, int n, fq_t* out_ext, uint32_t* out_comp, cudaStream_t st);
 
 inline int msm_windows_for_bits(unsigned max_bits) {

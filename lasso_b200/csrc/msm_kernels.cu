@@ -703,6 +703,60 @@ void launch_msm_direct(const pt_niels* M, size_t npts, const uint32_t* scalars, 
   msm_finish_quad_kernel<<<1, 128 * nrows, 0, st>>>(partials, nrows, nchunks, out_raw, tagged);
 }
 
+// ---------------------------------------------------------------- Hyrax row commitments over the multiples table
+// Integer-valued polynomials (indices, counters, table values: u32 scalars, <= 5 windows): one CTA per row, thread
+// t adds the table entries of the columns t, t+128, ... (one mixed addition per non-zero 8-bit digit, no sort, no
+// buckets, no 14-step bucket reduction per CTA), then a shared-memory tree over the 128 threads.  Plain
+// thread-per-point arithmetic: with thousands of rows this kernel is throughput-bound, not latency-bound.
+__global__ void __launch_bounds__(MSM_T)
+    msm_rows_direct_u32_kernel(const pt_niels* M, size_t npts, const uint32_t* scalars, size_t row_stride, int ncols, int nw,
+                               pt_ext* partials) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* buf = reinterpret_cast<uint32_t*>(smem_raw);  // SoA point storage, MSM_T points
+  const int tid = threadIdx.x, row = blockIdx.x;
+  const uint32_t* srow = scalars + (size_t)row * row_stride;
+  pt_ext acc = pt_identity();
+  uint32_t v = tid < ncols ? srow[tid] : 0u;
+  for (int c = tid; c < ncols; c += MSM_T) {
+    const uint32_t cur = v;
+    if (c + MSM_T < ncols) v = srow[c + MSM_T];
+    if (cur == 0) continue;
+    const uint64_t b = (uint64_t)cur + 0x8080808080ull;
+#pragma unroll
+    for (int w = 0; w < 5; w++) {
+      if (w < nw) {
+        const int d = (int)((b >> (8 * w)) & 0xff) - 128;
+        if (d != 0) {
+          const pt_niels* e = M + ((size_t)w * npts + c) * 128 + ((d < 0 ? -d : d) - 1);
+          pt_niels n = ld_niels(e);
+          acc = pt_madd(acc, d < 0 ? niels_neg(n) : n);
+        }
+      }
+    }
+  }
+  sm_store_pt(buf, MSM_T, tid, acc);
+  __syncthreads();
+  for (int d = MSM_T / 2; d >= 1; d >>= 1) {
+    if (tid < d) {
+      acc = pt_add(acc, sm_load_pt(buf, MSM_T, tid + d));
+      sm_store_pt(buf, MSM_T, tid, acc);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) partials[row] = acc;
+}
+// nrows rows of u32 scalars over the generators 0 .. ncols-1 of the multiples table; outputs as launch_msm_rows
+void launch_msm_rows_direct_u32(const pt_niels* M, size_t npts, const uint32_t* scalars, size_t row_stride, int nrows, int ncols,
+                                int nw, pt_ext* partials, fq_t* out_ext, uint32_t* out_comp, uint32_t* out_raw,
+                                cudaStream_t st) {
+  if (nrows <= 0) return;
+  if (nw < 1) nw = 1;
+  if (nw > 5) throw std::runtime_error("msm_rows_direct_u32: more than 5 windows");
+  msm_rows_direct_u32_kernel<<<nrows, MSM_T, 32 * MSM_T * sizeof(uint32_t), st>>>(M, npts, scalars, row_stride, ncols, nw,
+                                                                              partials);
+  msm_finish_kernel<<<nrows, 32, 0, st>>>(partials, nrows, 1, 1, 1, out_ext, out_comp, out_raw, nullptr, 0);
+}
+
 // Launch geometry.  wpc = windows per CTA (all of them over a shifted table), ngroups = window groups,
 // chunk_cols = columns per CTA: at most MSM_CHUNK list entries (columns x windows) per CTA; with only a few
 // rows (Bulletproofs rounds) the columns are split further so that about one CTA per SM exists.

@@ -333,6 +333,17 @@ static std::vector<uint8_t> commit_u32(Ctx* c, const Gens& g, const uint32_t* d_
   int nw = msm_windows_for_bits(max_bits);
   if (nw > 5) throw std::runtime_error("u32 MSM path: scalars wider than 32 bits");
   size_t R_loc = loc(c, R);
+  if (c->world == 1 && g.d_multiples.p && R <= g.n_direct && L > 8) {
+    // single GPU: rows as direct sums over the digit-multiples table (msm_kernels.cu), normalised on the device
+    std::vector<uint8_t> out(L * 32);
+    DBuf<pt_ext> part(c, L);
+    DBuf<uint32_t> comp(c, L * 8);
+    launch_msm_rows_direct_u32(g.d_multiples.p, g.n_direct, d_vals_loc, R, (int)L, (int)R, nw, part.p, nullptr, comp.p, nullptr,
+                               c->st);
+    g_launches += 2;
+    c->d2h(out.data(), comp.p, out.size());
+    return out;
+  }
   return msm_rows(c, g, d_vals_loc, 1, R_loc, (int)L, (int)R_loc, nw, nullptr, 0, 0);
 }
 
