@@ -745,6 +745,28 @@ __global__ void __launch_bounds__(MSM_T)
   }
   if (tid == 0) partials[row] = acc;
 }
+// One THREAD per row: normalise (one Fq inversion = a 265-step dependent chain, ~80 us whatever the row count)
+// and emit.  32 rows per CTA so that the chains of a commitment spread over all SMs.
+__global__ void __launch_bounds__(32)
+    normalize_rows_kernel(const pt_ext* pts, int nrows, fq_t* out_ext, uint32_t* out_comp) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= nrows) return;
+  const pt_ext acc = ld_pt(pts + row);
+  fq_t x, y;
+  pt_to_affine_canonical(acc, x, y);
+  if (out_comp) {
+    uint32_t c[8];
+    pt_compress_canonical(x, y, c);
+#pragma unroll
+    for (int l = 0; l < 8; l++) out_comp[(size_t)row * 8 + l] = c[l];
+  }
+  if (out_ext) {
+    out_ext[(size_t)row * 4 + 0] = fq_to_ark(x);
+    out_ext[(size_t)row * 4 + 1] = fq_to_ark(y);
+    out_ext[(size_t)row * 4 + 2] = fq_to_ark(fq_mul(x, y));
+    out_ext[(size_t)row * 4 + 3] = fq_to_ark(fq_one());
+  }
+}
 // nrows rows of u32 scalars over the generators 0 .. ncols-1 of the multiples table; outputs as launch_msm_rows
 void launch_msm_rows_direct_u32(const pt_niels* M, size_t npts, const uint32_t* scalars, size_t row_stride, int nrows, int ncols,
                                 int nw, pt_ext* partials, fq_t* out_ext, uint32_t* out_comp, uint32_t* out_raw,
@@ -754,7 +776,10 @@ void launch_msm_rows_direct_u32(const pt_niels* M, size_t npts, const uint32_t* 
   if (nw > 5) throw std::runtime_error("msm_rows_direct_u32: more than 5 windows");
   msm_rows_direct_u32_kernel<<<nrows, MSM_T, 32 * MSM_T * sizeof(uint32_t), st>>>(M, npts, scalars, row_stride, ncols, nw,
                                                                               partials);
-  msm_finish_kernel<<<nrows, 32, 0, st>>>(partials, nrows, 1, 1, 1, out_ext, out_comp, out_raw, nullptr, 0);
+  if (out_raw)
+    msm_finish_kernel<<<nrows, 32, 0, st>>>(partials, nrows, 1, 1, 1, out_ext, out_comp, out_raw, nullptr, 0);
+  else
+    normalize_rows_kernel<<<(nrows + 31) / 32, 32, 0, st>>>(partials, nrows, out_ext, out_comp);
 }
 
 // Launch geometry.  wpc = windows per CTA (all of them over a shifted table), ngroups = window groups,
