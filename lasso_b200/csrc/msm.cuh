@@ -41,9 +41,11 @@ int msm_direct_chunks(int len);
 void launch_msm_direct(const pt_niels* M, size_t npts, const uint32_t* scalars, const uint32_t* cols, int nrows, int len,
                        pt_ext* partials, uint32_t* out_raw, uint32_t* tagged, cudaStream_t st);
 // Hyrax row commitments of integer-valued polynomials as direct sums over the multiples table (no buckets)
-void launch_msm_rows_direct_u32(const pt_niels* M, size_t npts, const uint32_t* scalars, size_t row_stride, int nrows, int ncols,
-                                int nw, pt_ext* partials, fq_t* out_ext, uint32_t* out_comp, uint32_t* out_raw,
-                                cudaStream_t st);
+// M16 (may be null): 16-bit multiples M16[j][d-1] = d * G_j, d = 1..32768, of the generators 0 .. ncols-1
+void launch_build_multiples16(const pt_niels* T, const pt_niels* M, size_t npts8, size_t ncols, pt_niels* M16, cudaStream_t st);
+void launch_msm_rows_direct_u32(const pt_niels* M, size_t npts, const pt_niels* M16, const uint32_t* scalars, size_t row_stride,
+                                int nrows, int ncols, int nw, pt_ext* partials, fq_t* out_ext, uint32_t* out_comp,
+                                uint32_t* out_raw, cudaStream_t st);
 void launch_combine_points(const fq_t* in_ext, int n, fq_t* out_ext, uint32_t* out_comp, cudaStream_t st);
 
 inline int msm_windows_for_bits(unsigned max_bits) {

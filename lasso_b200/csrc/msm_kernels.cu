@@ -600,6 +600,44 @@ void launch_build_multiples(const pt_niels* T, size_t table_stride, size_t npts,
   multiples_table_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(T, table_stride, npts, nwindows, M);
 }
 
+// 16-bit multiples of the COMMITMENT generators (the columns of the Hyrax matrices): M16[j][d-1] = d * G_j,
+// d = 1..32768 (3 MB per generator: 12.9 GB for the 4096 columns of the 2^20-lookup configuration).  The
+// committed integers (16-bit indices, counters, table values) then cost ONE table entry each instead of one per
+// 8-bit digit plus a carry.  Thread (j, b) starts from (256 b) G_j = b * 2^8 G_j (an entry of M) and walks 256
+// mixed additions; normalisation is batched 16 at a time (Montgomery's trick: 3 multiplications per point + one
+// inversion per batch).
+__global__ void __launch_bounds__(128)
+    multiples16_table_kernel(const pt_niels* T, const pt_niels* M, size_t npts8, size_t ncols, pt_niels* M16) {
+  const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= ncols * 128) return;
+  const size_t j = id >> 7;
+  const int b = (int)(id & 127);
+  const pt_niels base = ld_niels(T + j);  // window 0: G_j
+  pt_ext acc = b == 0 ? pt_identity() : pt_from_niels(ld_niels(M + ((size_t)1 * npts8 + j) * 128 + (b - 1)));
+  pt_niels* out = M16 + j * 32768 + (size_t)256 * b;
+  for (int g = 0; g < 16; g++) {
+    pt_ext pts[16];
+    fq_t pref[16];
+#pragma unroll 1
+    for (int k = 0; k < 16; k++) {
+      acc = pt_madd(acc, base);
+      pts[k] = acc;
+      pref[k] = k == 0 ? acc.Z : fq_mul(pref[k - 1], acc.Z);
+    }
+    fq_t inv = fq_inv(pref[15]);
+#pragma unroll 1
+    for (int k = 15; k >= 0; k--) {
+      const fq_t zi = k == 0 ? inv : fq_mul(inv, pref[k - 1]);
+      inv = fq_mul(inv, pts[k].Z);
+      st_niels(out + 16 * g + k, niels_from_affine(fq_mul(pts[k].X, zi), fq_mul(pts[k].Y, zi)));
+    }
+  }
+}
+void launch_build_multiples16(const pt_niels* T, const pt_niels* M, size_t npts8, size_t ncols, pt_niels* M16, cudaStream_t st) {
+  const size_t n = ncols * 128;
+  multiples16_table_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(T, M, npts8, ncols, M16);
+}
+
 // mixed quad addition: the quad's accumulator + one affine-niels entry; lane 0 / 1 / 3 hold the entry's
 // (y-x | y+x) / (y+x | y-x) / (+-2dxy) already selected for the sign of the digit
 __device__ __forceinline__ fq_t quad_madd(unsigned mask, int lane, const fq_t& mine, const fq_t& operand) {
@@ -709,8 +747,8 @@ void launch_msm_direct(const pt_niels* M, size_t npts, const uint32_t* scalars, 
 // buckets, no 14-step bucket reduction per CTA), then a shared-memory tree over the 128 threads.  Plain
 // thread-per-point arithmetic: with thousands of rows this kernel is throughput-bound, not latency-bound.
 __global__ void __launch_bounds__(MSM_T)
-    msm_rows_direct_u32_kernel(const pt_niels* M, size_t npts, const uint32_t* scalars, size_t row_stride, int ncols, int nw,
-                               pt_ext* partials) {
+    msm_rows_direct_u32_kernel(const pt_niels* M, size_t npts, const pt_niels* M16, const uint32_t* scalars, size_t row_stride,
+                               int ncols, int nw, pt_ext* partials) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* buf = reinterpret_cast<uint32_t*>(smem_raw);  // SoA point storage, MSM_T points
   const int tid = threadIdx.x, row = blockIdx.x;
@@ -721,6 +759,28 @@ __global__ void __launch_bounds__(MSM_T)
     const uint32_t cur = v;
     if (c + MSM_T < ncols) v = srow[c + MSM_T];
     if (cur == 0) continue;
+    if (M16) {
+      // one signed 16-bit digit from the wide table; what is left (values >= 2^15 only) goes through the 8-bit
+      // multiples of the windows 2.. as usual
+      const int d16 = (int)(((uint64_t)cur + 0x8000u) & 0xffffu) - 0x8000;
+      const uint32_t rest = (uint32_t)(((int64_t)cur - d16) >> 16);
+      if (d16 != 0) {
+        pt_niels n = ld_niels(M16 + (size_t)c * 32768 + ((d16 < 0 ? -d16 : d16) - 1));
+        acc = pt_madd(acc, d16 < 0 ? niels_neg(n) : n);
+      }
+      if (rest != 0) {
+        const uint64_t br = (uint64_t)rest + 0x808080ull;
+#pragma unroll
+        for (int w = 0; w < 3; w++) {
+          const int d = (int)((br >> (8 * w)) & 0xff) - 128;
+          if (d != 0) {
+            pt_niels n = ld_niels(M + ((size_t)(w + 2) * npts + c) * 128 + ((d < 0 ? -d : d) - 1));
+            acc = pt_madd(acc, d < 0 ? niels_neg(n) : n);
+          }
+        }
+      }
+      continue;
+    }
     const uint64_t b = (uint64_t)cur + 0x8080808080ull;
 #pragma unroll
     for (int w = 0; w < 5; w++) {
@@ -768,14 +828,14 @@ __global__ void __launch_bounds__(32)
   }
 }
 // nrows rows of u32 scalars over the generators 0 .. ncols-1 of the multiples table; outputs as launch_msm_rows
-void launch_msm_rows_direct_u32(const pt_niels* M, size_t npts, const uint32_t* scalars, size_t row_stride, int nrows, int ncols,
-                                int nw, pt_ext* partials, fq_t* out_ext, uint32_t* out_comp, uint32_t* out_raw,
-                                cudaStream_t st) {
+void launch_msm_rows_direct_u32(const pt_niels* M, size_t npts, const pt_niels* M16, const uint32_t* scalars, size_t row_stride,
+                                int nrows, int ncols, int nw, pt_ext* partials, fq_t* out_ext, uint32_t* out_comp,
+                                uint32_t* out_raw, cudaStream_t st) {
   if (nrows <= 0) return;
   if (nw < 1) nw = 1;
   if (nw > 5) throw std::runtime_error("msm_rows_direct_u32: more than 5 windows");
-  msm_rows_direct_u32_kernel<<<nrows, MSM_T, 32 * MSM_T * sizeof(uint32_t), st>>>(M, npts, scalars, row_stride, ncols, nw,
-                                                                              partials);
+  msm_rows_direct_u32_kernel<<<nrows, MSM_T, 32 * MSM_T * sizeof(uint32_t), st>>>(M, npts, M16, scalars, row_stride, ncols,
+                                                                              nw, partials);
   if (out_raw)
     msm_finish_kernel<<<nrows, 32, 0, st>>>(partials, nrows, 1, 1, 1, out_ext, out_comp, out_raw, nullptr, 0);
   else

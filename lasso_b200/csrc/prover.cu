@@ -208,6 +208,15 @@ Gens* gens_create(Ctx* c, const uint64_t* stream_affine, size_t n_points, size_t
       g->d_multiples.alloc(c, (size_t)kMsmFullWindows * nd * 128);
       launch_build_multiples(g->d_table.p, n_points, nd, kMsmFullWindows, g->d_multiples.p, c->st);
       g_launches += 1;
+      const char* cap = getenv("LASSO_B200_TABLE_GB");
+      const double cap_gb = cap ? atof(cap) : 48.0;
+      const size_t ncols16 = nd - 2;
+      if ((double)ncols16 * 32768 * sizeof(pt_niels) <= cap_gb * 1e9) {
+        g->n_direct16 = ncols16;
+        g->d_multiples16.alloc(c, ncols16 * 32768);
+        launch_build_multiples16(g->d_table.p, g->d_multiples.p, nd, ncols16, g->d_multiples16.p, c->st);
+        g_launches += 1;
+      }
     }
   }
   c->sync();
@@ -338,8 +347,8 @@ static std::vector<uint8_t> commit_u32(Ctx* c, const Gens& g, const uint32_t* d_
     std::vector<uint8_t> out(L * 32);
     DBuf<pt_ext> part(c, L);
     DBuf<uint32_t> comp(c, L * 8);
-    launch_msm_rows_direct_u32(g.d_multiples.p, g.n_direct, d_vals_loc, R, (int)L, (int)R, nw, part.p, nullptr, comp.p, nullptr,
-                               c->st);
+    launch_msm_rows_direct_u32(g.d_multiples.p, g.n_direct, R <= g.n_direct16 ? g.d_multiples16.p : nullptr, d_vals_loc, R,
+                               (int)L, (int)R, nw, part.p, nullptr, comp.p, nullptr, c->st);
     g_launches += 2;
     c->d2h(out.data(), comp.p, out.size());
     return out;

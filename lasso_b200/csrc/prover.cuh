@@ -161,6 +161,10 @@ struct Gens {
   // the opening proofs (msm_kernels.cu).  Single-GPU contexts only; empty -> the bucket MSM is used.
   DBuf<pt_niels> d_multiples;
   size_t n_direct = 0;
+  // 16-bit multiples M16[j][d-1] = d * G_j (d = 1..32768) of the first n_direct16 generators: the Hyrax row
+  // commitments of integer-valued polynomials (3 MB per generator; LASSO_B200_TABLE_GB caps it, default 48)
+  DBuf<pt_niels> d_multiples16;
+  size_t n_direct16 = 0;
 };
 
 // DensifiedRepresentation<F, C> (lasso/densified.rs:8-18), device resident
