@@ -43,9 +43,11 @@ void launch_msm_direct(const pt_niels* M, size_t npts, const uint32_t* scalars, 
 // Hyrax row commitments of integer-valued polynomials as direct sums over the multiples table (no buckets)
 // M16 (may be null): 16-bit multiples M16[j][d-1] = d * G_j, d = 1..32768, of the generators 0 .. ncols-1
 void launch_build_multiples16(const pt_niels* T, const pt_niels* M, size_t npts8, size_t ncols, pt_niels* M16, cudaStream_t st);
-void launch_msm_rows_direct_u32(const pt_niels* M, size_t npts, const pt_niels* M16, const uint32_t* scalars, size_t row_stride,
-                                int nrows, int ncols, int nw, pt_ext* partials, fq_t* out_ext, uint32_t* out_comp,
-                                uint32_t* out_raw, cudaStream_t st);
+// K16 (with M16): the centring constant 2^15 * sum_{j < ncols} G_j for exactly this ncols (launch_centre_constant)
+void launch_centre_constant(const pt_niels* M16, int ncols, pt_ext* K16, cudaStream_t st);
+void launch_msm_rows_direct_u32(const pt_niels* M, size_t npts, const pt_niels* M16, const pt_ext* K16, const uint32_t* scalars,
+                                size_t row_stride, int nrows, int ncols, int nw, pt_ext* partials, fq_t* out_ext,
+                                uint32_t* out_comp, uint32_t* out_raw, cudaStream_t st);
 void launch_combine_points(const fq_t* in_ext, int n, fq_t* out_ext, uint32_t* out_comp, cudaStream_t st);
 
 inline int msm_windows_for_bits(unsigned max_bits) {

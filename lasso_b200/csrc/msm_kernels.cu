@@ -747,8 +747,8 @@ void launch_msm_direct(const pt_niels* M, size_t npts, const uint32_t* scalars, 
 // buckets, no 14-step bucket reduction per CTA), then a shared-memory tree over the 128 threads.  Plain
 // thread-per-point arithmetic: with thousands of rows this kernel is throughput-bound, not latency-bound.
 __global__ void __launch_bounds__(MSM_T)
-    msm_rows_direct_u32_kernel(const pt_niels* M, size_t npts, const pt_niels* M16, const uint32_t* scalars, size_t row_stride,
-                               int ncols, int nw, pt_ext* partials) {
+    msm_rows_direct_u32_kernel(const pt_niels* M, size_t npts, const pt_niels* M16, const pt_ext* K16, const uint32_t* scalars,
+                               size_t row_stride, int ncols, int nw, pt_ext* partials) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* buf = reinterpret_cast<uint32_t*>(smem_raw);  // SoA point storage, MSM_T points
   const int tid = threadIdx.x, row = blockIdx.x;
@@ -758,12 +758,13 @@ __global__ void __launch_bounds__(MSM_T)
   for (int c = tid; c < ncols; c += MSM_T) {
     const uint32_t cur = v;
     if (c + MSM_T < ncols) v = srow[c + MSM_T];
-    if (cur == 0) continue;
     if (M16) {
-      // one signed 16-bit digit from the wide table; what is left (values >= 2^15 only) goes through the 8-bit
-      // multiples of the windows 2.. as usual
-      const int d16 = (int)(((uint64_t)cur + 0x8000u) & 0xffffu) - 0x8000;
-      const uint32_t rest = (uint32_t)(((int64_t)cur - d16) >> 16);
+      // centred 16-bit digit: v = (v mod 2^16 - 2^15) + 2^15 + 2^16 (v >> 16).  The 2^15 of every column adds up to
+      // the constant K16 = 2^15 * sum_j G_j (added once per row below), so EVERY committed integer below 2^16 costs
+      // exactly one table entry — no carry term for the upper half of the range, no divergence between lanes;
+      // what is left of larger values goes through the 8-bit multiples of the windows 2.. as usual
+      const int d16 = (int)(cur & 0xffffu) - 0x8000;
+      const uint32_t rest = cur >> 16;
       if (d16 != 0) {
         pt_niels n = ld_niels(M16 + (size_t)c * 32768 + ((d16 < 0 ? -d16 : d16) - 1));
         acc = pt_madd(acc, d16 < 0 ? niels_neg(n) : n);
@@ -781,6 +782,7 @@ __global__ void __launch_bounds__(MSM_T)
       }
       continue;
     }
+    if (cur == 0) continue;
     const uint64_t b = (uint64_t)cur + 0x8080808080ull;
 #pragma unroll
     for (int w = 0; w < 5; w++) {
@@ -803,7 +805,7 @@ __global__ void __launch_bounds__(MSM_T)
     }
     __syncthreads();
   }
-  if (tid == 0) partials[row] = acc;
+  if (tid == 0) partials[row] = M16 ? pt_add(acc, ld_pt(K16)) : acc;
 }
 // One THREAD per row: normalise (one Fq inversion = a 265-step dependent chain, ~80 us whatever the row count)
 // and emit.  32 rows per CTA so that the chains of a commitment spread over all SMs.
@@ -828,14 +830,35 @@ __global__ void __launch_bounds__(32)
   }
 }
 // nrows rows of u32 scalars over the generators 0 .. ncols-1 of the multiples table; outputs as launch_msm_rows
-void launch_msm_rows_direct_u32(const pt_niels* M, size_t npts, const pt_niels* M16, const uint32_t* scalars, size_t row_stride,
-                                int nrows, int ncols, int nw, pt_ext* partials, fq_t* out_ext, uint32_t* out_comp,
-                                uint32_t* out_raw, cudaStream_t st) {
+// K16 = 2^15 * sum_{j < ncols} G_j (extended): thread t adds the 2^15-multiples of its columns, tree as above
+__global__ void __launch_bounds__(MSM_T) centre_constant_kernel(const pt_niels* M16, int ncols, pt_ext* K16) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* buf = reinterpret_cast<uint32_t*>(smem_raw);
+  const int tid = threadIdx.x;
+  pt_ext acc = pt_identity();
+  for (int c = tid; c < ncols; c += MSM_T) acc = pt_madd(acc, ld_niels(M16 + (size_t)c * 32768 + 32767));
+  sm_store_pt(buf, MSM_T, tid, acc);
+  __syncthreads();
+  for (int d = MSM_T / 2; d >= 1; d >>= 1) {
+    if (tid < d) {
+      acc = pt_add(acc, sm_load_pt(buf, MSM_T, tid + d));
+      sm_store_pt(buf, MSM_T, tid, acc);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) *K16 = acc;
+}
+void launch_centre_constant(const pt_niels* M16, int ncols, pt_ext* K16, cudaStream_t st) {
+  centre_constant_kernel<<<1, MSM_T, 32 * MSM_T * sizeof(uint32_t), st>>>(M16, ncols, K16);
+}
+void launch_msm_rows_direct_u32(const pt_niels* M, size_t npts, const pt_niels* M16, const pt_ext* K16, const uint32_t* scalars,
+                                size_t row_stride, int nrows, int ncols, int nw, pt_ext* partials, fq_t* out_ext,
+                                uint32_t* out_comp, uint32_t* out_raw, cudaStream_t st) {
   if (nrows <= 0) return;
   if (nw < 1) nw = 1;
   if (nw > 5) throw std::runtime_error("msm_rows_direct_u32: more than 5 windows");
-  msm_rows_direct_u32_kernel<<<nrows, MSM_T, 32 * MSM_T * sizeof(uint32_t), st>>>(M, npts, M16, scalars, row_stride, ncols,
-                                                                              nw, partials);
+  msm_rows_direct_u32_kernel<<<nrows, MSM_T, 32 * MSM_T * sizeof(uint32_t), st>>>(M, npts, M16, K16, scalars, row_stride,
+                                                                              ncols, nw, partials);
   if (out_raw)
     msm_finish_kernel<<<nrows, 32, 0, st>>>(partials, nrows, 1, 1, 1, out_ext, out_comp, out_raw, nullptr, 0);
   else

@@ -216,6 +216,11 @@ Gens* gens_create(Ctx* c, const uint64_t* stream_affine, size_t n_points, size_t
         g->d_multiples16.alloc(c, ncols16 * 32768);
         launch_build_multiples16(g->d_table.p, g->d_multiples.p, nd, ncols16, g->d_multiples16.p, c->st);
         g_launches += 1;
+        g->d_centre.alloc(c, 32);
+        for (size_t k = 0; ((size_t)1 << k) <= ncols16 && k < 32; k++) {  // one constant per power-of-two row length
+          launch_centre_constant(g->d_multiples16.p, 1 << k, g->d_centre.p + k, c->st);
+          g_launches += 1;
+        }
       }
     }
   }
@@ -347,8 +352,10 @@ static std::vector<uint8_t> commit_u32(Ctx* c, const Gens& g, const uint32_t* d_
     std::vector<uint8_t> out(L * 32);
     DBuf<pt_ext> part(c, L);
     DBuf<uint32_t> comp(c, L * 8);
-    launch_msm_rows_direct_u32(g.d_multiples.p, g.n_direct, R <= g.n_direct16 ? g.d_multiples16.p : nullptr, d_vals_loc, R,
-                               (int)L, (int)R, nw, part.p, nullptr, comp.p, nullptr, c->st);
+    const bool wide = R <= g.n_direct16;
+    launch_msm_rows_direct_u32(g.d_multiples.p, g.n_direct, wide ? g.d_multiples16.p : nullptr,
+                               wide ? g.d_centre.p + (nv - nv / 2) : nullptr, d_vals_loc, R, (int)L, (int)R, nw, part.p, nullptr,
+                               comp.p, nullptr, c->st);
     g_launches += 2;
     c->d2h(out.data(), comp.p, out.size());
     return out;

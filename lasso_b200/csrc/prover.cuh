@@ -165,6 +165,7 @@ struct Gens {
   // commitments of integer-valued polynomials (3 MB per generator; LASSO_B200_TABLE_GB caps it, default 48)
   DBuf<pt_niels> d_multiples16;
   size_t n_direct16 = 0;
+  DBuf<pt_ext> d_centre;  // centring constants 2^15 * sum_{j < R} G_j for R = 2^k, k = 0 .. 31 (entry k; msm_kernels.cu)
 };
 
 // DensifiedRepresentation<F, C> (lasso/densified.rs:8-18), device resident
