@@ -104,7 +104,10 @@ size_t lasso_gens_points_needed(size_t c, size_t s, size_t num_memories, size_t 
  * -> ChaCha20Rng -> G::rand, `count` affine points.  Deterministic; see DESIGN.md on what is unpinned. */
 int lasso_sample_generators(const char* label, size_t count, uint64_t* out_affine);
 /* SparsePolyCommitmentGens from an explicit generator stream (the parity contract passes generators in):
- * stream[0..n) = G, stream[n] = gens_1.G[0], stream[n+1] = h for each of the three PolyCommitmentGens. */
+ * stream[0..n) = G, stream[n] = gens_1.G[0], stream[n+1] = h for each of the three PolyCommitmentGens.
+ * Also expands the stream into the fixed-base window table and — on a single-GPU context — the digit-multiples
+ * tables of the opening / commitment generators (~14 GB of HBM at 2^20 lookups;
+ * LASSO_B200_NO_MULTIPLES=1 disables them, LASSO_B200_TABLE_GB caps the 16-bit one).  Outputs do not depend on it. */
 int lasso_gens_create(lasso_ctx*, const uint64_t* stream_affine, size_t n_points, size_t c, size_t s,
                       size_t num_memories, size_t log_m, lasso_gens** out);
 void lasso_gens_destroy(lasso_gens*);
