@@ -54,7 +54,7 @@ struct Ctx {
   uint32_t mapped_seq = 0;
   // tagged region of the mapped buffer (round messages of Fr elements, see common.cuh Finalize): words
   // [kTaggedWord0, kTaggedWord0 + 8 * kTaggedElems); the flag-based payload [0, 1024) + flag word 1024 stay separate
-  static constexpr size_t kTaggedWord0 = 2048, kTaggedElems = 128, kMappedBytes = (2048 + 8 * 128) * 4;
+  static constexpr size_t kTaggedWord0 = 2048, kTaggedElems = 512, kMappedBytes = (kTaggedWord0 + 8 * kTaggedElems) * 4;
   uint32_t fin_seq = 0;
   cudaEvent_t ev_aux = nullptr;  // marks a device->host copy that overlaps later launches on the same stream
   void d2h_small(void* dst, const void* src, size_t bytes);  // prover.cu
