@@ -21,14 +21,9 @@ size_t msm_partials_count(int nrows, int ncols, int nw);
 // out_comp = nrows x 32 bytes ark-serialize compressed; out_raw = nrows x 128 B un-normalised (X,Y,Z,T)
 // internal limbs for host-side normalisation (host_fq64.hpp) or the cross-GPU gather-then-add.
 // Local column c uses generator index c*col_mul + col_add.
-// mapped != null (nrows <= 8), fixed-base table, no other output: the rows go to mapped pinned host memory as
-// TAGGED canonical coordinates — element 3*row + {0,1,2} = X, Y, Z with bit 255 set, one 32-byte store each; the
-// host waits for the tags and clears them (prover.cu Ctx::wait_points).  `seq` is unused on that path.
-// Otherwise with mapped != null: raw rows at 32 words each + the sequence flag at word 1024 = seq.
 void launch_msm_rows(const pt_niels* table, size_t table_stride, int shifted, const void* scalars, int scalar_limbs,
                      size_t row_stride, int nrows, int ncols, int nw, int col_mul, int col_add, pt_ext* partials,
-                     fq_t* out_ext, uint32_t* out_comp, uint32_t* out_raw, cudaStream_t st, uint32_t* mapped = nullptr,
-                     uint32_t seq = 0);
+                     fq_t* out_ext, uint32_t* out_comp, uint32_t* out_raw, cudaStream_t st);
 // raw[(k*nrows + row)*32 ..): (X,Y,Z,T) of source k; adds the nsrc sources per row (cross-GPU gather-then-add)
 void launch_sum_raw_points(const uint32_t* raw, int nsrc, int nrows, uint32_t* out_raw, uint32_t* out_comp, fq_t* out_ext,
                            cudaStream_t st);
@@ -36,7 +31,8 @@ void launch_sum_raw_points(const uint32_t* raw, int nsrc, int nrows, uint32_t* o
 void launch_build_multiples(const pt_niels* T, size_t table_stride, size_t npts, int nwindows, pt_niels* M, cudaStream_t st);
 // bucket-free MSM of nrows <= 8 short rows over M (msm_kernels.cu): scalars = nrows x len canonical integers,
 // cols = generator index per term (null: term k uses generator k); partials: nrows x msm_direct_chunks(len);
-// tagged: mapped host memory, 3 coordinates per row (see launch_msm_rows)
+// tagged: mapped pinned host memory; the rows arrive as TAGGED canonical coordinates — element 3*row + {0,1,2} =
+// X, Y, Z with bit 255 set, one 32-byte store each; the host waits for the tags and clears them (Ctx::wait_points)
 int msm_direct_chunks(int len);
 void launch_msm_direct(const pt_niels* M, size_t npts, const uint32_t* scalars, const uint32_t* cols, int nrows, int len,
                        pt_ext* partials, uint32_t* out_raw, uint32_t* tagged, cudaStream_t st);

@@ -404,7 +404,7 @@ __device__ __forceinline__ pt_ext ld_pt(const pt_ext* p) {
 // rows: one inversion is a 265-step serial chain) or for the cross-GPU gather-then-add of partial points.
 __global__ void __launch_bounds__(256)
     msm_finish_kernel(const pt_ext* partials, int nrows, int nw, int nchunks, int shifted, fq_t* out_ext,
-                      uint32_t* out_comp, uint32_t* out_raw, uint32_t* mapped, uint32_t seq) {
+                      uint32_t* out_comp, uint32_t* out_raw) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row < nrows) {
@@ -438,16 +438,6 @@ __global__ void __launch_bounds__(256)
           out_raw[(size_t)row * 32 + 24 + l] = acc.T.v[l];
         }
       }
-      if (mapped) {  // straight into mapped pinned host memory: the host is spinning on the flag below
-#pragma unroll
-        for (int l = 0; l < 8; l++) {
-          mapped[row * 32 + l] = acc.X.v[l];
-          mapped[row * 32 + 8 + l] = acc.Y.v[l];
-          mapped[row * 32 + 16 + l] = acc.Z.v[l];
-          mapped[row * 32 + 24 + l] = acc.T.v[l];
-        }
-        __threadfence_system();
-      }
       if (out_comp || out_ext) {
         fq_t x, y;
         pt_to_affine_canonical(acc, x, y);
@@ -465,13 +455,6 @@ __global__ void __launch_bounds__(256)
           out_ext[(size_t)row * 4 + 3] = fq_to_ark(one);
         }
       }
-    }
-  }
-  if (mapped) {  // single-CTA launch (nrows <= 8): publish once every row is written
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence_system();
-      *((volatile uint32_t*)(mapped + 1024)) = seq;
     }
   }
 }
@@ -725,7 +708,7 @@ __global__ void __launch_bounds__(MSMD_T)
     st_fq(out + role, mine);
   }
 }
-// nrows (<= 8) short MSMs over the multiples table; result published like launch_msm_rows(..., mapped)
+// nrows (<= 8) short MSMs over the multiples table; the points go to mapped host memory (msm_finish_quad_kernel)
 int msm_direct_chunks(int len) {
   int c = (len * kMsmFullWindows + 128 * 4 - 1) / (128 * 4);  // ~4 entries per quad
   if (c > 73) c = 73;
@@ -860,7 +843,7 @@ void launch_msm_rows_direct_u32(const pt_niels* M, size_t npts, const pt_niels* 
   msm_rows_direct_u32_kernel<<<nrows, MSM_T, 32 * MSM_T * sizeof(uint32_t), st>>>(M, npts, M16, K16, scalars, row_stride,
                                                                               ncols, nw, partials);
   if (out_raw)
-    msm_finish_kernel<<<nrows, 32, 0, st>>>(partials, nrows, 1, 1, 1, out_ext, out_comp, out_raw, nullptr, 0);
+    msm_finish_kernel<<<nrows, 32, 0, st>>>(partials, nrows, 1, 1, 1, out_ext, out_comp, out_raw);
   else
     normalize_rows_kernel<<<(nrows + 31) / 32, 32, 0, st>>>(partials, nrows, out_ext, out_comp);
 }
@@ -900,11 +883,9 @@ size_t msm_partials_count(int nrows, int ncols, int nw) {  // upper bound over b
 
 void launch_msm_rows(const pt_niels* table, size_t table_stride, int shifted, const void* scalars, int scalar_limbs,
                      size_t row_stride, int nrows, int ncols, int nw, int col_mul, int col_add, pt_ext* partials,
-                     fq_t* out_ext, uint32_t* out_comp, uint32_t* out_raw, cudaStream_t st, uint32_t* mapped,
-                     uint32_t seq) {
+                     fq_t* out_ext, uint32_t* out_comp, uint32_t* out_raw, cudaStream_t st) {
   if (nrows <= 0) return;
   if (nw < 1) nw = 1;
-  if (mapped && nrows > 8) throw std::runtime_error("msm: mapped publication is for <= 8 rows");
   const MsmGeom g = msm_geometry(nrows, ncols, nw, shifted);
   const int nchunks = g.nchunks, chunk_cols = g.chunk_cols;
   static bool attr_set = false;
@@ -927,14 +908,7 @@ void launch_msm_rows(const pt_niels* table, size_t table_stride, int shifted, co
           table, table_stride, shifted, (const uint32_t*)scalars + (size_t)r0 * row_stride * 8, row_stride, ncols,
           chunk_cols, nw, g.wpc, col_mul, col_add, part);
   }
-  if (mapped && shifted && !out_ext && !out_comp)
-    msm_finish_quad_kernel<<<1, 128 * nrows, 0, st>>>(partials, nrows, g.ngroups * nchunks, out_raw, mapped);
-  else if (mapped)
-    msm_finish_kernel<<<1, 32 * nrows, 0, st>>>(partials, nrows, g.ngroups, nchunks, shifted, out_ext, out_comp, out_raw,
-                                                mapped, seq);
-  else
-    msm_finish_kernel<<<nrows, 32, 0, st>>>(partials, nrows, g.ngroups, nchunks, shifted, out_ext, out_comp, out_raw,
-                                            nullptr, 0);
+  msm_finish_kernel<<<nrows, 32, 0, st>>>(partials, nrows, g.ngroups, nchunks, shifted, out_ext, out_comp, out_raw);
 }
 
 // Cross-GPU "bucket-sum reduce": raw[(k * nrows + row) * 32 ..] = partial (X,Y,Z,T) of source k for `row`

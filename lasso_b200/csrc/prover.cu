@@ -209,7 +209,7 @@ Gens* gens_create(Ctx* c, const uint64_t* stream_affine, size_t n_points, size_t
       launch_build_multiples(g->d_table.p, n_points, nd, kMsmFullWindows, g->d_multiples.p, c->st);
       g_launches += 1;
       const char* cap = getenv("LASSO_B200_TABLE_GB");
-      const double cap_gb = cap ? atof(cap) : 48.0;
+      const double cap_gb = cap ? atof(cap) : 64.0;
       const size_t ncols16 = nd - 2;
       if ((double)ncols16 * 32768 * sizeof(pt_niels) <= cap_gb * 1e9) {
         g->n_direct16 = ncols16;
@@ -980,7 +980,7 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
     // next one wherever the transcript allows it.
     //   (Cx, Cy): rows (x_vec, 0, 0) and (0.., y, 0) of one two-row MSM        (dot_product.rs:192-197)
     //   round k : fold with u_{k-1}, weights, L/R scalars, c_L, c_R -> two-row MSM   (bullet.rs:73-134)
-    auto read_two_points = [&](uint32_t, uint8_t* comp64) {
+    auto read_two_points = [&](uint8_t* comp64) {
       uint32_t xyz[48];
       c->wait_points(2, xyz);
       h64::compress_xyz(xyz, comp64);
@@ -997,17 +997,16 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
       launch_msm_direct(g.d_multiples.p, g.n_direct, (const uint32_t*)sLR.p, d_cols, 2, (int)len, part.p, nullptr,
                         c->d_mapped + Ctx::kTaggedWord0, c->st);
       g_launches += 2;
-      return 0u;
     };
     launch_two_row_scalars(av, 0, fr_one(), fr_zero(), fr_zero(), Zr, fr_zero(), n, sLR.p, c->st);
-    uint32_t seq = two_row_msm(nullptr, n + 2);
+    two_row_msm(nullptr, n + 2);
     // a_vec of the transcript = canonical bytes of b; the copy is waited for only when it is appended
     launch_canonicalize(bv, canon.p, n, c->d_flag, c->st);
     LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin, canon.p, n * 32, cudaMemcpyDeviceToHost, c->st));
     LB_CUDA_CHECK(cudaEventRecord(c->ev_aux, c->st));
     g_launches += 2;
     uint8_t CxCy[64];
-    read_two_points(seq, CxCy);
+    read_two_points(CxCy);
     fr_t u = fr_one(), u_inv = fr_one();
     int fold = 0;
     size_t m = n;  // vector length entering the round (after the fold with the previous challenge)
@@ -1020,9 +1019,9 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
         std::swap(bv, bn);
         std::swap(W, Wn);
       }
-      return two_row_msm(cols.p, n / 2 + 2);
+      two_row_msm(cols.p, n / 2 + 2);
     };
-    if (m != 1) seq = launch_round(0);  // round 0 needs no challenge: it runs while the host absorbs Cx, Cy, a
+    if (m != 1) launch_round(0);  // round 0 needs no challenge: it runs while the host absorbs Cx, Cy, a
     transcript.append_point_compressed("Cx", CxCy);
     transcript.append_point_compressed("Cy", CxCy + 32);
     LB_CUDA_CHECK(cudaEventSynchronize(c->ev_aux));
@@ -1030,14 +1029,14 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
     sp1.reset(new SpanTimer(c, "PE.3 bullet rounds"));
     for (size_t round = 0; m != 1; round++) {
       uint8_t LR[64];
-      read_two_points(seq, LR);
+      read_two_points(LR);
       transcript.append_point_compressed("L", LR);
       transcript.append_point_compressed("R", LR + 32);
       u = transcript.challenge_scalar("u");
       u_inv = fr_inv(u);
       fold = 1;
       m /= 2;
-      if (m != 1) seq = launch_round(round + 1);
+      if (m != 1) launch_round(round + 1);
       blind_fin = fr_add(blind_fin, fr_add(fr_mul(fr_mul(v1[round], u), u), fr_mul(fr_mul(v2[round], u_inv), u_inv)));
       out.L_vec.insert(out.L_vec.end(), LR, LR + 32);
       out.R_vec.insert(out.R_vec.end(), LR + 32, LR + 64);

@@ -162,7 +162,7 @@ struct Gens {
   DBuf<pt_niels> d_multiples;
   size_t n_direct = 0;
   // 16-bit multiples M16[j][d-1] = d * G_j (d = 1..32768) of the first n_direct16 generators: the Hyrax row
-  // commitments of integer-valued polynomials (3 MB per generator; LASSO_B200_TABLE_GB caps it, default 48)
+  // commitments of integer-valued polynomials (3 MB per generator; LASSO_B200_TABLE_GB caps it, default 64)
   DBuf<pt_niels> d_multiples16;
   size_t n_direct16 = 0;
   DBuf<pt_ext> d_centre;  // centring constants 2^15 * sum_{j < R} G_j for R = 2^k, k = 0 .. 31 (entry k; msm_kernels.cu)
