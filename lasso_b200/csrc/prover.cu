@@ -203,7 +203,12 @@ Gens* gens_create(Ctx* c, const uint64_t* stream_affine, size_t n_points, size_t
     size_t nv = std::max(g->nv_l, std::max(g->nv_m, g->nv_d));
     size_t nd = ((size_t)1 << (nv - nv / 2)) + 2;
     const char* off = getenv("LASSO_B200_NO_MULTIPLES");
-    if (c->world == 1 && nd <= n_points && !(off && off[0] == '1')) {
+    // The tables are an optimisation: if the device cannot hold them (cap, or an allocation failure on a smaller
+    // or busier GPU) the prover silently keeps the bucket / 8-bit paths — outputs do not depend on it.
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const size_t bytes8 = (size_t)kMsmFullWindows * nd * 128 * sizeof(pt_niels);
+    if (c->world == 1 && nd <= n_points && !(off && off[0] == '1') && bytes8 < free_b / 2) {
       g->n_direct = nd;
       g->d_multiples.alloc(c, (size_t)kMsmFullWindows * nd * 128);
       launch_build_multiples(g->d_table.p, n_points, nd, kMsmFullWindows, g->d_multiples.p, c->st);
@@ -211,7 +216,8 @@ Gens* gens_create(Ctx* c, const uint64_t* stream_affine, size_t n_points, size_t
       const char* cap = getenv("LASSO_B200_TABLE_GB");
       const double cap_gb = cap ? atof(cap) : 64.0;
       const size_t ncols16 = nd - 2;
-      if ((double)ncols16 * 32768 * sizeof(pt_niels) <= cap_gb * 1e9) {
+      const size_t bytes16 = ncols16 * 32768 * sizeof(pt_niels);
+      if ((double)bytes16 <= cap_gb * 1e9 && bytes16 < (free_b - bytes8) / 2) {
         g->n_direct16 = ncols16;
         g->d_multiples16.alloc(c, ncols16 * 32768);
         launch_build_multiples16(g->d_table.p, g->d_multiples.p, nd, ncols16, g->d_multiples16.p, c->st);
