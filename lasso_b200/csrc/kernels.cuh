@@ -58,10 +58,18 @@ int sumcheck_max_blocks();
 void launch_sumcheck_eval_cubic(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Ceq, int ncirc, size_t half,
                                 const Finalize& fin, cudaStream_t st);
 
-// fused: bind A_k, B_k (in place) and eq (Cin -> Cout) with r, then evaluate the next round on the bound
-// values; h = bound length (>= 2).
-void launch_sumcheck_bind_eval_cubic(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Cin, fr_t* Cout, int ncirc, size_t h,
-                                     const fr_t& r, const Finalize& fin, cudaStream_t st);
+// What the prover runs (poly_kernels.cu): the same rounds with the batching coefficients of sumcheck.rs:95-97 folded
+// in — out = 3 elements  sum_k coeff_k (e0, e2, e3)_k.  scale != 0: the arrays A_k are still unscaled in memory (the
+// first evaluation and the first bind of a layer); the first bind stores coeff_k * A_k and later rounds use scale = 0.
+struct CubicCoeffs {
+  fr_t v[32];
+};
+void launch_sumcheck_eval_cubic_comb(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Ceq, int ncirc, size_t half,
+                                     const CubicCoeffs& cf, int scale, const Finalize& fin, cudaStream_t st);
+// fused: bind A_k, B_k (in place) and eq (Cin -> Cout) with r, then evaluate the next round on the bound values;
+// h = bound length (>= 2)
+void launch_sumcheck_bind_eval_cubic_comb(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Cin, fr_t* Cout, int ncirc, size_t h,
+                                          const fr_t& r, const CubicCoeffs& cf, int scale, const Finalize& fin, cudaStream_t st);
 
 // ---- K5: subtables (subtables/*.rs) ----
 // tables_fr: nsub x M Montgomery elements; tables_u32: nsub x M raw values

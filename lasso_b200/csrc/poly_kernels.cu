@@ -297,50 +297,97 @@ __global__ void __launch_bounds__(kThreads)
   // value index = circuit*3 + t
   finalize_block<3>(fin, acc, blockIdx.y * 3, blockIdx.x, gridDim.x, 3 * gridDim.y, gridDim.x * gridDim.y);
 }
-// Fused round: bind every A_k, B_k (in place) and the shared eq polynomial (Cin -> Cout, ping-pong: it is
-// read by all circuits) with the challenge of round j, and evaluate round j+1 on the bound values in the
-// same pass.  Per element pair this reads 4 and writes 2 elements instead of (2 + 2 reads, 1 write) x 2
-// kernels: 40 % less HBM traffic and one launch per round instead of three (sumcheck.rs:49-120).
+// ---- the same rounds with the batching coefficients folded in (what the prover runs) --------------------------
+// prove_cubic_batched only ever uses  sum_k coeff_k * (e0, e2, e3)_k  (sumcheck.rs:95-104), and everything in a
+// round is linear in A_k.  So the FIRST bind of a layer stores coeff_k * A_k, every later round works on the
+// scaled arrays, and a round evaluates  sum_i C_i(t) * sum_k A'_k,i(t) B_k,i(t):  per element pair 7
+// multiplications per circuit (4 binds + 3 products) + 5 shared (2 eq binds + 3 times C(t)) instead of 12 per
+// circuit; the round message is 3 elements instead of 3 per circuit.  The layer's claims A_k(r) are recovered on the
+// host with the inverse coefficients (one batch inversion per layer, off the critical path).
+//   scale != 0: the arrays A_k in memory are still unscaled; multiply by coeff_k on the fly (and store the scaled
+//   value when binding).  Circuits are strided over blockIdx.y so that small rounds still fill the machine.
+__global__ void __launch_bounds__(kThreads)
+    sc_eval_cubic_comb_kernel(fr_t* const* A, fr_t* const* B, const fr_t* Ceq, size_t half, int ncirc, CubicCoeffs cf,
+                              int scale, Finalize fin) {
+  __shared__ fr_t scratch[3 * kThreads / 32];
+  fr_t acc[3] = {fr_zero(), fr_zero(), fr_zero()};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
+    fr_t s0 = fr_zero(), s2 = fr_zero(), s3 = fr_zero();
+    for (int k = blockIdx.y; k < ncirc; k += gridDim.y) {
+      const fr_t* a = A[k];
+      const fr_t* b = B[k];
+      fr_t a0 = ld_fr_stream(a + i), a1 = ld_fr_stream(a + half + i);
+      if (scale) {
+        a0 = fr_mul(cf.v[k], a0);
+        a1 = fr_mul(cf.v[k], a1);
+      }
+      const fr_t b0 = ld_fr_stream(b + i), b1 = ld_fr_stream(b + half + i);
+      const fr_t da = fr_sub(a1, a0), db = fr_sub(b1, b0);
+      const fr_t a2 = fr_add(a1, da), b2 = fr_add(b1, db);
+      s0 = fr_add(s0, fr_mul(a0, b0));
+      s2 = fr_add(s2, fr_mul(a2, b2));
+      s3 = fr_add(s3, fr_mul(fr_add(a2, da), fr_add(b2, db)));
+    }
+    const fr_t c0 = ld_fr(Ceq + i), c1 = ld_fr(Ceq + half + i), dc = fr_sub(c1, c0), c2 = fr_add(c1, dc);
+    acc[0] = fr_add(acc[0], fr_mul(s0, c0));
+    acc[1] = fr_add(acc[1], fr_mul(s2, c2));
+    acc[2] = fr_add(acc[2], fr_mul(s3, fr_add(c2, dc)));
+  }
+  block_sum_fr<3>(acc, scratch);
+  const int total = gridDim.x * gridDim.y;
+  finalize_block<3>(fin, acc, 0, blockIdx.y * gridDim.x + blockIdx.x, total, 3, total);
+}
 // h = number of bound outputs per polynomial (current length / 2), must be >= 2.
 __global__ void __launch_bounds__(kThreads)
-    sc_bind_eval_cubic_kernel(fr_t* const* A, fr_t* const* B, const fr_t* Cin, fr_t* Cout, size_t h, fr_t r,
-                              Finalize fin) {
+    sc_bind_eval_cubic_comb_kernel(fr_t* const* A, fr_t* const* B, const fr_t* Cin, fr_t* Cout, size_t h, fr_t r, int ncirc,
+                                   CubicCoeffs cf, int scale, Finalize fin) {
   __shared__ fr_t scratch[3 * kThreads / 32];
-  fr_t* a = A[blockIdx.y];
-  fr_t* b = B[blockIdx.y];
   const size_t q = h / 2;
   fr_t acc[3] = {fr_zero(), fr_zero(), fr_zero()};
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < q; i += (size_t)gridDim.x * blockDim.x) {
+    fr_t s0 = fr_zero(), s2 = fr_zero(), s3 = fr_zero();
     fr_t lo, hi;
-    lo = ld_fr_stream(a + i); hi = ld_fr_stream(a + i + h);
-    fr_t a0 = fr_add(lo, fr_mul(r, fr_sub(hi, lo)));
-    lo = ld_fr_stream(a + i + q); hi = ld_fr_stream(a + i + q + h);
-    fr_t a1 = fr_add(lo, fr_mul(r, fr_sub(hi, lo)));
-    st_fr(a + i, a0);
-    st_fr(a + i + q, a1);
-    lo = ld_fr_stream(b + i); hi = ld_fr_stream(b + i + h);
-    fr_t b0 = fr_add(lo, fr_mul(r, fr_sub(hi, lo)));
-    lo = ld_fr_stream(b + i + q); hi = ld_fr_stream(b + i + q + h);
-    fr_t b1 = fr_add(lo, fr_mul(r, fr_sub(hi, lo)));
-    st_fr(b + i, b0);
-    st_fr(b + i + q, b1);
+    for (int k = blockIdx.y; k < ncirc; k += gridDim.y) {
+      fr_t* a = A[k];
+      fr_t* b = B[k];
+      lo = ld_fr_stream(a + i); hi = ld_fr_stream(a + i + h);
+      fr_t a0 = fr_add(lo, fr_mul(r, fr_sub(hi, lo)));
+      lo = ld_fr_stream(a + i + q); hi = ld_fr_stream(a + i + q + h);
+      fr_t a1 = fr_add(lo, fr_mul(r, fr_sub(hi, lo)));
+      if (scale) {
+        a0 = fr_mul(cf.v[k], a0);
+        a1 = fr_mul(cf.v[k], a1);
+      }
+      st_fr(a + i, a0);
+      st_fr(a + i + q, a1);
+      lo = ld_fr_stream(b + i); hi = ld_fr_stream(b + i + h);
+      const fr_t b0 = fr_add(lo, fr_mul(r, fr_sub(hi, lo)));
+      lo = ld_fr_stream(b + i + q); hi = ld_fr_stream(b + i + q + h);
+      const fr_t b1 = fr_add(lo, fr_mul(r, fr_sub(hi, lo)));
+      st_fr(b + i, b0);
+      st_fr(b + i + q, b1);
+      const fr_t da = fr_sub(a1, a0), db = fr_sub(b1, b0);
+      const fr_t a2 = fr_add(a1, da), b2 = fr_add(b1, db);
+      s0 = fr_add(s0, fr_mul(a0, b0));
+      s2 = fr_add(s2, fr_mul(a2, b2));
+      s3 = fr_add(s3, fr_mul(fr_add(a2, da), fr_add(b2, db)));
+    }
     lo = ld_fr(Cin + i); hi = ld_fr(Cin + i + h);
-    fr_t c0 = fr_add(lo, fr_mul(r, fr_sub(hi, lo)));
+    const fr_t c0 = fr_add(lo, fr_mul(r, fr_sub(hi, lo)));
     lo = ld_fr(Cin + i + q); hi = ld_fr(Cin + i + q + h);
-    fr_t c1 = fr_add(lo, fr_mul(r, fr_sub(hi, lo)));
+    const fr_t c1 = fr_add(lo, fr_mul(r, fr_sub(hi, lo)));
     if (blockIdx.y == 0) {
       st_fr(Cout + i, c0);
       st_fr(Cout + i + q, c1);
     }
-    acc[0] = fr_add(acc[0], fr_mul(fr_mul(a0, b0), c0));
-    fr_t da = fr_sub(a1, a0), db = fr_sub(b1, b0), dc = fr_sub(c1, c0);
-    fr_t a2 = fr_add(a1, da), b2 = fr_add(b1, db), c2 = fr_add(c1, dc);
-    acc[1] = fr_add(acc[1], fr_mul(fr_mul(a2, b2), c2));
-    fr_t a3 = fr_add(a2, da), b3 = fr_add(b2, db), c3 = fr_add(c2, dc);
-    acc[2] = fr_add(acc[2], fr_mul(fr_mul(a3, b3), c3));
+    const fr_t dc = fr_sub(c1, c0), c2 = fr_add(c1, dc);
+    acc[0] = fr_add(acc[0], fr_mul(s0, c0));
+    acc[1] = fr_add(acc[1], fr_mul(s2, c2));
+    acc[2] = fr_add(acc[2], fr_mul(s3, fr_add(c2, dc)));
   }
   block_sum_fr<3>(acc, scratch);
-  finalize_block<3>(fin, acc, blockIdx.y * 3, blockIdx.x, gridDim.x, 3 * gridDim.y, gridDim.x * gridDim.y);
+  const int total = gridDim.x * gridDim.y;
+  finalize_block<3>(fin, acc, 0, blockIdx.y * gridDim.x + blockIdx.x, total, 3, total);
 }
 // Latency-oriented variant of the two kernels above for the small and medium rounds (most of the ~300 rounds of
 // a grand-product argument move a few KB: what the host waits for is the dependent chain inside one thread,
@@ -354,7 +401,9 @@ __global__ void __launch_bounds__(kThreads)
 //   do_bind = 0: arrays hold 2q elements, evaluated as (i, i+q)               (q a power of two)
 __global__ void __launch_bounds__(1024)
     sc_cubic_quad_kernel(fr_t* const* A, fr_t* const* B, const fr_t* Cin, fr_t* Cout, size_t q, int lg_q, int do_bind,
-                         fr_t r, int ncirc, Finalize fin) {
+                         fr_t r, int ncirc, CubicCoeffs cf, int scale, int comb, Finalize fin) {
+  // cf / scale / comb: see the combined kernels above — scale: lane 0 multiplies its side by coeff_k (stored when
+  // binding); comb: the CTA yields 3 values (summed over all its circuits) instead of 3 per circuit
   __shared__ fr_t s_part[256 * 3];
   __shared__ int s_last;
   const int tid = threadIdx.x, role = tid & 3, lane = tid & 31;
@@ -372,14 +421,20 @@ __global__ void __launch_bounds__(1024)
       lo = ld_fr(src + i + q);
       hi = ld_fr(src + i + q + h);
       x1 = fr_add(lo, fr_mul(r, fr_sub(hi, lo)));
+    } else {
+      x0 = ld_fr(src + i);
+      x1 = ld_fr(src + i + q);
+    }
+    if (scale && role == 0) {
+      x0 = fr_mul(cf.v[k], x0);
+      x1 = fr_mul(cf.v[k], x1);
+    }
+    if (do_bind) {
       fr_t* dst = role == 2 ? (k == 0 ? Cout : nullptr) : src;
       if (dst) {
         st_fr(dst + i, x0);
         st_fr(dst + i + q, x1);
       }
-    } else {
-      x0 = ld_fr(src + i);
-      x1 = ld_fr(src + i + q);
     }
   }
   // this side at t = 0, 2, 3
@@ -399,7 +454,8 @@ __global__ void __launch_bounds__(1024)
   }
   if (!valid || role == 3) P = fr_zero();
   // sum over the pair indices of a circuit: gq = min(q, 8) consecutive units of a warp belong to one circuit
-  const int gq = q < 8 ? (int)q : 8;
+  // (combined: all 8 units of the warp, whatever their circuit)
+  const int gq = comb ? 8 : (q < 8 ? (int)q : 8);
   for (int off = 1; off < gq; off <<= 1) {
     fr_t o;
 #pragma unroll
@@ -409,13 +465,19 @@ __global__ void __launch_bounds__(1024)
   const int unit = tid >> 2;
   if ((unit & (gq - 1)) == 0 && role < 3) s_part[(unit / gq) * 3 + role] = P;
   __syncthreads();
-  // block outputs: cpb circuits x 3 values, each the sum of gpc group partials
+  // block outputs: cpb circuits x 3 values, each the sum of gpc group partials (combined: 3 values, all warps)
   const int cpb = q >= (size_t)upb ? 1 : upb >> lg_q;
   const int gpc = (int)((q >= (size_t)upb ? (size_t)upb : q) / gq);
-  const int bpv = q >= (size_t)upb ? (int)(q / upb) : 1;  // CTAs per circuit
+  const int bpv = comb ? (int)gridDim.x : (q >= (size_t)upb ? (int)(q / upb) : 1);  // CTAs per value
   int v = -1;
   fr_t val = fr_zero();
-  if (tid < cpb * 3) {
+  if (comb) {
+    if (tid < 3) {
+      const int nw = blockDim.x >> 5;
+      for (int w = 0; w < nw; w++) val = fr_add(val, s_part[w * 3 + tid]);
+      v = tid;
+    }
+  } else if (tid < cpb * 3) {
     const int cl = tid / 3, t = tid - 3 * cl;
     const int kk = q >= (size_t)upb ? (int)(blockIdx.x / bpv) : (int)blockIdx.x * cpb + cl;
     if (kk < ncirc) {
@@ -435,36 +497,50 @@ __global__ void __launch_bounds__(1024)
   if (tid == 0) s_last = (atomicAdd(fin.counter, 1u) == gridDim.x - 1);
   __syncthreads();
   if (!s_last) return;
-  finalize_last_stage(fin, bpv, 3 * ncirc);
+  finalize_last_stage(fin, bpv, comb ? 3 : 3 * ncirc);
 }
 static constexpr size_t kQuadMaxQ = 2048;  // beyond this the rounds are throughput-bound: thread-per-pair kernels
 static void launch_cubic_quad(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Cin, fr_t* Cout, int ncirc, size_t q,
-                              int do_bind, const fr_t& r, const Finalize& fin, cudaStream_t st) {
+                              int do_bind, const fr_t& r, const CubicCoeffs& cf, int scale, int comb, const Finalize& fin,
+                              cudaStream_t st) {
   int lg_q = 0;
   while (((size_t)1 << lg_q) < q) lg_q++;
   const size_t threads = 4 * (size_t)ncirc * q;
   if (threads <= 1024) {
     unsigned t = (unsigned)((threads + 31) / 32 * 32);
-    sc_cubic_quad_kernel<<<1, t, 0, st>>>(d_A, d_B, Cin, Cout, q, lg_q, do_bind, r, ncirc, fin);
+    sc_cubic_quad_kernel<<<1, t, 0, st>>>(d_A, d_B, Cin, Cout, q, lg_q, do_bind, r, ncirc, cf, scale, comb, fin);
   } else {
     unsigned blocks = (unsigned)(((size_t)ncirc * q + 63) / 64);
-    sc_cubic_quad_kernel<<<blocks, 256, 0, st>>>(d_A, d_B, Cin, Cout, q, lg_q, do_bind, r, ncirc, fin);
+    sc_cubic_quad_kernel<<<blocks, 256, 0, st>>>(d_A, d_B, Cin, Cout, q, lg_q, do_bind, r, ncirc, cf, scale, comb, fin);
   }
 }
-void launch_sumcheck_bind_eval_cubic(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Cin, fr_t* Cout, int ncirc, size_t h,
-                                     const fr_t& r, const Finalize& fin, cudaStream_t st) {
-  size_t q = h / 2;
-  if (q <= kQuadMaxQ && (q & (q - 1)) == 0) return launch_cubic_quad(d_A, d_B, Cin, Cout, ncirc, q, 1, r, fin, st);
-  int per = kMaxBlocks / ncirc;
-  if (per < 1) per = 1;
-  int bx = grid_for(q, kThreads, per);
-  dim3 grid(bx, ncirc);
-  sc_bind_eval_cubic_kernel<<<grid, kThreads, 0, st>>>(d_A, d_B, Cin, Cout, h, r, fin);
+// circuits are strided over blockIdx.y: enough CTAs for ~2 per SM even when a round has few pairs
+static dim3 comb_grid(size_t pairs, int ncirc) {
+  int bx = grid_for(pairs, kThreads, kMaxBlocks);
+  int gy = (2 * kNumSMs + bx - 1) / bx;
+  if (gy > ncirc) gy = ncirc;
+  if (gy < 1) gy = 1;
+  return dim3(bx, gy);
 }
+void launch_sumcheck_bind_eval_cubic_comb(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Cin, fr_t* Cout, int ncirc, size_t h,
+                                          const fr_t& r, const CubicCoeffs& cf, int scale, const Finalize& fin, cudaStream_t st) {
+  size_t q = h / 2;
+  if (q <= kQuadMaxQ && (q & (q - 1)) == 0) return launch_cubic_quad(d_A, d_B, Cin, Cout, ncirc, q, 1, r, cf, scale, 1, fin, st);
+  sc_bind_eval_cubic_comb_kernel<<<comb_grid(q, ncirc), kThreads, 0, st>>>(d_A, d_B, Cin, Cout, h, r, ncirc, cf, scale, fin);
+}
+void launch_sumcheck_eval_cubic_comb(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Ceq, int ncirc, size_t half,
+                                     const CubicCoeffs& cf, int scale, const Finalize& fin, cudaStream_t st) {
+  if (half <= kQuadMaxQ && (half & (half - 1)) == 0)
+    return launch_cubic_quad(d_A, d_B, Ceq, nullptr, ncirc, half, 0, fr_zero(), cf, scale, 1, fin, st);
+  sc_eval_cubic_comb_kernel<<<comb_grid(half, ncirc), kThreads, 0, st>>>(d_A, d_B, Ceq, half, ncirc, cf, scale, fin);
+}
+// per-circuit outputs (e0, e2, e3)_k, no batching coefficients: the per-loop C-ABI entry lasso_sumcheck_round_cubic
 void launch_sumcheck_eval_cubic(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Ceq, int ncirc, size_t half,
                                 const Finalize& fin, cudaStream_t st) {
-  if (half <= kQuadMaxQ && (half & (half - 1)) == 0)
-    return launch_cubic_quad(d_A, d_B, Ceq, nullptr, ncirc, half, 0, fr_zero(), fin, st);
+  if (half <= kQuadMaxQ && (half & (half - 1)) == 0) {
+    CubicCoeffs none;
+    return launch_cubic_quad(d_A, d_B, Ceq, nullptr, ncirc, half, 0, fr_zero(), none, 0, 0, fin, st);
+  }
   int per = kMaxBlocks / ncirc;
   if (per < 1) per = 1;
   int bx = grid_for(half, kThreads, per);

@@ -721,7 +721,8 @@ static GPAProof prove_gpa(Ctx* c, std::vector<Circuit*>& circuits, std::vector<f
   DBuf<fr_t> eqbuf(c, eq_cap), eqbuf2(c, std::max<size_t>(eq_cap / 2, 1));
   DBuf<fr_t> tail(c, (size_t)(2 * ncirc + 1) * G);  // replicated remainders of A_k, B_k, C (G elements each)
   std::vector<fr_t> rand;
-  std::vector<fr_t> ev((size_t)ncirc * 3), fin((size_t)2 * ncirc);
+  if (ncirc > 32) throw std::runtime_error("more than 32 circuits in one batched grand product");
+  std::vector<fr_t> ev(3), fin((size_t)2 * ncirc);
   // per slot: [A_0..A_{n-1} | B_0..B_{n-1} | A_0,B_0,A_1,B_1,...]
   std::vector<fr_t*> table(nslots * 4 * ncirc);
   auto slot_A = [&](size_t slot) { return d_ptrs.p + slot * 4 * ncirc; };
@@ -767,6 +768,12 @@ static GPAProof prove_gpa(Ctx* c, std::vector<Circuit*>& circuits, std::vector<f
     std::vector<fr_t> coeff_vec = transcript.challenge_vector("rand_coeffs_next_layer", ncirc);
     fr_t e = fr_zero();
     for (int k = 0; k < ncirc; k++) e = fr_add(e, fr_mul(claims_to_verify[k], coeff_vec[k]));
+    // The kernels fold the batching coefficients in (poly_kernels.cu): the first bind of the layer stores
+    // coeff_k * A_k, a round message is the 3 combined values of sumcheck.rs:95-97.
+    CubicCoeffs cf;
+    for (int k = 0; k < ncirc; k++) cf.v[k] = coeff_vec[k];
+    bool stored_scaled = false;
+    std::vector<fr_t> inv_coeff;  // computed while the first kernel of the layer runs
     LayerProof lp;
     std::vector<fr_t> rand_prod;
     fr_t* Ccur = eqbuf.p;
@@ -789,22 +796,32 @@ static GPAProof prove_gpa(Ctx* c, std::vector<Circuit*>& circuits, std::vector<f
       if (cur <= 1) break;
       if (!have_evals) {  // first round of a phase; later rounds come out of the fused bind+eval kernel
         fz = c->fin_begin();
-        launch_sumcheck_eval_cubic(dA, dB, Ccur, ncirc, cur / 2, fz, c->st);
+        launch_sumcheck_eval_cubic_comb(dA, dB, Ccur, ncirc, cur / 2, cf, stored_scaled ? 0 : 1, fz, c->st);
         g_launches += 1;
+      }
+      if (inv_coeff.empty()) {  // 1 / coeff_k by Montgomery's trick, overlapping the kernel just launched
+        inv_coeff.resize(ncirc);
+        std::vector<fr_t> pre(ncirc);
+        fr_t acc = fr_one();
+        for (int k = 0; k < ncirc; k++) {
+          pre[k] = acc;
+          acc = fr_mul(acc, coeff_vec[k]);
+        }
+        if (fr_eq(acc, fr_zero())) throw std::runtime_error("zero batching coefficient");
+        fr_t ainv = fr_inv(acc);
+        for (int k = ncirc; k-- > 0;) {
+          inv_coeff[k] = fr_mul(ainv, pre[k]);
+          ainv = fr_mul(ainv, coeff_vec[k]);
+        }
       }
       size_t half = cur / 2;
       auto tp0 = std::chrono::steady_clock::now();
       if (sharded || fz.mapped)
-        c->fin_wait(fz, ev.data(), 3 * ncirc);
+        c->fin_wait(fz, ev.data(), 3);
       else
         c->d2h(ev.data(), c->d_small, ev.size() * sizeof(fr_t));
       auto tp1 = std::chrono::steady_clock::now();
-      fr_t c0 = fr_zero(), c2 = fr_zero(), c3 = fr_zero();
-      for (int k = 0; k < ncirc; k++) {  // sumcheck.rs:95-97
-        c0 = fr_add(c0, fr_mul(ev[3 * k], coeff_vec[k]));
-        c2 = fr_add(c2, fr_mul(ev[3 * k + 1], coeff_vec[k]));
-        c3 = fr_add(c3, fr_mul(ev[3 * k + 2], coeff_vec[k]));
-      }
+      const fr_t c0 = ev[0], c2 = ev[1], c3 = ev[2];  // already combined over the circuits (sumcheck.rs:95-97)
       std::vector<fr_t> evals = {c0, fr_sub(e, c0), c2, c3};  // eval(1) = e - eval(0), sumcheck.rs:99-104
       std::vector<fr_t> coeffs = unipoly_from_evals(evals);
       unipoly_append(coeffs, transcript);
@@ -814,7 +831,8 @@ static GPAProof prove_gpa(Ctx* c, std::vector<Circuit*>& circuits, std::vector<f
       if (half > 1) {
         // bind with r_j and evaluate the next round in one pass (sumcheck.rs:116-120 + 63-89)
         fz = c->fin_begin();
-        launch_sumcheck_bind_eval_cubic(dA, dB, Ccur, Cnext, ncirc, half, r_j, fz, c->st);
+        launch_sumcheck_bind_eval_cubic_comb(dA, dB, Ccur, Cnext, ncirc, half, r_j, cf, stored_scaled ? 0 : 1, fz, c->st);
+        stored_scaled = true;
         g_launches += 1;
         std::swap(Ccur, Cnext);
         have_evals = true;
@@ -848,8 +866,8 @@ static GPAProof prove_gpa(Ctx* c, std::vector<Circuit*>& circuits, std::vector<f
       pack_heads(c, dAB, nullptr, 0, 2 * ncirc, c->d_small + 1024);
       c->d2h(fin.data(), c->d_small + 1024, fin.size() * sizeof(fr_t));
     }
-    for (int k = 0; k < ncirc; k++) {
-      lp.claims_prod_left.push_back(fin[2 * k]);
+    for (int k = 0; k < ncirc; k++) {  // the left arrays carry coeff_k once a bind has stored them
+      lp.claims_prod_left.push_back(stored_scaled ? fr_mul(fin[2 * k], inv_coeff[k]) : fin[2 * k]);
       lp.claims_prod_right.push_back(fin[2 * k + 1]);
     }
     for (int k = 0; k < ncirc; k++) {

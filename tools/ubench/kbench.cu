@@ -37,7 +37,7 @@ int main(int argc, char** argv) {
   cudaStream_t st;
   cudaStreamCreate(&st);
   const int ncirc = 8;
-  const size_t maxlen = (size_t)1 << 16;
+  const size_t maxlen = (size_t)1 << 19;
   std::vector<fr_t*> hA(ncirc), hB(ncirc);
   for (int k = 0; k < ncirc; k++) {
     cudaMalloc(&hA[k], maxlen * 32);
@@ -58,6 +58,8 @@ int main(int argc, char** argv) {
   unsigned* counter;
   cudaMalloc(&counter, 64);
   cudaMemset(counter, 0, 64);
+  uint32_t* small32;
+  cudaMalloc(&small32, 4096);
   uint32_t *h_mapped, *d_mapped;
   cudaHostAlloc((void**)&h_mapped, 4096 + 64, cudaHostAllocMapped);
   cudaHostGetDevicePointer((void**)&d_mapped, h_mapped, 0);
@@ -69,21 +71,23 @@ int main(int argc, char** argv) {
   fz.out_dev = small;
   fz.mapped = d_mapped;
   fz.tag = 1;
+  CubicCoeffs cf;
+  for (int k = 0; k < 32; k++) cf.v[k] = r;
   printf("%-52s %8.2f us\n", "empty kernel, back-to-back", time_us([&] { empty_kernel<<<1, 32, 0, st>>>(); }, 2000, st));
-  for (size_t h : {2, 8, 32, 128, 512, 2048, 8192, 32768}) {
+  for (size_t h : {2, 8, 32, 128, 512, 2048, 8192, 32768, 262144}) {
     char nm[96];
     snprintf(nm, sizeof nm, "sc_bind_eval_cubic ncirc=8 h=%zu (mapped)", h);
     fz.mapped = d_mapped;
-    double a = time_us([&] { launch_sumcheck_bind_eval_cubic(dA, dB, C0, C1, ncirc, h, r, fz, st); }, 500, st);
+    double a = time_us([&] { launch_sumcheck_bind_eval_cubic_comb(dA, dB, C0, C1, ncirc, h, r, cf, 0, fz, st); }, 500, st);
     fz.mapped = nullptr;
-    double b = time_us([&] { launch_sumcheck_bind_eval_cubic(dA, dB, C0, C1, ncirc, h, r, fz, st); }, 500, st);
+    double b = time_us([&] { launch_sumcheck_bind_eval_cubic_comb(dA, dB, C0, C1, ncirc, h, r, cf, 0, fz, st); }, 500, st);
     printf("%-52s %8.2f us   (no mapped publish: %.2f us)\n", nm, a, b);
   }
   for (size_t half : {1, 16, 256, 4096}) {
     char nm[96];
     snprintf(nm, sizeof nm, "sc_eval_cubic ncirc=8 half=%zu (mapped)", half);
     fz.mapped = d_mapped;
-    printf("%-52s %8.2f us\n", nm, time_us([&] { launch_sumcheck_eval_cubic(dA, dB, C0, ncirc, half, fz, st); }, 500, st));
+    printf("%-52s %8.2f us\n", nm, time_us([&] { launch_sumcheck_eval_cubic_comb(dA, dB, C0, ncirc, half, cf, 1, fz, st); }, 500, st));
   }
   // Bulletproofs round pieces at n = 2048 (the 2^20-lookup openings)
   for (size_t n : {1024, 2048, 4096}) {
@@ -105,8 +109,8 @@ int main(int argc, char** argv) {
     snprintf(nm, sizeof nm, "msm 2 rows x %zu cols x 32 windows (bucket+finish)", n + 2);
     printf("%-52s %8.2f us\n", nm,
            time_us([&] {
-             launch_msm_rows(table, n + 2, 1, sLR, 8, n + 2, 2, (int)(n + 2), kMsmFullWindows, 1, 0, part, nullptr, nullptr, nullptr,
-                             st, d_mapped, 7);
+             launch_msm_rows(table, n + 2, 1, sLR, 8, n + 2, 2, (int)(n + 2), kMsmFullWindows, 1, 0, part, nullptr, nullptr, small32,
+                             st);
            }, 300, st));
     {  // bucket-free MSM over the multiples table
       pt_niels* M;
