@@ -30,12 +30,13 @@ void launch_sum_raw_points(const uint32_t* raw, int nsrc, int nrows, uint32_t* o
 // multiples table M[w][j][d-1] = d * 2^(8w) * G_j (d = 1..128) of the first npts generators, from the window table T
 void launch_build_multiples(const pt_niels* T, size_t table_stride, size_t npts, int nwindows, pt_niels* M, cudaStream_t st);
 // bucket-free MSM of nrows <= 8 short rows over M (msm_kernels.cu): scalars = nrows x len canonical integers,
-// cols = generator index per term (null: term k uses generator k); partials: nrows x msm_direct_chunks(len);
+// cols = generator index per term (null: term k uses generator k); heavy_rows = how many of the rows carry
+// non-zero scalars (the CTAs per row are sized for those); partials: nrows x msm_direct_chunks(len, heavy_rows);
 // tagged: mapped pinned host memory; the rows arrive as TAGGED canonical coordinates — element 3*row + {0,1,2} =
 // X, Y, Z with bit 255 set, one 32-byte store each; the host waits for the tags and clears them (Ctx::wait_points)
-int msm_direct_chunks(int len);
+int msm_direct_chunks(int len, int heavy_rows);
 void launch_msm_direct(const pt_niels* M, size_t npts, const uint32_t* scalars, const uint32_t* cols, int nrows, int len,
-                       pt_ext* partials, uint32_t* out_raw, uint32_t* tagged, cudaStream_t st);
+                       int heavy_rows, pt_ext* partials, uint32_t* out_raw, uint32_t* tagged, cudaStream_t st);
 // Hyrax row commitments of integer-valued polynomials as direct sums over the multiples table (no buckets)
 // M16 (may be null): 16-bit multiples M16[j][d-1] = d * G_j, d = 1..32768, of the generators 0 .. ncols-1
 void launch_build_multiples16(const pt_niels* T, const pt_niels* M, size_t npts8, size_t ncols, pt_niels* M16, cudaStream_t st);

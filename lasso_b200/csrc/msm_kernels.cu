@@ -709,16 +709,18 @@ __global__ void __launch_bounds__(MSMD_T)
   }
 }
 // nrows (<= 8) short MSMs over the multiples table; the points go to mapped host memory (msm_finish_quad_kernel)
-int msm_direct_chunks(int len) {
+int msm_direct_chunks(int len, int heavy_rows) {
   int c = (len * kMsmFullWindows + 128 * 4 - 1) / (128 * 4);  // ~4 entries per quad
-  if (c > 73) c = 73;
+  if (heavy_rows < 1) heavy_rows = 1;
+  const int cap = (kNumSMs / heavy_rows - 1) | 1;  // about one CTA per SM over the rows that carry the work; odd
+  if (c > cap) c = cap;
   if (c < 1) c = 1;
   return c | 1;
 }
 void launch_msm_direct(const pt_niels* M, size_t npts, const uint32_t* scalars, const uint32_t* cols, int nrows, int len,
-                       pt_ext* partials, uint32_t* out_raw, uint32_t* tagged, cudaStream_t st) {
+                       int heavy_rows, pt_ext* partials, uint32_t* out_raw, uint32_t* tagged, cudaStream_t st) {
   if (nrows < 1 || nrows > 8) throw std::runtime_error("msm_direct: 1..8 rows");
-  const int nchunks = msm_direct_chunks(len);
+  const int nchunks = msm_direct_chunks(len, heavy_rows);
   dim3 grid(nchunks, nrows);
   msm_direct_kernel<<<grid, MSMD_T, 0, st>>>(M, npts, scalars, cols, len, partials);
   msm_finish_quad_kernel<<<1, 128 * nrows, 0, st>>>(partials, nrows, nchunks, out_raw, tagged);

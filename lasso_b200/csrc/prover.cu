@@ -1013,17 +1013,18 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
     a_alt.alloc(c, n);
     b_alt.alloc(c, n);
     fr_t *an = a_alt.p, *bn = b_alt.p;
-    DBuf<pt_ext> part(c, 2 * (size_t)msm_direct_chunks((int)(n + 2)));
+    DBuf<pt_ext> part(c, 2 * (size_t)msm_direct_chunks((int)(n + 2), 1));
     DBuf<fr_t> canon(c, n);
     DBuf<uint32_t> cols(c, 2 * (n / 2 + 2));
     // two short rows over the multiples table; len terms per row, generator index per term in cols (or identity)
-    auto two_row_msm = [&](const uint32_t* d_cols, size_t len) {
-      launch_msm_direct(g.d_multiples.p, g.n_direct, (const uint32_t*)sLR.p, d_cols, 2, (int)len, part.p, nullptr,
+    // heavy = rows that carry the terms: both in a round (L, R), one for (Cx, Cy) — Cy is a single term
+    auto two_row_msm = [&](const uint32_t* d_cols, size_t len, int heavy) {
+      launch_msm_direct(g.d_multiples.p, g.n_direct, (const uint32_t*)sLR.p, d_cols, 2, (int)len, heavy, part.p, nullptr,
                         c->d_mapped + Ctx::kTaggedWord0, c->st);
       g_launches += 2;
     };
     launch_two_row_scalars(av, 0, fr_one(), fr_zero(), fr_zero(), Zr, fr_zero(), n, sLR.p, c->st);
-    two_row_msm(nullptr, n + 2);
+    two_row_msm(nullptr, n + 2, 1);
     // a_vec of the transcript = canonical bytes of b; the copy is waited for only when it is appended
     launch_canonicalize(bv, canon.p, n, c->d_flag, c->st);
     LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin, canon.p, n * 32, cudaMemcpyDeviceToHost, c->st));
@@ -1043,7 +1044,7 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
         std::swap(bv, bn);
         std::swap(W, Wn);
       }
-      two_row_msm(cols.p, n / 2 + 2);
+      two_row_msm(cols.p, n / 2 + 2, 2);
     };
     if (m != 1) launch_round(0);  // round 0 needs no challenge: it runs while the host absorbs Cx, Cy, a
     transcript.append_point_compressed("Cx", CxCy);
@@ -1120,8 +1121,8 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
     // delta = d * g_hat + r_delta * h with g_hat = sum_j W[j] G_j (dot_product.rs:219-227) and
     // beta = d * Q + r_beta * h (dot_product.rs:229-230) as the two rows of one MSM
     launch_two_row_scalars(W, 1, d, fr_zero(), r_delta, d, r_beta, n, sLR.p, c->st);
-    DBuf<pt_ext> part(c, 2 * (size_t)msm_direct_chunks((int)(n + 2)));
-    launch_msm_direct(g.d_multiples.p, g.n_direct, (const uint32_t*)sLR.p, nullptr, 2, (int)(n + 2), part.p, nullptr,
+    DBuf<pt_ext> part(c, 2 * (size_t)msm_direct_chunks((int)(n + 2), 1));
+    launch_msm_direct(g.d_multiples.p, g.n_direct, (const uint32_t*)sLR.p, nullptr, 2, (int)(n + 2), 1, part.p, nullptr,
                       c->d_mapped + Ctx::kTaggedWord0, c->st);
     LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin, av, 32, cudaMemcpyDeviceToHost, c->st));
     LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin + 32, bv, 32, cudaMemcpyDeviceToHost, c->st));

@@ -130,10 +130,10 @@ int main(int argc, char** argv) {
         // compact bullet-round shape: n/2 + 2 terms per row, all non-zero; identity columns
         snprintf(nm, sizeof nm, "msm_direct 2 rows x %zu terms (direct+finish)", n / 2 + 2);
         printf("%-52s %8.2f us\n", nm,
-               time_us([&] { launch_msm_direct(M, npts, (const uint32_t*)sLR, nullptr, 2, (int)(n / 2 + 2), part, nullptr, d_mapped, st); }, 300, st));
+               time_us([&] { launch_msm_direct(M, npts, (const uint32_t*)sLR, nullptr, 2, (int)(n / 2 + 2), 2, part, nullptr, d_mapped, st); }, 300, st));
         snprintf(nm, sizeof nm, "msm_direct 2 rows x %zu terms (direct+finish)", n + 2);
         printf("%-52s %8.2f us\n", nm,
-               time_us([&] { launch_msm_direct(M, npts, (const uint32_t*)sLR, nullptr, 2, (int)(n + 2), part, nullptr, d_mapped, st); }, 300, st));
+               time_us([&] { launch_msm_direct(M, npts, (const uint32_t*)sLR, nullptr, 2, (int)(n + 2), 1, part, nullptr, d_mapped, st); }, 300, st));
         cudaFree(M);
       }
     }
