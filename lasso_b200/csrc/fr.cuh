@@ -219,56 +219,80 @@ LB_HD void fr_mul_row(uint32_t e[9], uint32_t o[8], uint32_t& stray, const uint3
 }
 
 #if !defined(__CUDA_ARCH__)
-// Host fast path (the prover's Fiat-Shamir glue: interpolation, challenge arithmetic, u^-1): plain
-// 4 x 64-bit CIOS with unsigned __int128, ~10x faster than emulating the 32-bit carry chains.
-inline fr_t fr_mul_host64(const fr_t& A, const fr_t& B) {
-  typedef unsigned __int128 u128;
-  static const uint64_t P[4] = {0x5812631a5cf5d3edULL, 0x14def9dea2f79cd6ULL, 0x0ULL, 0x1000000000000000ULL};
-  const uint64_t INV = 0xd2b51da312547e1bULL;
-  uint64_t a[4], b[4];
+// Host fast path (the prover's Fiat-Shamir glue: interpolation, challenge arithmetic, u^-1): 4 x 64-bit CIOS with
+// unsigned __int128; the Montgomery step uses the shape of l (limbs {p0, p1, 0, 2^60}): two products and a shift
+// per row instead of four products.  ~3x faster than the generic 64-bit loop it replaced, ~30x faster than emulating
+// the 32-bit carry chains.
+namespace frh {
+typedef unsigned __int128 u128;
+struct w4 {
+  uint64_t v[4];
+};
+static const uint64_t kP0 = 0x5812631a5cf5d3edULL, kP1 = 0x14def9dea2f79cd6ULL, kP3 = 0x1000000000000000ULL;
+static const uint64_t kInv = 0xd2b51da312547e1bULL;
+inline w4 mul(const w4& a, const w4& b) {
+  uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5;
   for (int i = 0; i < 4; i++) {
-    a[i] = (uint64_t)A.v[2 * i] | ((uint64_t)A.v[2 * i + 1] << 32);
-    b[i] = (uint64_t)B.v[2 * i] | ((uint64_t)B.v[2 * i + 1] << 32);
-  }
-  uint64_t t[6] = {0, 0, 0, 0, 0, 0};
-  for (int i = 0; i < 4; i++) {
-    u128 c = 0;
-    for (int j = 0; j < 4; j++) {
-      c += (u128)t[j] + (u128)a[j] * b[i];
-      t[j] = (uint64_t)c;
-      c >>= 64;
-    }
-    c += t[4];
-    t[4] = (uint64_t)c;
-    t[5] = (uint64_t)(c >> 64);
-    uint64_t m = t[0] * INV;
-    c = ((u128)t[0] + (u128)m * P[0]) >> 64;
-    for (int j = 1; j < 4; j++) {
-      c += (u128)t[j] + (u128)m * P[j];
-      t[j - 1] = (uint64_t)c;
-      c >>= 64;
-    }
-    c += t[4];
-    t[3] = (uint64_t)c;
-    t[4] = t[5] + (uint64_t)(c >> 64);
+    const uint64_t bi = b.v[i];
+    u128 c = (u128)a.v[0] * bi + t0;
+    t0 = (uint64_t)c;
+    c = (c >> 64) + (u128)a.v[1] * bi + t1;
+    t1 = (uint64_t)c;
+    c = (c >> 64) + (u128)a.v[2] * bi + t2;
+    t2 = (uint64_t)c;
+    c = (c >> 64) + (u128)a.v[3] * bi + t3;
+    t3 = (uint64_t)c;
+    c = (c >> 64) + t4;
+    t4 = (uint64_t)c;
+    t5 = (uint64_t)(c >> 64);
+    // t += m * l, then shift one limb: m * l = m*p0 + m*p1*2^64 + m*2^252
+    const uint64_t m = t0 * kInv;
+    c = ((u128)m * kP0 + t0) >> 64;
+    c += (u128)m * kP1 + t1;
+    t0 = (uint64_t)c;
+    c = (c >> 64) + t2;
+    t1 = (uint64_t)c;
+    c = (c >> 64) + (u128)t3 + ((u128)m << 60);  // m * 2^60 at limb 3 (spills into limb 4)
+    t2 = (uint64_t)c;
+    c = (c >> 64) + t4;
+    t3 = (uint64_t)c;
+    t4 = t5 + (uint64_t)(c >> 64);
   }
   // t < 2l: one conditional subtraction
-  uint64_t s[4];
-  u128 bw = 0;
-  for (int i = 0; i < 4; i++) {
-    u128 d = (u128)t[i] - P[i] - (uint64_t)bw;
-    s[i] = (uint64_t)d;
-    bw = (d >> 64) & 1;
-  }
-  bool ge = t[4] != 0 || bw == 0;
+  uint64_t s0, s1, s2, s3;
+  u128 d = (u128)t0 - kP0;
+  s0 = (uint64_t)d;
+  d = (u128)t1 - kP1 - (uint64_t)((d >> 64) & 1);
+  s1 = (uint64_t)d;
+  d = (u128)t2 - (uint64_t)((d >> 64) & 1);
+  s2 = (uint64_t)d;
+  d = (u128)t3 - kP3 - (uint64_t)((d >> 64) & 1);
+  s3 = (uint64_t)d;
+  const bool ge = t4 != 0 || ((d >> 64) & 1) == 0;
+  w4 r;
+  r.v[0] = ge ? s0 : t0;
+  r.v[1] = ge ? s1 : t1;
+  r.v[2] = ge ? s2 : t2;
+  r.v[3] = ge ? s3 : t3;
+  return r;
+}
+inline w4 load(const fr_t& a) {
+  w4 r;
+  for (int i = 0; i < 4; i++) r.v[i] = (uint64_t)a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32);
+  return r;
+}
+inline fr_t store(const w4& a) {
   fr_t r;
   for (int i = 0; i < 4; i++) {
-    uint64_t v = ge ? s[i] : t[i];
-    r.v[2 * i] = (uint32_t)v;
-    r.v[2 * i + 1] = (uint32_t)(v >> 32);
+    r.v[2 * i] = (uint32_t)a.v[i];
+    r.v[2 * i + 1] = (uint32_t)(a.v[i] >> 32);
   }
   return r;
 }
+}  // namespace frh
+#endif
+#if !defined(__CUDA_ARCH__)
+inline fr_t fr_mul_host64(const fr_t& A, const fr_t& B) { return frh::store(frh::mul(frh::load(A), frh::load(B))); }
 #endif
 
 // the even/odd carry-chain multiplication (device path; also runs on the host for validation)
@@ -315,14 +339,55 @@ LB_HD fr_t fr_to_canonical(const fr_t& a) {
 // from a raw < 2^256 integer to Montgomery form
 LB_HD fr_t fr_from_raw_int(const fr_t& raw) { return fr_mul(raw, fr_r2()); }
 
+
+#if !defined(__CUDA_ARCH__)
+namespace frh {
+// Inversion (u^-1 of every Bulletproofs round, the batching coefficients of a grand-product layer): the whole
+// exponentiation stays on 64-bit limbs; l - 2 = 2^252 + (125 bits) is walked with a fixed 4-bit window
+// (252 squarings + ~32 multiplications).
+inline fr_t inv(const fr_t& A) {
+  // l - 2 = 2^252 + 0x14def9dea2f79cd65812631a5cf5d3eb
+  static const uint64_t E[4] = {0x5812631a5cf5d3ebULL, 0x14def9dea2f79cd6ULL, 0x0ULL, 0x1000000000000000ULL};
+  w4 tab[16];
+  tab[1] = load(A);
+  tab[2] = mul(tab[1], tab[1]);
+  for (int i = 3; i < 16; i++) tab[i] = mul(tab[i - 1], tab[1]);
+  w4 acc = tab[1];  // the top window (bits 252..255) is 1
+  for (int w = 62; w >= 0; w--) {
+    acc = mul(acc, acc);
+    acc = mul(acc, acc);
+    acc = mul(acc, acc);
+    acc = mul(acc, acc);
+    const unsigned d = (unsigned)(E[w >> 4] >> (4 * (w & 15))) & 15u;
+    if (d) acc = mul(acc, tab[d]);
+  }
+  return store(acc);
+}
+}  // namespace frh
+#endif
+
 // a^(l-2)
 LB_HD fr_t fr_inv(const fr_t& a) {
+#if !defined(__CUDA_ARCH__)
+  return frh::inv(a);
+#else
   // l - 2 = 2^252 + 0x14def9dea2f79cd65812631a5cf5d3eb
   const uint32_t E[8] = {0x5cf5d3ebu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu, 0, 0, 0, 0x10000000u};
   fr_t acc = fr_one();
   for (int i = 252; i >= 0; i--) {
     acc = fr_sqr(acc);
     if ((E[i >> 5] >> (i & 31)) & 1) acc = fr_mul(acc, a);
+  }
+  return acc;
+#endif
+}
+// the bitwise square-and-multiply on the portable multiplication (reference for the host fast path)
+LB_HD fr_t fr_inv_chain(const fr_t& a) {
+  const uint32_t E[8] = {0x5cf5d3ebu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu, 0, 0, 0, 0x10000000u};
+  fr_t acc = fr_one();
+  for (int i = 252; i >= 0; i--) {
+    acc = fr_mul_chain(acc, acc);
+    if ((E[i >> 5] >> (i & 31)) & 1) acc = fr_mul_chain(acc, a);
   }
   return acc;
 }

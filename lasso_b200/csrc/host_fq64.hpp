@@ -109,6 +109,27 @@ inline void compress_xyz(const uint32_t* xyz, uint8_t out[32]) {
   memcpy(out, y.v, 32);
   if (neg) out[31] |= 0x80;
 }
+// Two points at once (L and R of a Bulletproofs round): one inversion for both (Montgomery's trick)
+inline void compress_xyz_pair(const uint32_t* xyz_a, const uint32_t* xyz_b, uint8_t out_a[32], uint8_t out_b[32]) {
+  const fe Za = from_limbs32(xyz_a + 16), Zb = from_limbs32(xyz_b + 16);
+  const fe zi = inv(mul(Za, Zb));
+  const fe zia = mul(zi, Zb), zib = mul(zi, Za);
+  const uint32_t* src[2] = {xyz_a, xyz_b};
+  const fe* z[2] = {&zia, &zib};
+  uint8_t* dst[2] = {out_a, out_b};
+  for (int k = 0; k < 2; k++) {
+    const fe x = canonical(mul(from_limbs32(src[k]), *z[k])), y = canonical(mul(from_limbs32(src[k] + 8), *z[k]));
+    u128 c = 9;  // x > (q-1)/2  <=>  x + 9 >= 2^254
+    uint64_t top = 0;
+    for (int i = 0; i < 4; i++) {
+      c += x.v[i];
+      top = (uint64_t)c;
+      c >>= 64;
+    }
+    memcpy(dst[k], y.v, 32);
+    if ((top >> 62) != 0) dst[k][31] |= 0x80;
+  }
+}
 
 }  // namespace h64
 }  // namespace lb

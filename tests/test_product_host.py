@@ -33,8 +33,17 @@ int main() {
     a = fr_add(m1, b);
     b = fr_sub(m2, fr_from_u64(g()));
   }
-  // fr_inv: a * a^-1 == 1
-  if (!fr_eq(fr_mul(a, fr_inv(a)), fr_one())) bad++;
+  // fr_inv (host: 64-bit limbs, 4-bit window) == bitwise square-and-multiply on the carry-chain multiplication
+  for (int i = 0; i < 300; i++) {
+    fr_t x = fr_add(fr_mul(a, fr_from_u64(g())), fr_from_u64(g()));
+    fr_t i1 = fr_inv(x), i2 = fr_inv_chain(x);
+    if (!fr_eq(i1, i2) || !fr_eq(fr_mul(x, i1), fr_one())) bad++;
+    a = x;
+  }
+  {
+    fr_t one = fr_one(), m1 = fr_sub(fr_zero(), one);
+    if (!fr_eq(fr_inv(one), one) || !fr_eq(fr_inv(m1), m1)) bad++;
+  }
   // 3. host Fq64 normalisation == device-code normalisation + ark compression
   fq_t bx = {{0x8f25d51au, 0xc9562d60u, 0x9525a7b2u, 0x692cc760u, 0xfdd6dc5cu, 0xc0a4e231u, 0xcd6e53feu, 0x216936d3u}};
   fq_t by = {{0x66666658u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u}};
@@ -51,6 +60,14 @@ int main() {
     uint8_t h[32];
     h64::compress_xyz(xyz, h);
     if (memcmp(h, c, 32)) bad++;
+    // pair version (one inversion for two points) against the single one: this point and its double
+    pt_ext dbl = pt_dbl(acc);
+    uint32_t xyz2[32];
+    memcpy(xyz2, dbl.X.v, 32); memcpy(xyz2 + 8, dbl.Y.v, 32); memcpy(xyz2 + 16, dbl.Z.v, 32); memcpy(xyz2 + 24, dbl.T.v, 32);
+    uint8_t h2[32], pa[32], pb[32];
+    h64::compress_xyz(xyz2, h2);
+    h64::compress_xyz_pair(xyz, xyz2, pa, pb);
+    if (memcmp(pa, h, 32) || memcmp(pb, h2, 32)) bad++;
   }
   printf("bad=%d\n", bad);
   return bad;
