@@ -342,6 +342,29 @@ int orc_grand_product_kat(const uint64_t* vals, size_t n, uint64_t* product_out)
   return 0;
 }
 
+// dense_mlpoly.rs:586-624 (check_polynomial_commit) and dot_product.rs:350-384 (check_dotproductproof_log) in one:
+// commit Z (n = 2^nv elements) with generators sampled from `label`, prove the evaluation at r, verify.
+// tamper != 0: the verifier is given eval + 1 and must reject.  eval_out = Z(r).  rc 0 = behaved as expected.
+int orc_polyeval_roundtrip(const uint64_t* Z, size_t n, const uint64_t* r, size_t nv, const char* label,
+                           const uint64_t* tape_seed, int tamper, uint64_t* eval_out) {
+  DensePolynomial poly(ldvec(Z, n));
+  if (poly.num_vars != nv) return 10;
+  std::vector<Fr> rv = ldvec(r, nv);
+  Fr eval = poly.evaluate(rv);
+  stfr(eval_out, eval);
+  size_t l, rr;
+  EqPolynomial::compute_factored_lens(nv, l, rr);
+  PolyCommitmentGens gens = PolyCommitmentGens::make(nv, sample_generators(pow2(rr) + 2, label));
+  PolyCommitment comm = poly.commit(gens);
+  RandomTape tape("proof", ldfr(tape_seed));
+  Transcript tp("example");
+  PolyEvalProof proof = PolyEvalProof::prove(poly, rv, eval, gens, tp, tape);
+  Transcript tv("example");
+  Fr claimed = tamper ? eval + Fr::one() : eval;
+  bool ok = proof.verify_plain(gens, tv, rv, claimed, comm);
+  return (ok == (tamper == 0)) ? 0 : 1;
+}
+
 // densified.rs:21-75: indices = n x C (u64, row-major); outputs dim/read (C x s), final (C x m) as integers
 void orc_densify(const uint64_t* indices, size_t n, size_t C, size_t log_m, uint64_t* dim, uint64_t* read,
                  uint64_t* fin) {

@@ -200,3 +200,23 @@ def test_split_bits_and_densify_fixture():
     idx = np.array([[1], [2], [1]], dtype=np.uint64)
     lib().orc_densify(P(idx), sz(3), sz(1), sz(3), P(dim), P(rd), P(fin))
     assert dim.tolist() == [1, 2, 1, 0] and rd.tolist() == [0, 0, 1, 0] and fin.tolist() == [1, 2, 1, 0, 0, 0, 0, 0]
+
+
+def test_polynomial_commit_roundtrip_kat():
+    """poly/dense_mlpoly.rs:586-624 check_polynomial_commit: Z = [1, 2, 1, 4], r = [4, 3] -> eval 28; commit with
+    PolyCommitmentGens::new(2, b"test-two"), PolyEvalProof::prove, verify accepts — and rejects eval + 1.  The same
+    roundtrip at 2^6 elements walks three rounds of the Bulletproofs reduction (dot_product.rs:350-384)."""
+    lib = ol.lib()
+    Z = ol.fr_array([1, 2, 1, 4])
+    r = ol.fr_array([4, 3])
+    seed = ol.fr_array([12345])
+    out = np.zeros(4, dtype=np.uint64)
+    for tamper in (0, 1):
+        rc = lib.orc_polyeval_roundtrip(ol.P(Z), ol.sz(4), ol.P(r), ol.sz(2), b"test-two", ol.P(seed), tamper, ol.P(out))
+        assert rc == 0
+        assert ol.fr_ints(out.reshape(1, 4)) == [28]
+    rng = np.random.default_rng(4)
+    Z = ol.rand_fr(rng, 64)
+    r = ol.rand_fr(rng, 6)
+    for tamper in (0, 1):
+        assert lib.orc_polyeval_roundtrip(ol.P(Z), ol.sz(64), ol.P(r), ol.sz(6), b"test-two", ol.P(seed), tamper, ol.P(out)) == 0
