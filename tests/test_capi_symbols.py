@@ -23,6 +23,40 @@ def test_library_exports_every_declared_symbol():
     assert not missing, missing
 
 
+def test_header_is_plain_c_and_links(tmp_path):
+    """The drop-in boundary is a C ABI: include/lasso_b200.h must compile as strict C11 (no C++, no torch types) and a
+    plain C program must link against the shared library; without a device the first call fails with a clean error."""
+    import subprocess
+
+    import lasso_b200 as lb
+
+    src = tmp_path / "t.c"
+    src.write_text(r"""
+#include "lasso_b200.h"
+#include <stdio.h>
+int main(void) {
+  lasso_ctx* ctx = 0;
+  int rc = lasso_ctx_create(&ctx, 0);
+  printf("%d|%s\n", rc, lasso_last_error());
+  if (rc == 0) lasso_ctx_destroy(ctx);
+  return 0;
+}
+""")
+    libdir = os.path.dirname(lb.library_path())
+    exe = tmp_path / "t"
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-L", libdir, "-llasso_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0
+    rc, msg = out.stdout.strip().split("|", 1)
+    import torch
+
+    if torch.cuda.is_available():
+        assert rc == "0"
+    else:
+        assert rc == "-1" and "no CPU fallback" in msg
+
+
 def test_no_cpu_fallback():
     import torch
 
