@@ -191,11 +191,27 @@ class Strobe {
     pos_ = 0;
     pos_begin_ = 0;
   }
+  // XOR the message into the rate portion, a block at a time (the 64 KB `a` vector of every opening goes through
+  // here as 2048 framed messages: 8 bytes per step instead of one)
   void absorb(const uint8_t* d, size_t n) {
     uint8_t* s = bytes();
-    for (size_t i = 0; i < n; i++) {
-      s[pos_] ^= d[i];
-      if (++pos_ == kRate) run_f();
+    while (n) {
+      size_t take = (size_t)(kRate - pos_);
+      if (take > n) take = n;
+      uint8_t* dst = s + pos_;
+      size_t i = 0;
+      for (; i + 8 <= take; i += 8) {
+        uint64_t a, b;
+        memcpy(&a, dst + i, 8);
+        memcpy(&b, d + i, 8);
+        a ^= b;
+        memcpy(dst + i, &a, 8);
+      }
+      for (; i < take; i++) dst[i] ^= d[i];
+      pos_ += (int)take;
+      d += take;
+      n -= take;
+      if (pos_ == kRate) run_f();
     }
   }
   void op(uint8_t flags, bool more) {

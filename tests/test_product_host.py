@@ -23,9 +23,68 @@ int main() {
   t.challenge_bytes("challenge", o, 32);
   for (int i = 0; i < 32; i++) printf("%02x", o[i]);
   printf("\n");
+  int bad = 0;
+  // 1b. block-wise absorb: random framed messages of every length (0 .. 400 bytes, crossing the 166-byte rate
+  // several times) against a byte-at-a-time STROBE written out here
+  {
+    struct SlowStrobe {
+      uint64_t lanes[25];
+      int pos = 0, pos_begin = 0;
+      uint8_t* b() { return reinterpret_cast<uint8_t*>(lanes); }
+      void run_f() {
+        b()[pos] ^= (uint8_t)pos_begin; b()[pos + 1] ^= 0x04; b()[167] ^= 0x80;
+        KeccakF1600::permute(lanes); pos = 0; pos_begin = 0;
+      }
+      void absorb(const uint8_t* d, size_t n) { for (size_t i = 0; i < n; i++) { b()[pos] ^= d[i]; if (++pos == 166) run_f(); } }
+      void op(uint8_t flags, bool more) {
+        if (more) return;
+        uint8_t hdr[2] = {(uint8_t)pos_begin, flags};
+        pos_begin = pos + 1;
+        absorb(hdr, 2);
+        if ((flags & (4 | 32)) && pos != 0) run_f();
+      }
+      explicit SlowStrobe(const std::string& proto) {
+        memset(lanes, 0, sizeof(lanes));
+        const uint8_t head[6] = {1, 168, 1, 0, 1, 96};
+        memcpy(b(), head, 6); memcpy(b() + 6, "STROBEv1.0.2", 12);
+        KeccakF1600::permute(lanes);
+        op(16 | 2, false); absorb((const uint8_t*)proto.data(), proto.size());
+      }
+      void msg(const char* label, const uint8_t* m, uint32_t n) {
+        op(16 | 2, false); absorb((const uint8_t*)label, strlen(label));
+        op(16 | 2, true); absorb((const uint8_t*)&n, 4);
+        op(2, false); absorb(m, n);
+      }
+      void chal(const char* label, uint8_t* out, uint32_t n) {
+        op(16 | 2, false); absorb((const uint8_t*)label, strlen(label));
+        op(16 | 2, true); absorb((const uint8_t*)&n, 4);
+        op(1 | 2 | 4, false);
+        for (uint32_t i = 0; i < n; i++) { out[i] = b()[pos]; b()[pos] = 0; if (++pos == 166) run_f(); }
+      }
+    };
+    std::mt19937_64 gg(99);
+    Transcript tf("blockwise");  // Transcript's constructor: STROBE("Merlin v1.0") + the "dom-sep" message
+    SlowStrobe ts("Merlin v1.0");
+    ts.msg("dom-sep", (const uint8_t*)"blockwise", 9);
+    int mism = 0;
+    std::vector<uint8_t> m(400);
+    for (int it = 0; it < 600; it++) {
+      uint32_t n = (uint32_t)(gg() % 401);
+      for (auto& x : m) x = (uint8_t)gg();
+      tf.append_message("lbl", m.data(), n);
+      ts.msg("lbl", m.data(), n);
+      if (it % 7 == 0) {
+        uint8_t o1[64], o2[64];
+        tf.challenge_bytes("ch", o1, 64);
+        ts.chal("ch", o2, 64);
+        if (memcmp(o1, o2, 64)) mism++;
+      }
+    }
+    if (mism) printf("blockwise absorb mismatches: %d\n", mism);
+    bad += mism;
+  }
   // 2. fast host Fr (64-bit limbs) == even/odd carry-chain multiplication (the device algorithm)
   std::mt19937_64 g(7);
-  int bad = 0;
   fr_t a = fr_from_u64(g()), b = fr_from_u64(g());
   for (int i = 0; i < 20000; i++) {
     fr_t m1 = fr_mul(a, b), m2 = fr_mul_chain(a, b);
