@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the Lasso prover hot path on B200 (contract in the task prompt).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--log-s 20]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload prove|msm] [--log-s 20]
 
 One "step" = one pass of the hot path over one batch of synthetic lookups:
     DensifiedRepresentation::from_lookup_indices -> commit -> SparsePolynomialEvaluationProof::prove
@@ -12,14 +12,20 @@ for the XOR subtable strategy, C = 4, M = 2^16, 2^20 lookups, G = curve25519 (BA
           index / counter arrays, commit, prove incl. every device->host transfer of round messages and
           the proof bytes)
   roofline     : the bind kernel (K1) timed alone with CUDA events on the library's stream
-  cpu_baseline : the CPU oracle port on this box's host cores, bounded sample (rank 0, N = 1 only)
+  cpu_baseline : the CPU oracle port on this box's host cores, the same 2^20 workload (rank 0, N = 1 only)
+  configs      : BASELINE.json configs 2-4 (XOR 2^20, LT C=8 2^22, RangeCheck<40> C=4 2^24), ONE proof each:
+                 N = 1 on one GPU; N > 1 the same proof SHARDED over the N GPUs (csrc/comm.cu), with the SHA-256 of
+                 the proof bytes compared with a single-GPU proof of the same inputs made in the same run and with the
+                 oracle-generated golden hash (tests/golden/big_proofs.json)
 
-N > 1: one process per GPU under torchrun; each rank proves its own independent batch (weak scaling, no
-data-path collective — proofs of different lookup batches are independent objects); value = N * s / max_t.
+N > 1: one process per GPU under torchrun; the headline numbers are N independent proofs (one per rank, weak scaling,
+no data-path collective — proofs of different lookup batches are independent objects): value = N * s / max_t.
 --impl reference: the reference's own CPU implementation of the path = the oracle port (the Rust crate cannot
-be built in this image: no cargo/rustc, crates not vendored), all host threads, rank 0 only.
+be built in this image: no cargo/rustc, crates not vendored), all host threads, rank 0 only, the SAME 2^20 workload.
+--workload msm: BASELINE.json configs[4], the VariableBaseMSM-only sweep (tools/msm_bench.py holds the details).
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -33,23 +39,17 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
+import workloads as wl  # noqa: E402
+
 METRIC = "Lasso prove lookups/sec (2^20 lookups, C=4, M=2^16)"
 UNIT = "lookups/s"
 KIND_XOR = 2
+make_inputs = wl.make_inputs
 
 
-def make_inputs(log_s, C, log_m, seed):
-    """Synthetic lookups mirroring src/benches/bench.rs:13-34: one uniform index per lookup, repeated in all
-    C dimensions ([x; C]); r = log2(s) uniform field elements; explicit recorded seed instead of test_rng."""
-    import oracle_lib as ol  # only for the big-int -> Montgomery helpers (no oracle code is executed)
-
-    rng = np.random.default_rng(seed)
-    n = 1 << log_s
-    col = rng.integers(0, 1 << log_m, size=(n, 1), dtype=np.uint64)
-    idx = np.ascontiguousarray(np.repeat(col, C, axis=1))
-    r = ol.rand_fr(rng, log_s)
-    tape_seed = ol.rand_fr(rng, 1)[0]
-    return idx, r, tape_seed
+def golden_cases():
+    p = os.path.join(ROOT, "tests", "golden", "big_proofs.json")
+    return json.load(open(p))["cases"] if os.path.exists(p) else {}
 
 
 class ClockSampler:
@@ -117,18 +117,19 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_sample(log_s_sample, C, log_m, threads=None):
-    """Time the oracle port (Densify + commit + prove) on host cores; one warm-up run first so lazily
-    backed VM memory is already faulted in (see oracle/capi.cpp)."""
-    import oracle_lib as ol
-
-    idx, r, seed = make_inputs(log_s_sample, C, log_m, 12345)
-    need = (1 << ((log_s_sample + 3) - (log_s_sample + 3) // 2)) + 2
-    gens = ol.generators(max(need, 300))
-    if threads:
-        ol.lib().orc_set_num_threads(int(threads))
-    cores = ol.lib().orc_num_threads()
-    return ol, idx, r, seed, gens, cores
+def generator_stream(lb, need):
+    """The first `need` points of the b"gens_sparse_poly" stream: a cached file of the oracle's sampler (the same
+    bytes: tests/test_gpu_kernels.py checks the library's sampler against it) or sampled here."""
+    d = os.path.join(ROOT, "oracle", "_build")
+    have = []
+    if os.path.isdir(d):
+        for f in os.listdir(d):
+            if f.startswith("gens_gens_sparse_poly_") and f.endswith(".npy"):
+                have.append(int(f[len("gens_gens_sparse_poly_"):-4]))
+    for cand in sorted(have):
+        if cand >= need:
+            return np.ascontiguousarray(np.load(os.path.join(d, "gens_gens_sparse_poly_%d.npy" % cand))[:need])
+    return lb.sample_generators(b"gens_sparse_poly", need)
 
 
 def best_threads(C=4, log_m=16, log_probe=14):
@@ -156,36 +157,95 @@ def best_threads(C=4, log_m=16, log_probe=14):
     return best_t, ncpu
 
 
+def cpu_workload(log_s, C=4, log_m=16):
+    """The bench workload itself (seed BENCH_SEED, rank 0) for the CPU arm."""
+    import oracle_lib as ol
+
+    idx, r, seed = make_inputs(log_s, C, log_m, wl.BENCH_SEED)
+    gens = np.ascontiguousarray(ol.generators(wl.gens_needed(C, log_s, C, log_m)))
+    return ol, idx, r, seed, gens
+
+
 def run_reference(args):
-    """--impl reference: the reference's own CPU path = oracle port, all host threads, rank 0 only."""
+    """--impl reference: the reference's own CPU path = oracle port, all host threads it can use, rank 0 only, the
+    SAME workload as the GPU arm (XOR C=4 M=2^16, 2^20 lookups per step, the same seed)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    C, log_m = 4, 16
-    log_ss = 18 if (args.steps + args.warmup) <= 6 else 16
+    C, log_m, log_s = 4, 16, args.log_s
     nthreads, ncpu = best_threads()
-    ol, idx, r, seed, gens, cores = cpu_sample(log_ss, C, log_m, threads=nthreads)
+    ol, idx, r, seed, gens = cpu_workload(log_s, C, log_m)
+    cores = ol.lib().orc_num_threads()
+    res = None
     for _ in range(max(1, args.warmup)):
-        ol.prove(KIND_XOR, C, log_m, 0, idx, r, gens, seed, flags=0)
+        res = ol.prove(KIND_XOR, C, log_m, 0, idx, r, gens, seed, flags=0)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         res = ol.prove(KIND_XOR, C, log_m, 0, idx, r, gens, seed, flags=0)
         assert res["rc"] == 0
     dt = time.perf_counter() - t0
-    val = args.steps * (1 << log_ss) / dt
-    sample = ("XOR C=4 M=2^16, 2^%d lookups per step (bounded sample of the 2^20 workload), densify+commit+prove; "
-              "OpenMP team = fastest of a probe over team sizes (%d of %d logical CPUs)" % (log_ss, nthreads, ncpu))
+    val = args.steps * (1 << log_s) / dt
+    sha = hashlib.sha256(res["proof"]).hexdigest()
+    gold = golden_cases().get("xor_c4_s20", {}) if log_s == 20 else {}
+    sample = ("XOR C=4 M=2^16, 2^%d lookups per step = the whole workload of the GPU arm (same seed), densify+commit+prove; "
+              "OpenMP team = fastest of a probe over team sizes (%d of %d logical CPUs)" % (log_s, nthreads, ncpu))
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64x4 Montgomery (CPU)", "data": "synthetic",
-        "config": {"workload": "Lasso XOR subtable, C=4, M=2^16, 2^20 lookups, G=curve25519 (CPU arm times a 2^%d sample)" % log_ss,
-                   "note": "restated CPU baseline (C++/OpenMP oracle port), not the Rust binary"},
+        "config": {"workload": "Lasso XOR subtable, C=4, M=2^16, 2^%d lookups per step, G=curve25519: densify + commit + prove" % log_s,
+                   "note": "restated CPU baseline (C++/OpenMP oracle port), not the Rust binary",
+                   "proof_sha256": sha, "golden_match": (sha == gold.get("proof_sha256")) if gold else None,
+                   "spans_ms": {k: round(v, 1) for k, v in res["spans"].items()}},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def prove_config(lb, ctx, name, steps, stream_cache):
+    """ONE proof of a BASELINE configuration on `ctx` (single GPU, or sharded when the context has a communicator):
+    1 warm-up, then `steps` timed end-to-end runs (densify + commit + prove, host buffers); returns the timings of the
+    library's own spans and the hashes of the bytes."""
+    kind, C, log_m, log_r, log_s, idx, r, tape_seed = wl.config_inputs(name)
+    S = lb.Strategy(kind, C, log_m, log_r)
+    s = 1 << log_s
+    need = lb.gens_points_needed(C, s, S.num_memories, log_m)
+    if need not in stream_cache:
+        stream_cache[need] = generator_stream(lb, need)
+    t0 = time.perf_counter()
+    gens = lb.SparsePolyCommitmentGens.new(ctx, b"gens_sparse_poly", C, s, S.num_memories, log_m, stream=stream_cache[need])
+    setup_ms = 1e3 * (time.perf_counter() - t0)
+    best = None
+    com = proof = None
+    for it in range(1 + steps):
+        t0 = time.perf_counter()
+        dense = lb.DensifiedRepresentation.from_lookup_indices(ctx, idx, log_m)
+        t1 = time.perf_counter()
+        com = dense.commit(gens)
+        t2 = time.perf_counter()
+        proof = lb.SparsePolynomialEvaluationProof.prove(ctx, S, dense, r, gens, tape_seed=tape_seed)
+        t3 = time.perf_counter()
+        del dense
+        cur = {"densify_ms": 1e3 * (t1 - t0), "commit_ms": 1e3 * (t2 - t1), "prove_ms": 1e3 * (t3 - t2)}
+        if it >= 1 and (best is None or cur["commit_ms"] + cur["prove_ms"] < best["commit_ms"] + best["prove_ms"]):
+            best = cur
+    del gens
+    out = {"name": name, "lookups": s, "setup_ms": round(setup_ms, 1)}
+    out.update({k: round(v, 3) for k, v in best.items()})
+    out["ms_per_proof"] = round(best["commit_ms"] + best["prove_ms"], 3)  # device-resident: commit + prove
+    out["e2e_ms_per_proof"] = round(best["densify_ms"] + best["commit_ms"] + best["prove_ms"], 3)
+    out["proof_sha256"] = hashlib.sha256(proof.bytes).hexdigest()
+    out["commitment_sha256"] = hashlib.sha256(com).hexdigest()
+    return out
+
+
+def run_msm(args):
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import msm_bench
+
+    msm_bench.main(args)
 
 
 def main():
@@ -194,12 +254,16 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="prove", choices=["prove", "msm"])
     ap.add_argument("--log-s", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sharded", action="store_true",
-                    help="N > 1: ONE proof sharded over the N GPUs (strong scaling, NCCL exchange per sumcheck round) "
-                         "instead of one independent proof per GPU")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-configuration block (configs 2-4, one proof each)")
+    ap.add_argument("--configs", default="xor_c4_s20,lt_c8_s22,rc40_c4_s24")
+    ap.add_argument("--msm-max-log", type=int, default=24)
     args = ap.parse_args()
+    if args.workload == "msm":
+        run_msm(args)
+        return
     if args.impl == "reference":
         run_reference(args)
         return
@@ -209,6 +273,7 @@ def main():
     import torch.distributed as dist
 
     import lasso_b200 as lb
+    from lasso_b200 import parallel
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -220,16 +285,17 @@ def main():
     C, log_m, log_s = 4, 16, args.log_s
     s = 1 << log_s
     S = lb.Strategy(lb.XOR, C, log_m)
-    sharded = args.sharded and world > 1
-    # independent proofs: each rank its own batch; sharded: every rank the same lookups (one proof)
-    idx, r, tape_seed = make_inputs(log_s, C, log_m, 0x4C4153534F + (0 if sharded else rank))
+    # independent proofs: each rank its own batch
+    idx, r, tape_seed = make_inputs(log_s, C, log_m, wl.BENCH_SEED + rank)
     ctx = lb.Context(local_rank)
-    if sharded:
-        ctx.init_comm(rank, world)
+    numa_node = ctx.bind_host_threads() if world > 1 else -1  # one process per GPU: keep its host side on the GPU's node
     need = lb.gens_points_needed(C, s, S.num_memories, log_m)
-    cache = os.path.join(ROOT, "oracle", "_build", "gens_gens_sparse_poly_%d.npy" % need)
-    stream = np.load(cache) if os.path.exists(cache) else lb.sample_generators(b"gens_sparse_poly", need)
-    gens = lb.SparsePolyCommitmentGens.new(ctx, b"gens_sparse_poly", C, s, S.num_memories, log_m, stream=stream)
+    streams = {need: generator_stream(lb, need)}
+    free0 = torch.cuda.mem_get_info()[0]
+    t0 = time.perf_counter()
+    gens = lb.SparsePolyCommitmentGens.new(ctx, b"gens_sparse_poly", C, s, S.num_memories, log_m, stream=streams[need])
+    setup_ms = 1e3 * (time.perf_counter() - t0)
+    tables_gb = (free0 - torch.cuda.mem_get_info()[0]) / 1e9
 
     def barrier():
         if world > 1:
@@ -242,9 +308,9 @@ def main():
         proof = lb.SparsePolynomialEvaluationProof.prove(ctx, S, dense, r, gens, tape_seed=tape_seed)
         return dense, com, proof
 
-    def step_resident(dense):
-        com = dense.commit(gens)
-        proof = lb.SparsePolynomialEvaluationProof.prove(ctx, S, dense, r, gens, tape_seed=tape_seed)
+    def step_resident(dense, g=None):
+        com = dense.commit(g or gens)
+        proof = lb.SparsePolynomialEvaluationProof.prove(ctx, S, dense, r, g or gens, tape_seed=tape_seed)
         return com, proof
 
     # ---- warm-up (>= 3): also produces the resident densified representation.  The clock sampler (one streaming
@@ -256,6 +322,7 @@ def main():
     for _ in range(args.warmup):
         dense, com0, proof0 = step_e2e()
     proof_bytes, com_bytes = len(proof0.bytes), len(com0)
+    proof_sha = hashlib.sha256(proof0.bytes).hexdigest()
 
     # ---- timed: device-resident (value)
     barrier()
@@ -275,25 +342,40 @@ def main():
     barrier()
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev2.record()
+    dens_ms = 0.0
     for _ in range(args.steps):
         step_e2e()
+        dens_ms += ctx.last_timings_ms()["densify"]
     ev3.record()
     barrier()
     t_e2e = ev2.elapsed_time(ev3) / 1e3
     # the timed region can be shorter than the sampling period: keep the same load running (untimed) until the
     # sampler has seen the GPU under it at least twice
     t_guard = time.perf_counter()
-    if sharded:  # collective steps: the same number on every rank
-        for _ in range(6):
-            step_resident(dense)
-    while not sharded and sampler.proc and sampler.count() < 2 and time.perf_counter() - t_guard < 3.0:
+    while sampler.proc and sampler.count() < 2 and time.perf_counter() - t_guard < 3.0:
         step_resident(dense)
     clocks = sampler.stop()
 
     if world > 1:
-        tt = torch.tensor([t_res, t_e2e], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_res, t_e2e = float(tt[0]), float(tt[1])
+        t_res, t_e2e = parallel.max_over_ranks([t_res, t_e2e])
+
+    # ---- the same step without the digit-multiples tables: the Pippenger-bucket path the north star names
+    no_tables = None
+    if world == 1:
+        os.environ["LASSO_B200_NO_MULTIPLES"] = "1"
+        try:
+            g2 = lb.SparsePolyCommitmentGens.new(ctx, b"gens_sparse_poly", C, s, S.num_memories, log_m, stream=streams[need])
+            com2, proof2 = step_resident(dense, g2)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                step_resident(dense, g2)
+            torch.cuda.synchronize()
+            no_tables = {"ms_per_step": round(1e3 * (time.perf_counter() - t0) / args.steps, 3),
+                         "same_bytes_as_table_path": bool(proof2.bytes == proof0.bytes and com2 == com0)}
+            del g2
+        finally:
+            del os.environ["LASSO_B200_NO_MULTIPLES"]
 
     # ---- roofline of the bind kernel (K1), timed alone with CUDA events on the library's stream:
     # 5 polynomials x 2^22 elements (640 MiB > 126 MB L2), 96 algorithmic bytes per output element
@@ -303,25 +385,65 @@ def main():
     achieved = alg_bytes / (ms * 1e-3) / 1e9
     peak, peak_src = measured_peak_hbm()
 
+    # ---- BASELINE configs 2-4, ONE proof each: single GPU at N = 1, the SAME proof sharded over the N GPUs otherwise
+    gold = golden_cases()
+    config_rows = []
+    if not args.no_configs:
+        del dense, gens
+        names = [n for n in args.configs.split(",") if n]
+        single = {}
+        if world > 1:
+            # reference bytes for the sharded proofs: a single-GPU proof of the same inputs, made by rank 0 right here
+            if rank == 0:
+                for n in names:
+                    single[n] = prove_config(lb, ctx, n, 1, streams)
+            dist.barrier()
+            sctx = lb.Context(local_rank)
+            sctx.init_comm(rank, world)
+        for n in names:
+            row = prove_config(lb, sctx if world > 1 else ctx, n, max(1, min(args.steps, 3)), streams)
+            row["mode"] = "one proof sharded over %d GPUs (low index bits)" % world if world > 1 else "one proof on one GPU"
+            if world > 1:
+                tm = parallel.max_over_ranks([row["ms_per_proof"], row["e2e_ms_per_proof"]])
+                row["ms_per_proof"], row["e2e_ms_per_proof"] = round(tm[0], 3), round(tm[1], 3)
+                if rank == 0:
+                    row["single_gpu_ms_per_proof"] = single[n]["ms_per_proof"]
+                    row["matches_single_gpu"] = bool(row["proof_sha256"] == single[n]["proof_sha256"] and
+                                                     row["commitment_sha256"] == single[n]["commitment_sha256"])
+            g = gold.get(n)
+            row["golden_match"] = bool(g and g["proof_sha256"] == row["proof_sha256"] and
+                                       g["commitment_sha256"] == row["commitment_sha256"]) if g else None
+            config_rows.append(row)
+        if world > 1:
+            sctx.close()
+
     line = None
     if rank == 0:
         nv_l = int(np.log2(2 * C * s))
         h2d = 4 * ((1 << nv_l) + (C << log_m))
+        g20 = gold.get("xor_c4_s20") if log_s == 20 else None
         line = {
-            "metric": METRIC, "value": (1 if sharded else world) * args.steps * s / t_res, "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": world * args.steps * s / t_res, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps,
-            "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 (8-limb 256-bit Montgomery)",
             "data": "synthetic",
             "config": {"workload": "Lasso XOR subtable, C=4, M=2^16, 2^%d lookups per GPU, G=curve25519: commit + prove "
-                                   "(densify in e2e); proof bit-exact vs CPU oracle" % log_s,
+                                   "(densify in e2e)" % log_s,
                        "l2": "inputs larger than L2 (>= 128 MiB per polynomial set)",
-                       "parallelism": ("ONE proof sharded over %d GPUs by the low index bits: NCCL all-gather of the partial "
-                                       "sums per sumcheck round + gather-then-add of partial MSM points" % world) if sharded
-                       else "independent proof per GPU (weak scaling, no data-path collective)",
-                       "proof_bytes": proof_bytes, "commitment_bytes": com_bytes, "wall_s_resident": wall},
-            "e2e": {"value": (1 if sharded else world) * args.steps * s / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": proof_bytes + com_bytes, "ms_per_step": 1e3 * t_e2e / args.steps},
+                       "parallelism": "independent proof per GPU (weak scaling, no data-path collective); the `configs` block "
+                                      "holds ONE proof per BASELINE configuration, sharded over the GPUs when N > 1",
+                       "proof_bytes": proof_bytes, "commitment_bytes": com_bytes, "wall_s_resident": wall,
+                       "proof_sha256": proof_sha,
+                       "golden_match": bool(g20 and g20["proof_sha256"] == proof_sha) if g20 else None,
+                       "golden": "tests/golden/big_proofs.json (CPU oracle, verifier accepted), rank 0's inputs",
+                       "setup_ms": round(setup_ms, 1), "tables_gb": round(tables_gb, 2),
+                       "setup": "SparsePolyCommitmentGens.new equivalent: generator stream -> window table + digit-multiples "
+                                "tables, outside the timed region like the reference's gens (bench.rs:54-57)",
+                       "no_tables": no_tables, "numa_node": numa_node},
+            "e2e": {"value": world * args.steps * s / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": proof_bytes + com_bytes, "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "densify_ms_per_step": dens_ms / args.steps},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"kernel": "bind_top_kernel (K1)", "bound": "hbm", "achieved": achieved, "peak": peak,
@@ -331,20 +453,23 @@ def main():
                          "traffic": 966613504,
                          "peak_source": peak_src, "ms_per_launch": ms,
                          "alg_bytes_per_launch": alg_bytes},
+            "configs": config_rows,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
-                log_ss = 18
                 nthreads, ncpu = best_threads()
-                ol, cidx, cr, cseed, cgens, cores = cpu_sample(log_ss, C, log_m, threads=nthreads)
+                ol, cidx, cr, cseed, cgens = cpu_workload(log_s, C, log_m)
+                cores = ol.lib().orc_num_threads()
                 ol.prove(KIND_XOR, C, log_m, 0, cidx, cr, cgens, cseed, flags=0)  # warm-up
                 t0 = time.perf_counter()
                 res = ol.prove(KIND_XOR, C, log_m, 0, cidx, cr, cgens, cseed, flags=0)
                 dt = time.perf_counter() - t0
-                line["cpu_baseline"] = {"value": (1 << log_ss) / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                                        "sample": "XOR C=4 M=2^16, 2^%d lookups, densify+commit+prove, 1 timed run after "
-                                                  "1 warm-up (oracle C++/OpenMP port; not the Rust binary); OpenMP team = "
-                                                  "fastest of a probe (%d of %d logical CPUs)" % (log_ss, nthreads, ncpu),
+                line["cpu_baseline"] = {"value": (1 << log_s) / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                        "sample": "the whole workload: XOR C=4 M=2^16, 2^%d lookups, same inputs as the GPU arm, "
+                                                  "densify+commit+prove, 1 timed run after 1 warm-up (oracle C++/OpenMP port; not "
+                                                  "the Rust binary); OpenMP team = fastest of a probe (%d of %d logical CPUs)"
+                                                  % (log_s, nthreads, ncpu),
+                                        "same_bytes_as_gpu": bool(res["proof"] == proof0.bytes),
                                         "spans_ms": {k: round(v, 1) for k, v in res["spans"].items()}}
             except Exception as e:  # the checker failing must not hide the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": "failed: %r" % e}

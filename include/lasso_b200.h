@@ -50,14 +50,21 @@ const char* lasso_last_error(void);
 int lasso_ctx_create(lasso_ctx** out, int device_id);
 void lasso_ctx_destroy(lasso_ctx* ctx);
 
-/* One proof sharded over `world` GPUs (one process per GPU, world a power of two): rank 0 obtains an id with
- * lasso_comm_unique_id, every rank receives it out of band (e.g. torch.distributed broadcast) and calls
- * lasso_ctx_init_comm before any other call.  Afterwards lasso_densify / lasso_commit / lasso_prove are
- * collective: every rank passes the SAME arguments, holds the low-index-bit shard of every polynomial, and
- * receives the same (bit-identical to single-GPU) commitment and proof bytes.  Exchanges: one small all-gather
- * per sumcheck round and one gather-then-add of partial points per row-MSM (NCCL over NVLink). */
+/* One proof sharded over `world` ranks of ONE node (one process per GPU, world a power of two <= 8; several ranks
+ * may also share a GPU): rank 0 obtains an id with lasso_comm_unique_id, every rank receives it out of band (e.g.
+ * torch.distributed broadcast) and calls lasso_ctx_init_comm before any other call.  Afterwards lasso_densify /
+ * lasso_commit / lasso_prove are collective: every rank passes the SAME arguments, holds the low-index-bit shard
+ * of every polynomial, and receives the same (bit-identical to single-GPU) commitment and proof bytes.
+ * Exchanges: per sumcheck round every GPU stores its three partial sums into the shared
+ * pinned host segment of every process (no collective, no extra launch); the few bulk hand-overs (partial points
+ * of a row-MSM, heads of the polynomials, the LZ vector of an opening) are all-gathers written as one kernel of
+ * peer-memory stores over NVLink (CUDA IPC), or ncclAllGather under LASSO_B200_XCHG=nccl. */
 int lasso_comm_unique_id(uint8_t out[128]);
 int lasso_ctx_init_comm(lasso_ctx*, const uint8_t id[128], int rank, int world);
+/* Optional: bind the calling process's host threads (Fiat-Shamir transcript, timestamp scan, pinned staging) to the
+ * CPUs of the NUMA node the context's GPU hangs off (sysfs).  Returns the node id, or -1 if it is not exposed.
+ * With one process per GPU on a two-socket node this keeps the per-proof host work and its pinned buffers local. */
+int lasso_ctx_bind_host_threads(lasso_ctx*);
 
 /* ---------------------------------------------------------------- per-loop entry points (host buffers) */
 

@@ -106,23 +106,27 @@ class Context:
             pass
 
     def init_comm(self, rank=None, world=None):
-        """Shard ONE proof over the GPUs of a torch.distributed job (one process per GPU, world a power of two).
-        The NCCL id is created on rank 0 and broadcast through torch.distributed (any backend)."""
-        import torch
+        """Shard ONE proof over the ranks of a torch.distributed job (one process per GPU, world a power of two
+        <= 8, one node).  The 128-byte job id (random bytes naming the job's shared host segments, or the NCCL
+        unique id under LASSO_B200_XCHG=nccl) is created on rank 0 and broadcast through torch.distributed
+        (any backend).  Collective: every rank must call it."""
         import torch.distributed as dist
+
+        from . import parallel
 
         rank = dist.get_rank() if rank is None else rank
         world = dist.get_world_size() if world is None else world
         ident = np.zeros(128, dtype=np.uint8)
         if rank == 0:
             _chk(lib().lasso_comm_unique_id(_p(ident)))
-        t = torch.from_numpy(ident)
-        if dist.get_backend() == "nccl":
-            t = t.cuda()
-        dist.broadcast(t, src=0)
-        ident = np.ascontiguousarray(t.cpu().numpy())
+        ident = np.frombuffer(parallel.broadcast_bytes(ident.tobytes(), src=0), dtype=np.uint8).copy()
         _chk(lib().lasso_ctx_init_comm(self._h, _p(ident), int(rank), int(world)))
         self.rank, self.world = rank, world
+
+    def bind_host_threads(self):
+        """Pin this process's host threads (transcript, timestamp scan, staging) to the NUMA node of the
+        context's GPU; returns the node id or -1 when the topology is not exposed."""
+        return int(lib().lasso_ctx_bind_host_threads(self._h))
 
     @property
     def launches(self):

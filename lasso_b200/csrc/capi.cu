@@ -22,6 +22,12 @@ static int fail(int code, const std::string& msg) {
   return code;
 }
 #define LB_TRY try {
+// every entry point that takes a context makes the context's device current first: a process may hold contexts on
+// several GPUs, and kernel launches / allocations go to the CURRENT device
+#define LB_TRY_CTX(h) \
+  try {               \
+    if (!(h) || !(h)->c) return fail(-1, "null context"); \
+    LB_CUDA_CHECK(cudaSetDevice((h)->c->device));
 #define LB_CATCH                                  \
   }                                               \
   catch (const std::exception& e) {               \
@@ -45,7 +51,10 @@ int lasso_ctx_create(lasso_ctx** out, int device_id) {
 }
 void lasso_ctx_destroy(lasso_ctx* ctx) {
   if (!ctx) return;
-  comm_destroy(ctx->c);
+  try {
+    comm_destroy(ctx->c);
+  } catch (...) {
+  }
   ctx_destroy(ctx->c);
   delete ctx;
 }
@@ -56,14 +65,19 @@ int lasso_comm_unique_id(uint8_t out[128]) {
   LB_CATCH
 }
 int lasso_ctx_init_comm(lasso_ctx* h, const uint8_t id[128], int rank, int world) {
-  LB_TRY
+  LB_TRY_CTX(h)
   comm_init(h->c, id, rank, world);
   return 0;
   LB_CATCH
 }
 
+int lasso_ctx_bind_host_threads(lasso_ctx* h) {
+  if (!h || !h->c) return -1;
+  return bind_host_threads(h->c->device);
+}
+
 int lasso_bind_top(lasso_ctx* h, uint64_t* Z, size_t len, const uint64_t r[4]) {
-  LB_TRY
+  LB_TRY_CTX(h)
   if (!is_pow2(len) || len < 2) return fail(LASSO_ERR_NOT_POW2, "bind_top: len must be a power of two >= 2");
   Ctx* c = h->c;
   DBuf<fr_t> d(c, len);
@@ -78,7 +92,7 @@ int lasso_bind_top(lasso_ctx* h, uint64_t* Z, size_t len, const uint64_t r[4]) {
   LB_CATCH
 }
 int lasso_bind_bot(lasso_ctx* h, uint64_t* Z, size_t len, const uint64_t r[4]) {
-  LB_TRY
+  LB_TRY_CTX(h)
   if (!is_pow2(len) || len < 2) return fail(LASSO_ERR_NOT_POW2, "bind_bot: len must be a power of two >= 2");
   Ctx* c = h->c;
   DBuf<fr_t> d(c, len), o(c, len / 2);
@@ -93,7 +107,7 @@ int lasso_bind_bot(lasso_ctx* h, uint64_t* Z, size_t len, const uint64_t r[4]) {
   LB_CATCH
 }
 int lasso_eq_evals(lasso_ctx* h, const uint64_t* r, int ell, uint64_t* out) {
-  LB_TRY
+  LB_TRY_CTX(h)
   if (ell < 0 || ell > 28) return fail(LASSO_ERR_LENGTH, "eq_evals: 0 <= ell <= 28");
   Ctx* c = h->c;
   FrVec rv;
@@ -109,7 +123,7 @@ int lasso_eq_evals(lasso_ctx* h, const uint64_t* r, int ell, uint64_t* out) {
 }
 int lasso_sumcheck_round_arbitrary(lasso_ctx* h, int strategy, int C, int log_M, int log_R,
                                    const uint64_t* const* polys, size_t len, uint64_t* evals_out) {
-  LB_TRY
+  LB_TRY_CTX(h)
   Strategy S = mkS(strategy, C, log_M, log_R);
   if (!S.valid()) return fail(LASSO_ERR_STRATEGY, "unsupported strategy parameters");
   if (!is_pow2(len) || len < 2) return fail(LASSO_ERR_NOT_POW2, "len must be a power of two >= 2");
@@ -119,7 +133,7 @@ int lasso_sumcheck_round_arbitrary(lasso_ctx* h, int strategy, int C, int log_M,
   for (int k = 0; k < np; k++)
     LB_CUDA_CHECK(cudaMemcpyAsync(d.p + (size_t)k * len, polys[k], len * 32, cudaMemcpyHostToDevice, c->st));
   Finalize f = c->fin_begin();
-  f.mapped = nullptr;  // plain device result + copy on this entry point
+  f.pub.ndst = 0;  // plain device result + copy on this entry point
   launch_sumcheck_eval_arbitrary(S, d.p, len, len / 2, f, c->st);
   g_launches += 1;
   c->d2h(evals_out, c->d_small, (size_t)npts * 32);
@@ -128,7 +142,7 @@ int lasso_sumcheck_round_arbitrary(lasso_ctx* h, int strategy, int C, int log_M,
 }
 int lasso_sumcheck_round_cubic(lasso_ctx* h, int n_circuits, const uint64_t* const* A, const uint64_t* const* B,
                                const uint64_t* Ceq, size_t len, uint64_t* out) {
-  LB_TRY
+  LB_TRY_CTX(h)
   if (!is_pow2(len) || len < 2) return fail(LASSO_ERR_NOT_POW2, "len must be a power of two >= 2");
   if (n_circuits < 1 || n_circuits > 512) return fail(LASSO_ERR_LENGTH, "1 <= n_circuits <= 512");
   Ctx* c = h->c;
@@ -145,7 +159,7 @@ int lasso_sumcheck_round_cubic(lasso_ctx* h, int n_circuits, const uint64_t* con
   LB_CUDA_CHECK(cudaMemcpyAsync(pA.p, hA.data(), n_circuits * sizeof(fr_t*), cudaMemcpyHostToDevice, c->st));
   LB_CUDA_CHECK(cudaMemcpyAsync(pB.p, hB.data(), n_circuits * sizeof(fr_t*), cudaMemcpyHostToDevice, c->st));
   Finalize f = c->fin_begin();
-  f.mapped = nullptr;
+  f.pub.ndst = 0;
   launch_sumcheck_eval_cubic(pA.p, pB.p, dC.p, n_circuits, len / 2, f, c->st);
   g_launches += 1;
   c->d2h(out, c->d_small, (size_t)n_circuits * 3 * 32);
@@ -153,7 +167,7 @@ int lasso_sumcheck_round_cubic(lasso_ctx* h, int n_circuits, const uint64_t* con
   LB_CATCH
 }
 int lasso_materialize_subtables(lasso_ctx* h, int strategy, int C, int log_M, int log_R, uint64_t* const* tables_out) {
-  LB_TRY
+  LB_TRY_CTX(h)
   Strategy S = mkS(strategy, C, log_M, log_R);
   if (!S.valid()) return fail(LASSO_ERR_STRATEGY, "unsupported strategy parameters");
   Ctx* c = h->c;
@@ -169,7 +183,7 @@ int lasso_materialize_subtables(lasso_ctx* h, int strategy, int C, int log_M, in
 }
 int lasso_gather_lookup_polys(lasso_ctx* h, int strategy, int C, int log_M, int log_R, const uint64_t* const* nz,
                               size_t s, uint64_t* const* E_out) {
-  LB_TRY
+  LB_TRY_CTX(h)
   Strategy S = mkS(strategy, C, log_M, log_R);
   if (!S.valid()) return fail(LASSO_ERR_STRATEGY, "unsupported strategy parameters");
   Ctx* c = h->c;
@@ -229,7 +243,7 @@ static void msm_variable_base(Ctx* c, const uint64_t* bases_affine, size_t nbase
   c->sync();
 }
 int lasso_msm(lasso_ctx* h, const uint64_t* bases_affine, const uint64_t* scalars, size_t n, uint64_t out_xytz[16]) {
-  LB_TRY
+  LB_TRY_CTX(h)
   if (n == 0 || n > (1u << 30)) return fail(LASSO_ERR_LENGTH, "msm: 1 <= n <= 2^30");
   msm_variable_base(h->c, bases_affine, n, scalars, 1, n, out_xytz);
   return 0;
@@ -237,7 +251,7 @@ int lasso_msm(lasso_ctx* h, const uint64_t* bases_affine, const uint64_t* scalar
 }
 int lasso_commit_rows(lasso_ctx* h, const uint64_t* gens_affine, const uint64_t* Z, size_t L_size, size_t R_size,
                       uint64_t* out_points) {
-  LB_TRY
+  LB_TRY_CTX(h)
   if (!L_size || !R_size) return fail(LASSO_ERR_LENGTH, "commit_rows: empty matrix");
   // blind = 0 on this path, so the trailing generator h contributes nothing (commitments.rs:89-92)
   msm_variable_base(h->c, gens_affine, R_size, Z, L_size, R_size, out_points);
@@ -256,7 +270,7 @@ int lasso_sample_generators(const char* label, size_t count, uint64_t* out_affin
 }
 int lasso_gens_create(lasso_ctx* h, const uint64_t* stream_affine, size_t n_points, size_t c, size_t s,
                       size_t num_memories, size_t log_m, lasso_gens** out) {
-  LB_TRY
+  LB_TRY_CTX(h)
   *out = nullptr;
   if (!is_pow2(s)) return fail(LASSO_ERR_NOT_POW2, "s must be a power of two");
   Gens* g = gens_create(h->c, stream_affine, n_points, c, s, num_memories, log_m);
@@ -272,7 +286,7 @@ void lasso_gens_destroy(lasso_gens* g) {
 }
 
 int lasso_densify(lasso_ctx* h, const uint64_t* indices, size_t n_lookups, size_t C, size_t log_m, lasso_dense** out) {
-  LB_TRY
+  LB_TRY_CTX(h)
   *out = nullptr;
   auto t0 = std::chrono::steady_clock::now();
   int err = 0;
@@ -293,6 +307,11 @@ size_t lasso_dense_read(lasso_ctx* h, const lasso_dense* dd, int which, uint64_t
   try {
     const Dense& d = *dd->d;
     Ctx* c = h->c;
+    LB_CUDA_CHECK(cudaSetDevice(c->device));
+    if (c->world > 1) {  // the arrays hold this rank's low-bit shard only: the field views below do not apply
+      g_err = "lasso_dense_read is not available on a sharded context";
+      return 0;
+    }
     size_t n = 0;
     if (which == 0) {
       n = d.C * d.s;
@@ -321,7 +340,7 @@ size_t lasso_dense_read(lasso_ctx* h, const lasso_dense* dd, int which, uint64_t
 }
 
 int lasso_commit(lasso_ctx* h, const lasso_dense* d, const lasso_gens* g, uint8_t* out, size_t cap, size_t* out_len) {
-  LB_TRY
+  LB_TRY_CTX(h)
   auto t0 = std::chrono::steady_clock::now();
   std::vector<uint8_t> b = commit(h->c, *d->d, *g->g);
   h->c->t_commit_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -336,7 +355,7 @@ int lasso_prove(lasso_ctx* h, int strategy, int log_R, lasso_dense* d, const uin
                 const lasso_gens* g, const char* transcript_label, const char* tape_label, const uint64_t tape_seed[4],
                 uint8_t* proof_out, size_t proof_cap, size_t* proof_len, uint64_t* challenges_out,
                 size_t challenges_cap, size_t* n_challenges) {
-  LB_TRY
+  LB_TRY_CTX(h)
   Strategy S = mkS(strategy, (int)d->d->C, (int)d->d->log_m, log_R);
   if (!S.valid()) return fail(LASSO_ERR_STRATEGY, "unsupported strategy parameters");
   // assert_eq!(r.len(), log2(dense.s))  surge.rs:131
@@ -365,7 +384,7 @@ int lasso_prove(lasso_ctx* h, int strategy, int log_R, lasso_dense* d, const uin
   LB_CATCH
 }
 
-unsigned long long lasso_launch_count(const lasso_ctx*) { return g_launches; }
+unsigned long long lasso_launch_count(const lasso_ctx*) { return g_launches.load(); }
 void lasso_last_timings(const lasso_ctx* h, double out_ms[3]) {
   out_ms[0] = h->c->t_densify_ms;
   out_ms[1] = h->c->t_commit_ms;
@@ -384,7 +403,7 @@ size_t lasso_spans(const lasso_ctx* h, char* buf, size_t cap) {
 }
 
 int lasso_bench_bind(lasso_ctx* h, size_t len, int npolys, int iters, double* avg_ms) {
-  LB_TRY
+  LB_TRY_CTX(h)
   if (!is_pow2(len) || len < 2 || npolys < 1) return fail(LASSO_ERR_NOT_POW2, "bench_bind: bad shape");
   Ctx* c = h->c;
   DBuf<fr_t> d(c, len * npolys);

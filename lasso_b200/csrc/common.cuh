@@ -19,6 +19,10 @@ namespace lb {
                                std::to_string(__LINE__));                                             \
   } while (0)
 
+// after every kernel launch: a bad configuration (shared memory opt-in missing on this device, grid too large)
+// fails synchronously and must not go unnoticed
+#define LB_LAUNCH_CHECK() LB_CUDA_CHECK(cudaGetLastError())
+
 static constexpr int kNumSMs = 148;  // B200
 
 #if defined(__CUDACC__)
@@ -99,16 +103,49 @@ __device__ __forceinline__ void block_sum_fr(fr_t (&v)[NV], fr_t* scratch) {
 // host is spinning on.  One kernel per sumcheck round instead of eval + reduce + copy: the rounds of the
 // grand-product ladder are pure launch/sync latency.
 //
-// Publication needs no flag and no system-scope fence (each costs microseconds per round): an Fr element is
-// < 2^253, so bits 29..31 of its last word are free.  Every published element carries a 3-bit tag there and
-// travels as ONE 32-byte store; the host waits until all `count` elements show the tag of this round, strips
-// it, and clears the slots (prover.cu Ctx::fin_wait).  Ordering between elements is irrelevant.
+// Publication needs no flag and no system-scope fence (each costs microseconds per round) and makes NO
+// assumption about the atomicity of wide stores: a published value x < 2^255 (an Fr residue or a canonical
+// Fq coordinate) travels as FIVE 64-bit words, word k = bits [51k, 51k+51) of x in its low 51 bits and a
+// 13-bit message tag in its high bits.  Aligned 64-bit stores are single-copy atomic in the PTX memory model,
+// so every word identifies the message it belongs to on its own: the host polls each of the five words for the
+// tag of the message it waits for, reassembles x, and zeroes the slot (a cleared word can never satisfy a later
+// wait).  Order between words or elements is irrelevant; a word of an older message is simply not accepted.
+// One proof sharded over G GPUs uses the same mechanism as its per-round exchange: every process maps every
+// other process's receive buffer (a shared pinned host segment, comm.cu) and each GPU stores its partial sums
+// into all G of them — the G replicated host transcripts add the G residues, no collective, no extra launch.
+static constexpr int kPubSlotWords = 8;       // 64 B per element slot (5 words used): never straddles a line
+static constexpr int kPubMaxReaders = 8;      // one node
+static constexpr int kPubRegions = 4;         // ring of regions per writer: consecutive messages never share one
+static constexpr int kPubElems = 512;         // elements per region (largest message: 8 * alpha tree tops)
+static constexpr uint32_t kPubTagMod = 8191;  // tags 1..8191 (13 bits, 0 = empty)
+struct PubDst {
+  unsigned long long* dst[kPubMaxReaders];  // device pointers: (this writer, region) inside reader p's buffer
+  int ndst;                                 // 0: no publication
+  uint32_t tag;
+  // host-side bookkeeping of the wait (ignored by kernels)
+  int region, all;
+};
+// x = 8 x u32 little-endian, x < 2^255
+__device__ __forceinline__ void pub_store(const PubDst& p, int v, const uint32_t x[8]) {
+  const unsigned long long q0 = x[0] | ((unsigned long long)x[1] << 32), q1 = x[2] | ((unsigned long long)x[3] << 32),
+                           q2 = x[4] | ((unsigned long long)x[5] << 32), q3 = x[6] | ((unsigned long long)x[7] << 32);
+  const unsigned long long M = (1ull << 51) - 1, T = (unsigned long long)p.tag << 51;
+  const unsigned long long w0 = (q0 & M) | T, w1 = (((q0 >> 51) | (q1 << 13)) & M) | T,
+                           w2 = (((q1 >> 38) | (q2 << 26)) & M) | T, w3 = (((q2 >> 25) | (q3 << 39)) & M) | T,
+                           w4 = (q3 >> 12) | T;
+#pragma unroll 1
+  for (int d = 0; d < p.ndst; d++) {
+    unsigned long long* s = p.dst[d] + (size_t)v * kPubSlotWords;
+    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(s), "l"(w0), "l"(w1) : "memory");
+    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(s + 2), "l"(w2), "l"(w3) : "memory");
+    asm volatile("st.global.u64 [%0], %1;" ::"l"(s + 4), "l"(w4) : "memory");
+  }
+}
 struct Finalize {
   fr_t* partial;      // scratch: [nvals][blocks_per_val]
   unsigned* counter;  // device ticket counter: 0 on entry, reset to 0 by the last CTA
   fr_t* out_dev;      // nvals results (always written, untagged)
-  uint32_t* mapped;   // optional mapped host buffer: element v at words [8v, 8v+8), tagged
-  uint32_t tag;       // 1..7
+  PubDst pub;         // optional publication to mapped host memory
 };
 __device__ __forceinline__ fr_t ld_fr_cg(const fr_t* p) {  // bypass L1: written by other CTAs of this launch
   fr_t r;
@@ -121,11 +158,7 @@ __device__ __forceinline__ fr_t ld_fr_cg(const fr_t* p) {  // bypass L1: written
 // result v of a round: device copy + tagged host copy
 __device__ __forceinline__ void finalize_publish(const Finalize& f, int v, const fr_t& val) {
   f.out_dev[v] = val;
-  if (f.mapped) {
-    fr_t t = val;
-    t.v[7] |= f.tag << 29;
-    st_fr((fr_t*)f.mapped + v, t);
-  }
+  if (f.pub.ndst) pub_store(f.pub, v, val.v);
 }
 // the LAST CTA of a launch (all threads): add the partials of every value and publish
 __device__ __forceinline__ void finalize_last_stage(const Finalize& f, int blocks_per_val, int nvals_total) {

@@ -87,6 +87,11 @@ __global__ void __launch_bounds__(32)
   }
 }
 
+// function attributes are per device: called from ctx_create for the context's device
+void densify_init_device() {
+  LB_CUDA_CHECK(cudaFuncSetAttribute(chunk_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  LB_CUDA_CHECK(cudaFuncSetAttribute(rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+}
 bool densify_gpu_supported(size_t s, size_t log_m) { return log_m <= 16 && s >= 32; }
 size_t densify_chunk(size_t s) {
   size_t B = s / 512;
@@ -101,18 +106,13 @@ int launch_densify_dim(const uint32_t* d_idx, size_t n, size_t s, int C, int dim
   const uint32_t m = 1u << log_m;
   const size_t B = densify_chunk(s), nchunks = s / B;
   const size_t smem = (size_t)((m + 1) / 2) * 4;
-  static bool attr = false;
-  if (!attr) {
-    LB_CUDA_CHECK(cudaFuncSetAttribute(chunk_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    LB_CUDA_CHECK(cudaFuncSetAttribute(rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr = true;
-  }
   size_t eb = (s + 255) / 256;
   if (eb > (size_t)kNumSMs * 8) eb = kNumSMs * 8;
   extract_dim_kernel<<<(unsigned)eb, 256, 0, st>>>(d_idx, n, s, C, dim, d_addr);
   chunk_hist_kernel<<<(unsigned)nchunks, kDenseThreads, smem, st>>>(d_addr, B, m, d_P);
   col_scan_kernel<<<(m + 255) / 256, 256, 0, st>>>(d_P, nchunks, m, G, g, final_loc);
   rank_kernel<<<(unsigned)nchunks, 32, smem, st>>>(d_addr, B, m, d_P, G, g, dim_loc, read_loc);
+  LB_LAUNCH_CHECK();
   return 4;
 }
 

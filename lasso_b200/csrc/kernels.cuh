@@ -27,7 +27,13 @@ struct Strategy {
   }
   int memory_to_dimension_index(int i) const { return kind == STRAT_RANGE ? i : i / num_subtables(); }
   bool valid() const {
-    return kind >= 0 && kind <= 4 && C >= 1 && C <= 16 && log_m >= 2 && log_m <= 24 && (log_m % 2 == 0 || kind == STRAT_RANGE);
+    if (!(kind >= 0 && kind <= 4 && C >= 1 && C <= 16 && log_m >= 2 && log_m <= 24 && (log_m % 2 == 0 || kind == STRAT_RANGE)))
+      return false;
+    // combine_lookups weights are F::from(1u64 << (i * inc)) (and.rs:45-53, range_check.rs:78-86): the shift must
+    // stay below 64 (the debug-build reference panics on overflow); RangeCheck<LOG_R> needs LOG_R >= 0
+    if (kind != STRAT_LT && (num_memories() - 1) * (kind == STRAT_RANGE ? log_m : log_m / 2) >= 64) return false;
+    if (kind == STRAT_RANGE && log_r < 0) return false;
+    return true;
   }
 };
 
@@ -107,7 +113,8 @@ void launch_product_layer(const fr_t* in, fr_t* out, size_t n_out, cudaStream_t 
 struct TreePtrs {
   fr_t* p[32];
 };
-void launch_product_trees(const TreePtrs& trees, int ntrees, size_t N, int slot0, const Finalize& fin, cudaStream_t st);
+void launch_product_trees(const TreePtrs& trees, int ntrees, size_t N, int slot0, int stop_len, const Finalize& fin,
+                          cudaStream_t st);
 int product_trees_launches(size_t N);
 // x_k[0] <- x_k[0] + r (x_k[1] - x_k[0]) for the n arrays x_k = d_AB[k]; results also published (Finalize)
 void launch_bind_heads(fr_t* const* d_AB, int n, const fr_t& r, const Finalize& fin, cudaStream_t st);
@@ -130,6 +137,7 @@ void launch_scale_strided(const fr_t* in, fr_t* out, size_t n, size_t stride, si
 void launch_scale(const fr_t* in, fr_t* out, size_t n, const fr_t& k, cudaStream_t st);
 
 // ---- densify on the GPU (densify_kernels.cu; densified.rs:33-56) ----
+void densify_init_device();
 bool densify_gpu_supported(size_t s, size_t log_m);
 size_t densify_chunk(size_t s);
 int launch_densify_dim(const uint32_t* d_idx, size_t n, size_t s, int C, int dim, size_t log_m, int G, int g,

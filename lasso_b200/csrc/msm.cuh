@@ -32,19 +32,23 @@ void launch_build_multiples(const pt_niels* T, size_t table_stride, size_t npts,
 // bucket-free MSM of nrows <= 8 short rows over M (msm_kernels.cu): scalars = nrows x len canonical integers,
 // cols = generator index per term (null: term k uses generator k); heavy_rows = how many of the rows carry
 // non-zero scalars (the CTAs per row are sized for those); partials: nrows x msm_direct_chunks(len, heavy_rows);
-// tagged: mapped pinned host memory; the rows arrive as TAGGED canonical coordinates — element 3*row + {0,1,2} =
-// X, Y, Z with bit 255 set, one 32-byte store each; the host waits for the tags and clears them (Ctx::wait_points)
+// pub: tagged publication to mapped pinned host memory (common.cuh PubDst) — element 3*row + {0,1,2} = canonical
+// X, Y, Z; the host waits for the message and clears it (Ctx::wait_points)
 int msm_direct_chunks(int len, int heavy_rows);
 void launch_msm_direct(const pt_niels* M, size_t npts, const uint32_t* scalars, const uint32_t* cols, int nrows, int len,
-                       int heavy_rows, pt_ext* partials, uint32_t* out_raw, uint32_t* tagged, cudaStream_t st);
+                       int heavy_rows, pt_ext* partials, uint32_t* out_raw, const PubDst& pub, cudaStream_t st);
 // Hyrax row commitments of integer-valued polynomials as direct sums over the multiples table (no buckets)
 // M16 (may be null): 16-bit multiples M16[j][d-1] = d * G_j, d = 1..32768, of the generators 0 .. ncols-1
-void launch_build_multiples16(const pt_niels* T, const pt_niels* M, size_t npts8, size_t ncols, pt_niels* M16, cudaStream_t st);
+// local column jl <-> generator jl * col_mul + col_add (one proof sharded over col_mul GPUs: this rank's columns)
+void launch_build_multiples16(const pt_niels* T, const pt_niels* M, size_t npts8, size_t ncols, size_t col_mul, size_t col_add,
+                              pt_niels* M16, cudaStream_t st);
 // K16 (with M16): the centring constant 2^15 * sum_{j < ncols} G_j for exactly this ncols (launch_centre_constant)
 void launch_centre_constant(const pt_niels* M16, int ncols, pt_ext* K16, cudaStream_t st);
+// M is indexed by generator (local column c -> c * col_mul + col_add), M16 / K16 by LOCAL column
 void launch_msm_rows_direct_u32(const pt_niels* M, size_t npts, const pt_niels* M16, const pt_ext* K16, const uint32_t* scalars,
-                                size_t row_stride, int nrows, int ncols, int nw, pt_ext* partials, fq_t* out_ext,
-                                uint32_t* out_comp, uint32_t* out_raw, cudaStream_t st);
+                                size_t row_stride, int nrows, int ncols, int nw, int col_mul, int col_add, pt_ext* partials,
+                                fq_t* out_ext, uint32_t* out_comp, uint32_t* out_raw, cudaStream_t st);
+void msm_init_device();
 void launch_combine_points(const fq_t* in_ext, int n, fq_t* out_ext, uint32_t* out_comp, cudaStream_t st);
 
 inline int msm_windows_for_bits(unsigned max_bits) {

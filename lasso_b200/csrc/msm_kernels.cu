@@ -88,6 +88,7 @@ void launch_build_table(const fq_t* bases_ark, size_t n, pt_niels* T, size_t str
   unsigned blocks = (unsigned)((n + 127) / 128);
   table_first_kernel<<<blocks, 128, 0, st>>>(bases_ark, n, T);
   for (int w = 1; w < nwindows; w++) table_next_kernel<<<blocks, 128, 0, st>>>(T, n, stride, w);
+  LB_LAUNCH_CHECK();
 }
 
 // ---------------------------------------------------------------- scalars
@@ -111,6 +112,7 @@ void launch_canonicalize(const fr_t* in, fr_t* out, size_t n, unsigned* d_max_bi
   if (b > (size_t)kNumSMs * 8) b = kNumSMs * 8;
   if (b == 0) return;
   canonicalize_kernel<<<(unsigned)b, 256, 0, st>>>(in, out, n, d_max_bits);
+  LB_LAUNCH_CHECK();
 }
 
 // signed digits (c = 8): byte w of (s + 0x80..80) minus 128.  MsmDigits biases the scalar once; digit(w) with a
@@ -508,10 +510,10 @@ __device__ __forceinline__ fq_t quad_add(unsigned mask, int lane, const fq_t& mi
 }
 // Finish for a handful of rows over a shifted table (the rounds of the opening proofs): ONE CTA, 32 quads
 // per row; each quad adds its share of the row's partials, then a 5-level tree through shared memory.
-// The result (X, Y, Z canonical) goes to mapped host memory, one tagged 32-byte store per coordinate (bit
-// 255 is free below q): no flag, no system fence (see common.cuh Finalize).
+// The result (X, Y, Z canonical) goes to mapped host memory as a tagged message (common.cuh PubDst): no flag,
+// no system fence.
 __global__ void __launch_bounds__(1024)
-    msm_finish_quad_kernel(const pt_ext* partials, int nrows, int P, uint32_t* out_raw, uint32_t* tagged) {
+    msm_finish_quad_kernel(const pt_ext* partials, int nrows, int P, uint32_t* out_raw, PubDst pub) {
   __shared__ fq_t sm_pt[8 * 32 * 4];
   const int tid = threadIdx.x, lane = tid & 31, role = tid & 3;
   const int row = tid >> 7, qr = (tid & 127) >> 2;  // blockDim = 128 * nrows
@@ -544,10 +546,9 @@ __global__ void __launch_bounds__(1024)
 #pragma unroll
       for (int l = 0; l < 8; l++) out_raw[(size_t)row * 32 + role * 8 + l] = mine.v[l];
     }
-    if (tagged) {
-      fq_t c = fq_canonical(mine);
-      c.v[7] |= 0x80000000u;
-      st_fq(reinterpret_cast<fq_t*>(tagged) + row * 3 + role, c);
+    if (pub.ndst) {  // canonical coordinate < 2^255: element 3*row + {0, 1, 2} of the tagged message
+      const fq_t c = fq_canonical(mine);
+      pub_store(pub, row * 3 + role, c.v);
     }
   }
 }
@@ -581,6 +582,7 @@ __global__ void __launch_bounds__(128)
 void launch_build_multiples(const pt_niels* T, size_t table_stride, size_t npts, int nwindows, pt_niels* M, cudaStream_t st) {
   const size_t n = (size_t)nwindows * npts;
   multiples_table_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(T, table_stride, npts, nwindows, M);
+  LB_LAUNCH_CHECK();
 }
 
 // 16-bit multiples of the COMMITMENT generators (the columns of the Hyrax matrices): M16[j][d-1] = d * G_j,
@@ -590,14 +592,15 @@ void launch_build_multiples(const pt_niels* T, size_t table_stride, size_t npts,
 // mixed additions; normalisation is batched 16 at a time (Montgomery's trick: 3 multiplications per point + one
 // inversion per batch).
 __global__ void __launch_bounds__(128)
-    multiples16_table_kernel(const pt_niels* T, const pt_niels* M, size_t npts8, size_t ncols, pt_niels* M16) {
+    multiples16_table_kernel(const pt_niels* T, const pt_niels* M, size_t npts8, size_t ncols, size_t col_mul, size_t col_add,
+                             pt_niels* M16) {
   const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= ncols * 128) return;
-  const size_t j = id >> 7;
+  const size_t jl = id >> 7, j = jl * col_mul + col_add;  // local column jl <-> generator j (sharded: this rank's columns)
   const int b = (int)(id & 127);
   const pt_niels base = ld_niels(T + j);  // window 0: G_j
   pt_ext acc = b == 0 ? pt_identity() : pt_from_niels(ld_niels(M + ((size_t)1 * npts8 + j) * 128 + (b - 1)));
-  pt_niels* out = M16 + j * 32768 + (size_t)256 * b;
+  pt_niels* out = M16 + jl * 32768 + (size_t)256 * b;
   for (int g = 0; g < 16; g++) {
     pt_ext pts[16];
     fq_t pref[16];
@@ -616,9 +619,11 @@ __global__ void __launch_bounds__(128)
     }
   }
 }
-void launch_build_multiples16(const pt_niels* T, const pt_niels* M, size_t npts8, size_t ncols, pt_niels* M16, cudaStream_t st) {
+void launch_build_multiples16(const pt_niels* T, const pt_niels* M, size_t npts8, size_t ncols, size_t col_mul, size_t col_add,
+                              pt_niels* M16, cudaStream_t st) {
   const size_t n = ncols * 128;
-  multiples16_table_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(T, M, npts8, ncols, M16);
+  multiples16_table_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(T, M, npts8, ncols, col_mul, col_add, M16);
+  LB_LAUNCH_CHECK();
 }
 
 // mixed quad addition: the quad's accumulator + one affine-niels entry; lane 0 / 1 / 3 hold the entry's
@@ -718,12 +723,14 @@ int msm_direct_chunks(int len, int heavy_rows) {
   return c | 1;
 }
 void launch_msm_direct(const pt_niels* M, size_t npts, const uint32_t* scalars, const uint32_t* cols, int nrows, int len,
-                       int heavy_rows, pt_ext* partials, uint32_t* out_raw, uint32_t* tagged, cudaStream_t st) {
+                       int heavy_rows, pt_ext* partials, uint32_t* out_raw, const PubDst& pub, cudaStream_t st) {
   if (nrows < 1 || nrows > 8) throw std::runtime_error("msm_direct: 1..8 rows");
   const int nchunks = msm_direct_chunks(len, heavy_rows);
   dim3 grid(nchunks, nrows);
   msm_direct_kernel<<<grid, MSMD_T, 0, st>>>(M, npts, scalars, cols, len, partials);
-  msm_finish_quad_kernel<<<1, 128 * nrows, 0, st>>>(partials, nrows, nchunks, out_raw, tagged);
+  LB_LAUNCH_CHECK();
+  msm_finish_quad_kernel<<<1, 128 * nrows, 0, st>>>(partials, nrows, nchunks, out_raw, pub);
+  LB_LAUNCH_CHECK();
 }
 
 // ---------------------------------------------------------------- Hyrax row commitments over the multiples table
@@ -733,7 +740,7 @@ void launch_msm_direct(const pt_niels* M, size_t npts, const uint32_t* scalars, 
 // thread-per-point arithmetic: with thousands of rows this kernel is throughput-bound, not latency-bound.
 __global__ void __launch_bounds__(MSM_T)
     msm_rows_direct_u32_kernel(const pt_niels* M, size_t npts, const pt_niels* M16, const pt_ext* K16, const uint32_t* scalars,
-                               size_t row_stride, int ncols, int nw, pt_ext* partials) {
+                               size_t row_stride, int ncols, int nw, int col_mul, int col_add, pt_ext* partials) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* buf = reinterpret_cast<uint32_t*>(smem_raw);  // SoA point storage, MSM_T points
   const int tid = threadIdx.x, row = blockIdx.x;
@@ -760,7 +767,7 @@ __global__ void __launch_bounds__(MSM_T)
         for (int w = 0; w < 3; w++) {
           const int d = (int)((br >> (8 * w)) & 0xff) - 128;
           if (d != 0) {
-            pt_niels n = ld_niels(M + ((size_t)(w + 2) * npts + c) * 128 + ((d < 0 ? -d : d) - 1));
+            pt_niels n = ld_niels(M + ((size_t)(w + 2) * npts + (size_t)c * col_mul + col_add) * 128 + ((d < 0 ? -d : d) - 1));
             acc = pt_madd(acc, d < 0 ? niels_neg(n) : n);
           }
         }
@@ -774,7 +781,7 @@ __global__ void __launch_bounds__(MSM_T)
       if (w < nw) {
         const int d = (int)((b >> (8 * w)) & 0xff) - 128;
         if (d != 0) {
-          const pt_niels* e = M + ((size_t)w * npts + c) * 128 + ((d < 0 ? -d : d) - 1);
+          const pt_niels* e = M + ((size_t)w * npts + (size_t)c * col_mul + col_add) * 128 + ((d < 0 ? -d : d) - 1);
           pt_niels n = ld_niels(e);
           acc = pt_madd(acc, d < 0 ? niels_neg(n) : n);
         }
@@ -835,19 +842,22 @@ __global__ void __launch_bounds__(MSM_T) centre_constant_kernel(const pt_niels* 
 }
 void launch_centre_constant(const pt_niels* M16, int ncols, pt_ext* K16, cudaStream_t st) {
   centre_constant_kernel<<<1, MSM_T, 32 * MSM_T * sizeof(uint32_t), st>>>(M16, ncols, K16);
+  LB_LAUNCH_CHECK();
 }
 void launch_msm_rows_direct_u32(const pt_niels* M, size_t npts, const pt_niels* M16, const pt_ext* K16, const uint32_t* scalars,
-                                size_t row_stride, int nrows, int ncols, int nw, pt_ext* partials, fq_t* out_ext,
-                                uint32_t* out_comp, uint32_t* out_raw, cudaStream_t st) {
+                                size_t row_stride, int nrows, int ncols, int nw, int col_mul, int col_add, pt_ext* partials,
+                                fq_t* out_ext, uint32_t* out_comp, uint32_t* out_raw, cudaStream_t st) {
   if (nrows <= 0) return;
   if (nw < 1) nw = 1;
   if (nw > 5) throw std::runtime_error("msm_rows_direct_u32: more than 5 windows");
   msm_rows_direct_u32_kernel<<<nrows, MSM_T, 32 * MSM_T * sizeof(uint32_t), st>>>(M, npts, M16, K16, scalars, row_stride,
-                                                                              ncols, nw, partials);
+                                                                              ncols, nw, col_mul, col_add, partials);
+  LB_LAUNCH_CHECK();
   if (out_raw)
     msm_finish_kernel<<<nrows, 32, 0, st>>>(partials, nrows, 1, 1, 1, out_ext, out_comp, out_raw);
   else
     normalize_rows_kernel<<<(nrows + 31) / 32, 32, 0, st>>>(partials, nrows, out_ext, out_comp);
+  LB_LAUNCH_CHECK();
 }
 
 // Launch geometry.  wpc = windows per CTA (all of them over a shifted table), ngroups = window groups,
@@ -883,6 +893,11 @@ size_t msm_partials_count(int nrows, int ncols, int nw) {  // upper bound over b
   return (size_t)nrows * (ca > cb ? ca : cb);
 }
 
+// function attributes are per device: called from ctx_create for the context's device
+void msm_init_device() {
+  LB_CUDA_CHECK(cudaFuncSetAttribute(msm_bucket_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MsmSmem)));
+  LB_CUDA_CHECK(cudaFuncSetAttribute(msm_bucket_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MsmSmem)));
+}
 void launch_msm_rows(const pt_niels* table, size_t table_stride, int shifted, const void* scalars, int scalar_limbs,
                      size_t row_stride, int nrows, int ncols, int nw, int col_mul, int col_add, pt_ext* partials,
                      fq_t* out_ext, uint32_t* out_comp, uint32_t* out_raw, cudaStream_t st) {
@@ -890,12 +905,7 @@ void launch_msm_rows(const pt_niels* table, size_t table_stride, int shifted, co
   if (nw < 1) nw = 1;
   const MsmGeom g = msm_geometry(nrows, ncols, nw, shifted);
   const int nchunks = g.nchunks, chunk_cols = g.chunk_cols;
-  static bool attr_set = false;
-  if (!attr_set) {
-    LB_CUDA_CHECK(cudaFuncSetAttribute(msm_bucket_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MsmSmem)));
-    LB_CUDA_CHECK(cudaFuncSetAttribute(msm_bucket_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MsmSmem)));
-    attr_set = true;
-  }
+  if (nchunks > 65535) throw std::runtime_error("msm_rows: too many column chunks for one launch");
   // gridDim.y is limited to 65535 rows per launch
   for (int r0 = 0; r0 < nrows; r0 += 65535) {
     int nr = nrows - r0 < 65535 ? nrows - r0 : 65535;
@@ -910,7 +920,9 @@ void launch_msm_rows(const pt_niels* table, size_t table_stride, int shifted, co
           table, table_stride, shifted, (const uint32_t*)scalars + (size_t)r0 * row_stride * 8, row_stride, ncols,
           chunk_cols, nw, g.wpc, col_mul, col_add, part);
   }
+  LB_LAUNCH_CHECK();
   msm_finish_kernel<<<nrows, 32, 0, st>>>(partials, nrows, g.ngroups, nchunks, shifted, out_ext, out_comp, out_raw);
+  LB_LAUNCH_CHECK();
 }
 
 // Cross-GPU "bucket-sum reduce": raw[(k * nrows + row) * 32 ..] = partial (X,Y,Z,T) of source k for `row`
@@ -963,6 +975,7 @@ __global__ void __launch_bounds__(64)
 void launch_sum_raw_points(const uint32_t* raw, int nsrc, int nrows, uint32_t* out_raw, uint32_t* out_comp, fq_t* out_ext,
                            cudaStream_t st) {
   sum_raw_points_kernel<<<(nrows + 63) / 64, 64, 0, st>>>(raw, nsrc, nrows, out_raw, out_comp, out_ext);
+  LB_LAUNCH_CHECK();
 }
 
 // sum of a few extended points + normalisation (used to add a blind*h term or combine rows)
@@ -993,6 +1006,7 @@ __global__ void combine_points_kernel(const fq_t* in_ext /*n x 4 ark*/, int n, f
 }
 void launch_combine_points(const fq_t* in_ext, int n, fq_t* out_ext, uint32_t* out_comp, cudaStream_t st) {
   combine_points_kernel<<<1, 32, 0, st>>>(in_ext, n, out_ext, out_comp);
+  LB_LAUNCH_CHECK();
 }
 
 }  // namespace lb

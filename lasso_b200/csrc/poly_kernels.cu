@@ -51,6 +51,7 @@ void launch_bind_top(fr_t* base, size_t stride, int npolys, size_t half, const f
   if (per < kNumSMs / 4) per = kNumSMs / 4;
   dim3 grid(grid_for(half, kThreads, per), npolys);
   bind_top_kernel<<<grid, kThreads, 0, st>>>(base, stride, half, r);
+  LB_LAUNCH_CHECK();
 }
 void launch_bind_top_ptrs(fr_t* const* d_ptrs, int npolys, size_t half, const fr_t& r, cudaStream_t st) {
   if (half == 0 || npolys == 0) return;
@@ -58,10 +59,12 @@ void launch_bind_top_ptrs(fr_t* const* d_ptrs, int npolys, size_t half, const fr
   if (per < kNumSMs / 4) per = kNumSMs / 4;
   dim3 grid(grid_for(half, kThreads, per), npolys);
   bind_top_ptrs_kernel<<<grid, kThreads, 0, st>>>(d_ptrs, half, r);
+  LB_LAUNCH_CHECK();
 }
 void launch_bind_bot(const fr_t* Z, fr_t* out, size_t half, const fr_t& r, cudaStream_t st) {
   if (half == 0) return;
   bind_bot_kernel<<<grid_for(half), kThreads, 0, st>>>(Z, out, half, r);
+  LB_LAUNCH_CHECK();
 }
 
 // ------------------------------------------------------------------------------------ K4
@@ -101,6 +104,7 @@ __global__ void __launch_bounds__(kThreads) eq_outer_kernel(const fr_t* t_hi, co
 void launch_eq_evals(const FrVec& r, int ell, fr_t* out, fr_t* scratch, cudaStream_t st) {
   if (ell <= 11) {
     eq_small_kernel<<<1, 1024, 0, st>>>(r, 0, ell, out);
+    LB_LAUNCH_CHECK();
     return;
   }
   int ell_lo = ell / 2 > 11 ? 11 : ell / 2;
@@ -111,15 +115,20 @@ void launch_eq_evals(const FrVec& r, int ell, fr_t* out, fr_t* scratch, cudaStre
     fr_t* hi_tab = out + (((size_t)1 << ell) - ((size_t)1 << ell_hi));
     launch_eq_evals(r, ell_hi, hi_tab, scratch, st);
     eq_small_kernel<<<1, 1024, 0, st>>>(r, ell_hi, ell_lo, scratch);
+    LB_LAUNCH_CHECK();
     cudaMemcpyAsync(scratch + 4096, hi_tab, sizeof(fr_t) << ell_hi, cudaMemcpyDeviceToDevice, st);
     size_t n = (size_t)1 << ell;
     eq_outer_kernel<<<grid_for(n), kThreads, 0, st>>>(scratch + 4096, scratch, ell_lo, n, out);
+    LB_LAUNCH_CHECK();
     return;
   }
   eq_small_kernel<<<1, 1024, 0, st>>>(r, 0, ell_hi, scratch);
+  LB_LAUNCH_CHECK();
   eq_small_kernel<<<1, 1024, 0, st>>>(r, ell_hi, ell_lo, scratch + 4096);
+  LB_LAUNCH_CHECK();
   size_t n = (size_t)1 << ell;
   eq_outer_kernel<<<grid_for(n), kThreads, 0, st>>>(scratch, scratch + 4096, ell_lo, n, out);
+  LB_LAUNCH_CHECK();
 }
 
 // ------------------------------------------------------------------------------------ partial-sum reduce
@@ -203,6 +212,68 @@ __global__ void __launch_bounds__(128)
   finalize_block<NP>(fin, acc, 0, blockIdx.x, gridDim.x, NP, gridDim.x);
 }
 
+// Any other C (the reference is generic in C, lt.rs:13-14): the C+2 evaluation points are processed TB at a time so
+// the live state stays in registers whatever C is; every pass re-reads the polynomials (a fallback, not a hot path).
+// tv.v[t] = F::from(t).
+template <int TB>
+__global__ void __launch_bounds__(128)
+    sc_eval_lt_generic_kernel(const fr_t* base, size_t stride, size_t half, int C, FrVec tv, Finalize fin) {
+  __shared__ fr_t scratch[TB * 128 / 32];
+  __shared__ fr_t res[32];
+  __shared__ int s_last;
+  const int NP = C + 2;
+  const fr_t* eq = base + (size_t)(2 * C) * stride;
+  for (int t0 = 0; t0 < NP; t0 += TB) {
+    fr_t acc[TB];
+#pragma unroll
+    for (int t = 0; t < TB; t++) acc[t] = fr_zero();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
+      fr_t h[TB];
+#pragma unroll
+      for (int t = 0; t < TB; t++) h[t] = fr_zero();
+#pragma unroll 1
+      for (int k = C - 1; k >= 0; k--) {
+        const fr_t* PL = base + (size_t)(2 * k) * stride;
+        const fr_t* PE = base + (size_t)(2 * k + 1) * stride;
+        const fr_t l0 = ld_fr(PL + i), l1 = ld_fr(PL + half + i), e0 = ld_fr(PE + i), e1 = ld_fr(PE + half + i);
+        const fr_t dl = fr_sub(l1, l0), de = fr_sub(e1, e0);
+        fr_t cl = fr_add(l0, fr_mul(tv.v[t0], dl)), ce = fr_add(e0, fr_mul(tv.v[t0], de));
+#pragma unroll
+        for (int t = 0; t < TB; t++) {
+          h[t] = fr_add(cl, fr_mul(ce, h[t]));
+          cl = fr_add(cl, dl);
+          ce = fr_add(ce, de);
+        }
+      }
+      const fr_t q0 = ld_fr(eq + i), q1 = ld_fr(eq + half + i), dq = fr_sub(q1, q0);
+      fr_t cq = fr_add(q0, fr_mul(tv.v[t0], dq));
+#pragma unroll
+      for (int t = 0; t < TB; t++) {
+        acc[t] = fr_add(acc[t], fr_mul(h[t], cq));
+        cq = fr_add(cq, dq);
+      }
+    }
+    block_sum_fr<TB>(acc, scratch);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int t = 0; t < TB; t++)
+        if (t0 + t < NP) res[t0 + t] = acc[t];
+    }
+    __syncthreads();
+  }
+  if (gridDim.x == 1) {
+    if ((int)threadIdx.x < NP) finalize_publish(fin, threadIdx.x, res[threadIdx.x]);
+    return;
+  }
+  if ((int)threadIdx.x < NP) fin.partial[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = res[threadIdx.x];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(fin.counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  finalize_last_stage(fin, gridDim.x, NP);
+}
+
 static FrVec linear_weights(const Strategy& S) {
   FrVec w;
   int inc = S.kind == STRAT_RANGE ? S.log_m : S.log_m / 2;
@@ -213,6 +284,7 @@ static FrVec linear_weights(const Strategy& S) {
 template <int C>
 static void launch_lt(const fr_t* base, size_t stride, size_t half, const Finalize& fin, int blocks, cudaStream_t st) {
   sc_eval_lt_kernel<C><<<blocks, 128, 0, st>>>(base, stride, half, fin);
+  LB_LAUNCH_CHECK();
 }
 
 void launch_sumcheck_eval_arbitrary(const Strategy& S, const fr_t* base, size_t stride, size_t half, const Finalize& fin,
@@ -226,11 +298,17 @@ void launch_sumcheck_eval_arbitrary(const Strategy& S, const fr_t* base, size_t 
       case 3: launch_lt<3>(base, stride, half, fin, blocks, st); break;
       case 4: launch_lt<4>(base, stride, half, fin, blocks, st); break;
       case 8: launch_lt<8>(base, stride, half, fin, blocks, st); break;
-      default: throw std::runtime_error("LT strategy: unsupported C (1,2,3,4,8 are built)");
+      default: {
+        FrVec tv;
+        for (int t = 0; t < 32; t++) tv.v[t] = fr_from_u64((uint64_t)t);
+        sc_eval_lt_generic_kernel<6><<<blocks, 128, 0, st>>>(base, stride, half, S.C, tv, fin);
+        LB_LAUNCH_CHECK();
+      }
     }
   } else {
     blocks = grid_for(half);
     sc_eval_linear_kernel<<<blocks, kThreads, 0, st>>>(base, stride, S.num_memories(), half, linear_weights(S), fin);
+    LB_LAUNCH_CHECK();
   }
 }
 
@@ -271,7 +349,9 @@ void launch_sumcheck_claim(const Strategy& S, const fr_t* base, size_t stride, s
     claim_lt_kernel<<<blocks, kThreads, 0, st>>>(base, stride, S.C, n, partial);
   else
     claim_linear_kernel<<<blocks, kThreads, 0, st>>>(base, stride, S.num_memories(), n, linear_weights(S), partial);
+  LB_LAUNCH_CHECK();
   reduce_partials_kernel<<<1, kThreads, 0, st>>>(partial, blocks, out);
+  LB_LAUNCH_CHECK();
 }
 
 // ------------------------------------------------------------------------------------ K3
@@ -509,9 +589,11 @@ static void launch_cubic_quad(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Ci
   if (threads <= 1024) {
     unsigned t = (unsigned)((threads + 31) / 32 * 32);
     sc_cubic_quad_kernel<<<1, t, 0, st>>>(d_A, d_B, Cin, Cout, q, lg_q, do_bind, r, ncirc, cf, scale, comb, fin);
+    LB_LAUNCH_CHECK();
   } else {
     unsigned blocks = (unsigned)(((size_t)ncirc * q + 63) / 64);
     sc_cubic_quad_kernel<<<blocks, 256, 0, st>>>(d_A, d_B, Cin, Cout, q, lg_q, do_bind, r, ncirc, cf, scale, comb, fin);
+    LB_LAUNCH_CHECK();
   }
 }
 // circuits are strided over blockIdx.y: enough CTAs for ~2 per SM even when a round has few pairs
@@ -527,12 +609,14 @@ void launch_sumcheck_bind_eval_cubic_comb(fr_t* const* d_A, fr_t* const* d_B, co
   size_t q = h / 2;
   if (q <= kQuadMaxQ && (q & (q - 1)) == 0) return launch_cubic_quad(d_A, d_B, Cin, Cout, ncirc, q, 1, r, cf, scale, 1, fin, st);
   sc_bind_eval_cubic_comb_kernel<<<comb_grid(q, ncirc), kThreads, 0, st>>>(d_A, d_B, Cin, Cout, h, r, ncirc, cf, scale, fin);
+  LB_LAUNCH_CHECK();
 }
 void launch_sumcheck_eval_cubic_comb(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Ceq, int ncirc, size_t half,
                                      const CubicCoeffs& cf, int scale, const Finalize& fin, cudaStream_t st) {
   if (half <= kQuadMaxQ && (half & (half - 1)) == 0)
     return launch_cubic_quad(d_A, d_B, Ceq, nullptr, ncirc, half, 0, fr_zero(), cf, scale, 1, fin, st);
   sc_eval_cubic_comb_kernel<<<comb_grid(half, ncirc), kThreads, 0, st>>>(d_A, d_B, Ceq, half, ncirc, cf, scale, fin);
+  LB_LAUNCH_CHECK();
 }
 // per-circuit outputs (e0, e2, e3)_k, no batching coefficients: the per-loop C-ABI entry lasso_sumcheck_round_cubic
 void launch_sumcheck_eval_cubic(fr_t* const* d_A, fr_t* const* d_B, const fr_t* Ceq, int ncirc, size_t half,
@@ -546,6 +630,7 @@ void launch_sumcheck_eval_cubic(fr_t* const* d_A, fr_t* const* d_B, const fr_t* 
   int bx = grid_for(half, kThreads, per);
   dim3 grid(bx, ncirc);
   sc_eval_cubic_kernel<<<grid, kThreads, 0, st>>>(d_A, d_B, Ceq, half, fin);
+  LB_LAUNCH_CHECK();
 }
 
 // ------------------------------------------------------------------------------------ K5
@@ -577,6 +662,7 @@ void launch_materialize_subtables(const Strategy& S, fr_t* tables_fr, uint32_t* 
   size_t n = (size_t)S.M() * S.num_subtables();
   materialize_kernel<<<grid_for(n), kThreads, 0, st>>>(S.kind, S.num_subtables(), S.log_m, S.log_r, tables_fr,
                                                        tables_u32);
+  LB_LAUNCH_CHECK();
 }
 struct GatherMap {
   int sub[32], dim[32];
@@ -604,6 +690,7 @@ void launch_gather_lookup_polys(const Strategy& S, const fr_t* tables_fr, const 
   }
   dim3 grid(grid_for(s, kThreads, kMaxBlocks / S.num_memories() + 1), S.num_memories());
   gather_kernel<<<grid, kThreads, 0, st>>>(map, S.log_m, tables_fr, tables_u32, nz, s, E_fr, E_stride, E_u32);
+  LB_LAUNCH_CHECK();
 }
 __global__ void __launch_bounds__(kThreads) from_u32_kernel(const uint32_t* in, fr_t* out, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -635,7 +722,9 @@ void launch_multi_dot(const fr_t* base, size_t stride, int npolys, const fr_t* e
   int bx = grid_for(n, kThreads, per);
   dim3 grid(bx, npolys);
   multi_dot_kernel<<<grid, kThreads, 0, st>>>(base, stride, eq, n, partial);
+  LB_LAUNCH_CHECK();
   reduce_partials_kernel<<<npolys, kThreads, 0, st>>>(partial, bx, out);
+  LB_LAUNCH_CHECK();
 }
 
 // dense_mlpoly.rs:183-207: LZ[i] = sum_j L[j] Z[j*R + i].  Thread = column (coalesced across the
@@ -665,7 +754,9 @@ void launch_bound(const fr_t* Z, const fr_t* L, size_t L_size, size_t R_size, fr
   size_t rows_per_chunk = (L_size + chunks - 1) / chunks;
   dim3 grid((unsigned)((R_size + kThreads - 1) / kThreads), chunks);
   bound_kernel<<<grid, kThreads, 0, st>>>(Z, L, L_size, R_size, rows_per_chunk, partial);
+  LB_LAUNCH_CHECK();
   bound_reduce_kernel<<<(unsigned)((R_size + kThreads - 1) / kThreads), kThreads, 0, st>>>(partial, chunks, R_size, out);
+  LB_LAUNCH_CHECK();
 }
 
 // memory_checking.rs:249-252: hash(a, v, t) = t*gamma^2 + v*gamma + a - tau
@@ -694,12 +785,14 @@ void launch_gp_fingerprints_mem(const fr_t* table, const fr_t* final_fr, size_t 
                                 const fr_t& gamma, const fr_t& tau, fr_t* out_init, fr_t* out_final, cudaStream_t st) {
   fp_mem_kernel<<<grid_for(M_local), kThreads, 0, st>>>(table, final_fr, M_local, G, g, gamma, fr_sqr(gamma), tau,
                                                         out_init, out_final);
+  LB_LAUNCH_CHECK();
 }
 void launch_gp_fingerprints_ops(const fr_t* dim_fr, const fr_t* E_fr, const fr_t* read_fr, size_t s,
                                 const fr_t& gamma, const fr_t& tau, fr_t* out_read, fr_t* out_write,
                                 cudaStream_t st) {
   fp_ops_kernel<<<grid_for(s), kThreads, 0, st>>>(dim_fr, E_fr, read_fr, s, gamma, fr_sqr(gamma), tau, out_read,
                                                   out_write);
+  LB_LAUNCH_CHECK();
 }
 // grand_product.rs:20-36 with the layer stored contiguously as [left | right]
 __global__ void __launch_bounds__(kThreads) product_layer_kernel(const fr_t* in, fr_t* out, size_t n_out) {
@@ -708,6 +801,7 @@ __global__ void __launch_bounds__(kThreads) product_layer_kernel(const fr_t* in,
 }
 void launch_product_layer(const fr_t* in, fr_t* out, size_t n_out, cudaStream_t st) {
   product_layer_kernel<<<grid_for(n_out), kThreads, 0, st>>>(in, out, n_out);
+  LB_LAUNCH_CHECK();
 }
 
 // All product trees of one size at once (single GPU).  A tree is one contiguous array: layer 0 (N elements),
@@ -715,15 +809,18 @@ void launch_product_layer(const fr_t* in, fr_t* out, size_t n_out, cudaStream_t 
 // tree (blockIdx.y) while the layers are large, then ONE CTA per tree walks the remaining small layers with
 // a barrier in between and publishes the two elements of the top layer (grand_product.rs:60-65 `evaluate`)
 // as tagged values 2*slot0 + 2*tree + {0, 1}: ~16 launches per proof instead of ~270 + 16 small copies.
+// stop_len = 2: a whole tree (single GPU).  stop_len = 1: the tree of a low-bit SHARD (N = local length) — the walk ends
+// with the rank's single element of the layer of global length G, published as value slot0 + tree.
 __global__ void __launch_bounds__(kThreads) product_layers_kernel(TreePtrs trees, size_t in_off, size_t n_out) {
   const fr_t* in = trees.p[blockIdx.y] + in_off;
   fr_t* out = trees.p[blockIdx.y] + in_off + 2 * n_out;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (size_t)gridDim.x * blockDim.x)
     st_fr(out + i, fr_mul(ld_fr(in + i), ld_fr(in + n_out + i)));
 }
-__global__ void __launch_bounds__(1024) product_tail_kernel(TreePtrs trees, size_t off, size_t len, int slot0, Finalize fin) {
+__global__ void __launch_bounds__(1024)
+    product_tail_kernel(TreePtrs trees, size_t off, size_t len, int slot0, int stop_len, Finalize fin) {
   fr_t* base = trees.p[blockIdx.x];
-  while (len > 2) {
+  while (len > (size_t)stop_len) {
     const size_t n_out = len / 2;
     for (size_t i = threadIdx.x; i < n_out; i += blockDim.x)
       st_fr(base + off + len + i, fr_mul(ld_fr(base + off + i), ld_fr(base + off + n_out + i)));
@@ -731,18 +828,22 @@ __global__ void __launch_bounds__(1024) product_tail_kernel(TreePtrs trees, size
     off += len;
     len = n_out;
   }
-  if (threadIdx.x < 2) finalize_publish(fin, 2 * (slot0 + (int)blockIdx.x) + (int)threadIdx.x, ld_fr(base + off + threadIdx.x));
+  if ((int)threadIdx.x < stop_len)
+    finalize_publish(fin, stop_len * (slot0 + (int)blockIdx.x) + (int)threadIdx.x, ld_fr(base + off + threadIdx.x));
 }
-void launch_product_trees(const TreePtrs& trees, int ntrees, size_t N, int slot0, const Finalize& fin, cudaStream_t st) {
+void launch_product_trees(const TreePtrs& trees, int ntrees, size_t N, int slot0, int stop_len, const Finalize& fin,
+                          cudaStream_t st) {
   size_t off = 0, len = N;
   while (len > 4096) {
     const size_t n_out = len / 2;
     dim3 grid(grid_for(n_out, kThreads, kMaxBlocks / ntrees + 1), ntrees);
     product_layers_kernel<<<grid, kThreads, 0, st>>>(trees, off, n_out);
+    LB_LAUNCH_CHECK();
     off += len;
     len = n_out;
   }
-  product_tail_kernel<<<ntrees, 1024, 0, st>>>(trees, off, len, slot0, fin);
+  product_tail_kernel<<<ntrees, 1024, 0, st>>>(trees, off, len, slot0, stop_len, fin);
+  LB_LAUNCH_CHECK();
 }
 int product_trees_launches(size_t N) {
   int n = 1;
@@ -762,6 +863,7 @@ __global__ void bind_heads_kernel(fr_t* const* AB, int n, fr_t r, Finalize fin) 
 }
 void launch_bind_heads(fr_t* const* d_AB, int n, const fr_t& r, const Finalize& fin, cudaStream_t st) {
   bind_heads_kernel<<<1, (n + 31) / 32 * 32, 0, st>>>(d_AB, n, r, fin);
+  LB_LAUNCH_CHECK();
 }
 
 // ---- Bulletproofs scalar-side helpers (bullet.rs:73-134) ----
@@ -774,6 +876,7 @@ __global__ void __launch_bounds__(kThreads) fold_ab_kernel(fr_t* a, fr_t* b, siz
 }
 void launch_fold_ab(fr_t* a, fr_t* b, size_t h, const fr_t& u, const fr_t& uinv, cudaStream_t st) {
   fold_ab_kernel<<<grid_for(h), kThreads, 0, st>>>(a, b, h, u, uinv);
+  LB_LAUNCH_CHECK();
 }
 __global__ void __launch_bounds__(kThreads) cross_ip_kernel(const fr_t* a, const fr_t* b, size_t h, fr_t* partial) {
   __shared__ fr_t scratch[2 * kThreads / 32];
@@ -791,7 +894,9 @@ __global__ void __launch_bounds__(kThreads) cross_ip_kernel(const fr_t* a, const
 void launch_cross_inner_products(const fr_t* a, const fr_t* b, size_t h, fr_t* partial, fr_t* out, cudaStream_t st) {
   int bx = grid_for(h, kThreads, 64);
   cross_ip_kernel<<<bx, kThreads, 0, st>>>(a, b, h, partial);
+  LB_LAUNCH_CHECK();
   reduce_partials_kernel<<<2, kThreads, 0, st>>>(partial, bx, out);
+  LB_LAUNCH_CHECK();
 }
 __global__ void __launch_bounds__(kThreads)
     expand_weights_kernel(const fr_t* w, fr_t* w_out, size_t n_in, fr_t u, fr_t uinv) {
@@ -803,6 +908,7 @@ __global__ void __launch_bounds__(kThreads)
 }
 void launch_expand_weights(const fr_t* w, fr_t* w_out, size_t n_in, const fr_t& u, const fr_t& uinv, cudaStream_t st) {
   expand_weights_kernel<<<grid_for(n_in), kThreads, 0, st>>>(w, w_out, n_in, u, uinv);
+  LB_LAUNCH_CHECK();
 }
 // Round with current vector length m (half h = m/2) over n original generators, weights w[t], t < n/m.
 // Global column j = t*m + pos:   sL[j] = a[pos-h] * w[t] for pos >= h (else 0),
@@ -832,6 +938,7 @@ __global__ void __launch_bounds__(kThreads)
 void launch_bullet_scalars(const fr_t* a, const fr_t* w, size_t n_loc, size_t m, int G, int g, int a_rep, fr_t* sL,
                            fr_t* sR, cudaStream_t st) {
   bullet_scalars_kernel<<<grid_for(n_loc), kThreads, 0, st>>>(a, w, n_loc, m, G, g, a_rep, sL, sR);
+  LB_LAUNCH_CHECK();
 }
 // One Bulletproofs round's scalar side in ONE launch (single GPU): fold a, b with the previous round's
 // challenge (bullet.rs:127-130), expand the generator weights, form the L / R scalars of the unfolded
@@ -916,6 +1023,7 @@ void launch_bullet_round(const fr_t* a_in, const fr_t* b_in, const fr_t* w_in, f
   unsigned blocks = (unsigned)((n + kThreads - 1) / kThreads);
   bullet_round_kernel<<<blocks, kThreads, 0, st>>>(a_in, b_in, w_in, a_out, b_out, w_out, n, m, fold, u, uinv, blind_L,
                                                    blind_R, s_out, cols_out, partial, counter);
+  LB_LAUNCH_CHECK();
 }
 // Two MSM rows over the n + 2 generators (G_0..G_{n-1}, Q, h) in canonical form:
 //   row 0 = (k * v[0..n), t00, t01)    row 1 = (0 .. 0, t10, t11)
@@ -939,6 +1047,7 @@ __global__ void __launch_bounds__(kThreads)
 void launch_two_row_scalars(const fr_t* v, int scale, const fr_t& k, const fr_t& t00, const fr_t& t01, const fr_t& t10,
                             const fr_t& t11, size_t n, fr_t* out, cudaStream_t st) {
   two_row_scalars_kernel<<<grid_for(n + 2), kThreads, 0, st>>>(v, scale, k, t00, t01, t10, t11, n, out);
+  LB_LAUNCH_CHECK();
 }
 // out[i] = in[i*stride + off] * k
 __global__ void __launch_bounds__(kThreads)
@@ -948,6 +1057,7 @@ __global__ void __launch_bounds__(kThreads)
 }
 void launch_scale_strided(const fr_t* in, fr_t* out, size_t n, size_t stride, size_t off, const fr_t& k, cudaStream_t st) {
   scale_strided_kernel<<<grid_for(n), kThreads, 0, st>>>(in, out, n, stride, off, k);
+  LB_LAUNCH_CHECK();
 }
 __global__ void __launch_bounds__(kThreads) scale_kernel(const fr_t* in, fr_t* out, size_t n, fr_t k) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -955,6 +1065,7 @@ __global__ void __launch_bounds__(kThreads) scale_kernel(const fr_t* in, fr_t* o
 }
 void launch_scale(const fr_t* in, fr_t* out, size_t n, const fr_t& k, cudaStream_t st) {
   scale_kernel<<<grid_for(n), kThreads, 0, st>>>(in, out, n, k);
+  LB_LAUNCH_CHECK();
 }
 
 }  // namespace lb

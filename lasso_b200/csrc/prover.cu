@@ -17,13 +17,17 @@
 // over one fixed table T[w][j] = 2^(8w) G_j.  The group elements are identical; only the schedule differs.
 #include "prover.cuh"
 
+#include <sched.h>
+
+#include <cctype>
+#include <mutex>
 #include <thread>
 
 #include "host_fq64.hpp"
 
 namespace lb {
 
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 
 // ---------------------------------------------------------------------------------------------- context
 __global__ void publish_kernel(const uint32_t* src, int nwords, uint32_t* mapped, uint32_t seq) {
@@ -42,15 +46,21 @@ void Ctx::d2h_small(void* dst, const void* src, size_t bytes) {
   wait_flag(seq);
   memcpy(dst, (const void*)h_mapped, bytes);
 }
-void Ctx::fin_wait(const Finalize& f, fr_t* dst, int count) {
-  if (f.mapped) {
-    // every element arrives as one 32-byte store carrying the round's tag in bits 29..31 of its last word
-    if ((size_t)count > kTaggedElems) throw std::runtime_error("round message larger than the tagged buffer");
-    volatile uint32_t* w = h_mapped + kTaggedWord0;
-    auto t0 = std::chrono::steady_clock::now();
-    unsigned spins = 0;
-    for (int v = 0; v < count; v++) {
-      while ((w[8 * v + 7] >> 29) != f.tag) {
+// One element = five 64-bit words, each carrying 51 value bits and the 13-bit tag of its message (common.cuh): a
+// word is accepted only when it shows the tag, so neither the order in which the device's stores become visible
+// nor the width of the store instruction matters.  Consumed slots are zeroed.
+void Ctx::pub_wait_raw(const PubDst& p, int writer, int count, uint32_t* out) {
+  if (!h_pub || !p.ndst) throw std::runtime_error("no publication buffer for this message");
+  if ((size_t)count > (size_t)kPubElems) throw std::runtime_error("message larger than a publication region");
+  volatile unsigned long long* base = h_pub + ((size_t)writer * kPubRegions + p.region) * kPubElems * kPubSlotWords;
+  const unsigned long long tag = p.tag, M = (1ull << 51) - 1;
+  auto t0 = std::chrono::steady_clock::now();
+  unsigned spins = 0;
+  for (int v = 0; v < count; v++) {
+    volatile unsigned long long* s = base + (size_t)v * kPubSlotWords;
+    unsigned long long w[5];
+    for (int k = 0; k < 5; k++) {
+      while (((w[k] = s[k]) >> 51) != tag) {
         __builtin_ia32_pause();
         if ((++spins & 0xffff) == 0) {  // surface kernel faults instead of spinning forever
           double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -58,40 +68,32 @@ void Ctx::fin_wait(const Finalize& f, fr_t* dst, int count) {
           if (dt > 120.0) throw std::runtime_error("timeout waiting for a device result");
         }
       }
+      w[k] &= M;
     }
-    __sync_synchronize();
-    memcpy(dst, (const void*)w, (size_t)count * sizeof(fr_t));
-    for (int v = 0; v < count; v++) {
-      dst[v].v[7] &= 0x1fffffffu;
-      w[8 * v + 7] = 0;  // consumed: no stale tag can satisfy a later wait
-    }
+    for (int k = 0; k < 5; k++) s[k] = 0;  // consumed
+    const unsigned long long q0 = w[0] | (w[1] << 51), q1 = (w[1] >> 13) | (w[2] << 38), q2 = (w[2] >> 26) | (w[3] << 25),
+                             q3 = (w[3] >> 39) | (w[4] << 12);
+    uint32_t* o = out + 8 * (size_t)v;
+    o[0] = (uint32_t)q0; o[1] = (uint32_t)(q0 >> 32);
+    o[2] = (uint32_t)q1; o[3] = (uint32_t)(q1 >> 32);
+    o[4] = (uint32_t)q2; o[5] = (uint32_t)(q2 >> 32);
+    o[6] = (uint32_t)q3; o[7] = (uint32_t)(q3 >> 32);
+  }
+}
+void Ctx::fin_wait(const Finalize& f, fr_t* dst, int count) {
+  if (!f.pub.all) {
+    pub_wait_raw(f.pub, rank, count, (uint32_t*)dst);
     return;
   }
-  comm_allreduce_fr(this, d_small, count);
-  d2h(dst, d_small, (size_t)count * sizeof(fr_t));
-}
-void Ctx::wait_points(int npoints, uint32_t* xyz) {
-  volatile uint32_t* w = h_mapped + kTaggedWord0;
-  const int count = 3 * npoints;
-  auto t0 = std::chrono::steady_clock::now();
-  unsigned spins = 0;
-  for (int v = 0; v < count; v++) {
-    while ((w[8 * v + 7] >> 31) == 0) {
-      __builtin_ia32_pause();
-      if ((++spins & 0xffff) == 0) {
-        double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        if (dt > 0.5) LB_CUDA_CHECK(cudaStreamQuery(st) == cudaErrorNotReady ? cudaSuccess : cudaStreamSynchronize(st));
-        if (dt > 120.0) throw std::runtime_error("timeout waiting for a device result");
-      }
-    }
-  }
-  __sync_synchronize();
-  memcpy(xyz, (const void*)w, (size_t)count * 32);
-  for (int v = 0; v < count; v++) {
-    xyz[8 * v + 7] &= 0x7fffffffu;
-    w[8 * v + 7] = 0;
+  // one proof sharded over `world` GPUs: every rank stored its partial sums here; add the residues (mod l)
+  std::vector<fr_t> tmp((size_t)count);
+  for (int w = 0; w < world; w++) {
+    pub_wait_raw(f.pub, w, count, (uint32_t*)(w == 0 ? dst : tmp.data()));
+    if (w)
+      for (int v = 0; v < count; v++) dst[v] = fr_add(dst[v], tmp[v]);
   }
 }
+void Ctx::wait_points(const PubDst& p, int npoints, uint32_t* xyz) { pub_wait_raw(p, rank, 3 * npoints, xyz); }
 void Ctx::wait_flag(uint32_t seq) {
   volatile uint32_t* flag = h_mapped + 1024;
   auto t0 = std::chrono::steady_clock::now();
@@ -108,6 +110,53 @@ void Ctx::wait_flag(uint32_t seq) {
   }
   __sync_synchronize();
 }
+// Pin the calling thread (and the threads it creates later) to the CPUs of the NUMA node the device hangs off.
+int bind_host_threads(int device) {
+  try {
+    char busid[64] = {0};
+    if (cudaDeviceGetPCIBusId(busid, sizeof busid, device) != cudaSuccess) return -1;
+    for (char* p = busid; *p; p++) *p = (char)tolower(*p);
+    int node = -1;
+    {
+      std::string path = std::string("/sys/bus/pci/devices/") + busid + "/numa_node";
+      FILE* f = fopen(path.c_str(), "r");
+      if (!f) return -1;
+      if (fscanf(f, "%d", &node) != 1) node = -1;
+      fclose(f);
+    }
+    if (node < 0) return -1;
+    std::string path = "/sys/devices/system/node/node" + std::to_string(node) + "/cpulist";
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) return -1;
+    char buf[4096] = {0};
+    if (!fgets(buf, sizeof buf, f)) {
+      fclose(f);
+      return -1;
+    }
+    fclose(f);
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int count = 0;
+    for (char* tok = strtok(buf, ",\n"); tok; tok = strtok(nullptr, ",\n")) {  // "0-31,64-95"
+      int lo = 0, hi = 0;
+      if (sscanf(tok, "%d-%d", &lo, &hi) == 2) {
+      } else if (sscanf(tok, "%d", &lo) == 1) {
+        hi = lo;
+      } else {
+        continue;
+      }
+      for (int cpu = lo; cpu <= hi && cpu < CPU_SETSIZE; cpu++) {
+        CPU_SET(cpu, &set);
+        count++;
+      }
+    }
+    if (count == 0) return -1;
+    if (sched_setaffinity(0, sizeof set, &set) != 0) return -1;
+    return node;
+  } catch (...) {
+    return -1;
+  }
+}
 Ctx* ctx_create(int device) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
@@ -115,6 +164,10 @@ Ctx* ctx_create(int device) {
     throw std::runtime_error("lasso_b200 needs a CUDA device (sm_100a); there is no CPU fallback");
   if (device < 0 || device >= count) throw std::runtime_error("invalid device id");
   LB_CUDA_CHECK(cudaSetDevice(device));
+  {
+    const char* nb = getenv("LASSO_B200_NUMA_BIND");  // bind before the pinned buffers are first touched
+    if (nb && nb[0] == '1') bind_host_threads(device);
+  }
   std::unique_ptr<Ctx> c(new Ctx());
   c->device = device;
   LB_CUDA_CHECK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
@@ -137,8 +190,14 @@ Ctx* ctx_create(int device) {
       LB_CUDA_CHECK(cudaHostAlloc((void**)&c->h_mapped, Ctx::kMappedBytes, cudaHostAllocMapped));
       memset(c->h_mapped, 0, Ctx::kMappedBytes);
       LB_CUDA_CHECK(cudaHostGetDevicePointer((void**)&c->d_mapped, c->h_mapped, 0));
+      LB_CUDA_CHECK(cudaHostAlloc((void**)&c->h_pub, Ctx::kPubBytes, cudaHostAllocMapped));
+      memset(c->h_pub, 0, Ctx::kPubBytes);
+      c->h_pub_owned = true;
+      LB_CUDA_CHECK(cudaHostGetDevicePointer((void**)&c->d_pub_reader[0], c->h_pub, 0));
     }
   }
+  msm_init_device();      // per-device function attributes (dynamic shared memory opt-in)
+  densify_init_device();
   LB_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming));
   const char* sp = getenv("LASSO_B200_SPANS");
   c->span_sync = sp && sp[0] == '1';
@@ -155,6 +214,7 @@ void ctx_destroy(Ctx* c) {
   if (c->ev_aux) cudaEventDestroy(c->ev_aux);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->h_mapped) cudaFreeHost(c->h_mapped);
+  if (c->h_pub && c->h_pub_owned) cudaFreeHost(c->h_pub);
   cudaFreeHost(c->h_pin);
   cudaStreamDestroy(c->st);
   delete c;
@@ -205,25 +265,29 @@ Gens* gens_create(Ctx* c, const uint64_t* stream_affine, size_t n_points, size_t
     const char* off = getenv("LASSO_B200_NO_MULTIPLES");
     // The tables are an optimisation: if the device cannot hold them (cap, or an allocation failure on a smaller
     // or busier GPU) the prover silently keeps the bucket / 8-bit paths — outputs do not depend on it.
+    // One proof sharded over G GPUs: the openings run replicated (every rank needs the 8-bit multiples of all
+    // nd generators), the Hyrax commitments are column-sharded (a rank needs the 16-bit multiples of ITS columns
+    // only: 1/G of the table per GPU).
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
+    const size_t G = (size_t)c->world, gr = (size_t)c->rank;
     const size_t bytes8 = (size_t)kMsmFullWindows * nd * 128 * sizeof(pt_niels);
-    if (c->world == 1 && nd <= n_points && !(off && off[0] == '1') && bytes8 < free_b / 2) {
+    if (nd <= n_points && !(off && off[0] == '1') && bytes8 < free_b / 2) {
       g->n_direct = nd;
       g->d_multiples.alloc(c, (size_t)kMsmFullWindows * nd * 128);
       launch_build_multiples(g->d_table.p, n_points, nd, kMsmFullWindows, g->d_multiples.p, c->st);
       g_launches += 1;
       const char* cap = getenv("LASSO_B200_TABLE_GB");
       const double cap_gb = cap ? atof(cap) : 64.0;
-      const size_t ncols16 = nd - 2;
+      const size_t ncols16 = (nd - 2) / G;  // this rank's columns: generators j * G + rank
       const size_t bytes16 = ncols16 * 32768 * sizeof(pt_niels);
-      if ((double)bytes16 <= cap_gb * 1e9 && bytes16 < (free_b - bytes8) / 2) {
+      if (ncols16 >= 1 && (nd - 2) % G == 0 && (double)bytes16 <= cap_gb * 1e9 && bytes16 < (free_b - bytes8) / 2) {
         g->n_direct16 = ncols16;
         g->d_multiples16.alloc(c, ncols16 * 32768);
-        launch_build_multiples16(g->d_table.p, g->d_multiples.p, nd, ncols16, g->d_multiples16.p, c->st);
+        launch_build_multiples16(g->d_table.p, g->d_multiples.p, nd, ncols16, G, gr, g->d_multiples16.p, c->st);
         g_launches += 1;
         g->d_centre.alloc(c, 32);
-        for (size_t k = 0; ((size_t)1 << k) <= ncols16 && k < 32; k++) {  // one constant per power-of-two row length
+        for (size_t k = 0; ((size_t)1 << k) <= ncols16 && k < 32; k++) {  // one constant per power-of-two (local) row length
           launch_centre_constant(g->d_multiples16.p, 1 << k, g->d_centre.p + k, c->st);
           g_launches += 1;
         }
@@ -241,10 +305,25 @@ static inline size_t loc(const Ctx* c, size_t n) {
   if (n % (size_t)c->world) throw std::runtime_error("array shorter than the number of GPUs");
   return n / (size_t)c->world;
 }
-// sum a device-side partial result over the ranks, then bring it to the host
+// a few field elements computed on the device -> host, summed over the ranks of a sharded proof: one tiny kernel
+// publishes them as a tagged message to every process (common.cuh PubDst)
+__global__ void publish_fr_kernel(const fr_t* src, int count, PubDst pub) {
+  for (int v = threadIdx.x; v < count; v += blockDim.x) {
+    const fr_t x = src[v];
+    pub_store(pub, v, x.v);
+  }
+}
 static void reduce_to_host(Ctx* c, fr_t* d_buf, int count, fr_t* h_out) {
-  comm_allreduce_fr(c, d_buf, count);
-  c->d2h(h_out, d_buf, (size_t)count * sizeof(fr_t));
+  if (!c->h_pub || count > kPubElems) {
+    if (c->world > 1) throw std::runtime_error("sharded proof without publication buffers");
+    c->d2h(h_out, d_buf, (size_t)count * sizeof(fr_t));
+    return;
+  }
+  Finalize f = c->fin_begin(true);
+  publish_fr_kernel<<<1, 128, 0, c->st>>>(d_buf, count, f.pub);
+  LB_LAUNCH_CHECK();
+  g_launches += 1;
+  c->fin_wait(f, h_out, count);
 }
 // this rank's shard of eq(r[off .. off+ell)) (eq_poly.rs:21-38): eq[i*G + g] = eq_hi[i] * eq_lo[g] where
 // eq_lo is the table of the LAST log2(G) coordinates (they bind the low index bits: r[0] <-> MSB)
@@ -264,42 +343,35 @@ static void eq_evals_shard(Ctx* c, const std::vector<fr_t>& r, size_t off, size_
 }
 
 // ---------------------------------------------------------------------------------------------- MSM helpers
-// Row-MSMs over the generator table.  `d_scal` holds this rank's columns (ncols_loc per row, local column c'
-// = global column c'*G + g + col0).  Optional replicated tail: `d_tail` = nrows x ntail scalars on the
-// generators [tail_col0, tail_col0 + ntail) (the Q and h terms of a Bulletproofs round) — identical on
-// every rank, so it is added once, after the cross-GPU gather.  Returns nrows compressed points.
+// Row-MSMs over the generator table with the bucket kernels.  Column-sharded (replicated == false, G > 1): `d_scal`
+// holds this rank's columns (ncols per row, local column c' = generator c'*G + rank), the per-row partial points
+// of every rank are all-gathered and added ("bucket-sum reduce" = gather-then-add).  Replicated: every rank
+// passes the same full rows and computes the same points, no exchange.  Returns nrows compressed points.
 static std::vector<uint8_t> msm_rows(Ctx* c, const Gens& g, const void* d_scal, int limbs, size_t row_stride, int nrows,
-                                     int ncols_loc, int nw, const fr_t* d_tail_canon, int ntail, size_t tail_col0) {
-  const int G = c->world;
+                                     int ncols, int nw, bool replicated) {
+  const int G = replicated ? 1 : c->world, gr = replicated ? 0 : c->rank;
   std::vector<uint8_t> out((size_t)nrows * 32);
   const bool few = nrows <= 8;
-  DBuf<pt_ext> part(c, msm_partials_count(nrows, ncols_loc, nw));
-  if (G == 1 && !d_tail_canon && !few) {  // the common single-GPU commit: normalise on the device
+  DBuf<pt_ext> part(c, msm_partials_count(nrows, ncols, nw));
+  if (G == 1 && !few) {  // the common single-GPU commit: normalise on the device
     DBuf<uint32_t> comp(c, (size_t)nrows * 8);
-    launch_msm_rows(g.d_table.p, g.n_points, 1, d_scal, limbs, row_stride, nrows, ncols_loc, nw, 1, 0, part.p, nullptr,
-                    comp.p, nullptr, c->st);
+    launch_msm_rows(g.d_table.p, g.n_points, 1, d_scal, limbs, row_stride, nrows, ncols, nw, 1, 0, part.p, nullptr, comp.p,
+                    nullptr, c->st);
     g_launches += 2;
     c->d2h(out.data(), comp.p, out.size());
     return out;
   }
-  // general path: raw partial points -> (gather over ranks) -> (+ tail) -> sum -> normalise
-  const int nsrc = G + (d_tail_canon ? 1 : 0);
-  DBuf<uint32_t> raw(c, (size_t)(nsrc + 1) * nrows * 32);
-  uint32_t* mine = raw.p + (size_t)nsrc * nrows * 32;  // scratch slot for this rank's partials
-  launch_msm_rows(g.d_table.p, g.n_points, 1, d_scal, limbs, row_stride, nrows, ncols_loc, nw, G, c->rank, part.p, nullptr,
-                  nullptr, G == 1 ? raw.p : mine, c->st);
+  // raw partial points -> (gather over ranks) -> sum -> normalise
+  DBuf<uint32_t> raw(c, (size_t)(G + 1) * nrows * 32);
+  uint32_t* mine = raw.p + (size_t)G * nrows * 32;  // scratch slot for this rank's partials
+  launch_msm_rows(g.d_table.p, g.n_points, 1, d_scal, limbs, row_stride, nrows, ncols, nw, G, gr, part.p, nullptr, nullptr,
+                  G == 1 ? raw.p : mine, c->st);
   g_launches += 2;
   if (G > 1) comm_allgather(c, mine, raw.p, (size_t)nrows * 128);
-  if (d_tail_canon) {
-    DBuf<pt_ext> tpart(c, msm_partials_count(nrows, ntail, kMsmFullWindows));
-    launch_msm_rows(g.d_table.p + tail_col0, g.n_points, 1, d_tail_canon, 8, (size_t)ntail, nrows, ntail, kMsmFullWindows,
-                    1, 0, tpart.p, nullptr, nullptr, raw.p + (size_t)G * nrows * 32, c->st);
-    g_launches += 2;
-  }
   if (few) {
     uint32_t xyzt[8 * 32];
-    if (nsrc > 1) {
-      launch_sum_raw_points(raw.p, nsrc, nrows, mine, nullptr, nullptr, c->st);
+    if (G > 1) {
+      launch_sum_raw_points(raw.p, G, nrows, mine, nullptr, nullptr, c->st);
       g_launches += 1;
       c->d2h(xyzt, mine, (size_t)nrows * 128);
     } else {
@@ -310,39 +382,18 @@ static std::vector<uint8_t> msm_rows(Ctx* c, const Gens& g, const void* d_scal, 
     return out;
   }
   DBuf<uint32_t> comp(c, (size_t)nrows * 8);
-  launch_sum_raw_points(raw.p, nsrc, nrows, nullptr, comp.p, nullptr, c->st);
+  launch_sum_raw_points(raw.p, G, nrows, nullptr, comp.p, nullptr, c->st);
   g_launches += 1;
   c->d2h(out.data(), comp.p, out.size());
   return out;
 }
-// rows of Montgomery Fr scalars (this rank's columns) + optional replicated Montgomery tail scalars
-static std::vector<uint8_t> msm_rows_fr(Ctx* c, const Gens& g, const fr_t* d_scal_mont, int nrows, int ncols_loc,
-                                        const fr_t* d_tail_mont = nullptr, int ntail = 0, size_t tail_col0 = 0) {
-  DBuf<fr_t> canon(c, (size_t)nrows * ncols_loc + (size_t)nrows * ntail);
-  launch_canonicalize(d_scal_mont, canon.p, (size_t)nrows * ncols_loc, c->d_flag, c->st);
+// replicated rows of Montgomery Fr scalars over the generators [0, ncols) (the openings when the multiples tables
+// are not available): every rank computes the same points
+static std::vector<uint8_t> msm_rows_fr(Ctx* c, const Gens& g, const fr_t* d_scal_mont, int nrows, int ncols) {
+  DBuf<fr_t> canon(c, (size_t)nrows * ncols);
+  launch_canonicalize(d_scal_mont, canon.p, (size_t)nrows * ncols, c->d_flag, c->st);
   g_launches += 1;
-  fr_t* tcan = nullptr;
-  if (d_tail_mont) {
-    tcan = canon.p + (size_t)nrows * ncols_loc;
-    launch_canonicalize(d_tail_mont, tcan, (size_t)nrows * ntail, c->d_flag, c->st);
-    g_launches += 1;
-  }
-  return msm_rows(c, g, canon.p, 8, (size_t)ncols_loc, nrows, ncols_loc, kMsmFullWindows, tcan, ntail, tail_col0);
-}
-// replicated tiny MSM on generators [col0, col0 + ncols): every rank computes the same point, no exchange
-static std::vector<uint8_t> msm_replicated_fr(Ctx* c, const Gens& g, const fr_t* d_scal_mont, int ncols, size_t col0) {
-  DBuf<fr_t> canon(c, (size_t)ncols);
-  launch_canonicalize(d_scal_mont, canon.p, (size_t)ncols, c->d_flag, c->st);
-  DBuf<pt_ext> part(c, msm_partials_count(1, ncols, kMsmFullWindows));
-  DBuf<uint32_t> raw(c, 32);
-  launch_msm_rows(g.d_table.p + col0, g.n_points, 1, canon.p, 8, (size_t)ncols, 1, ncols, kMsmFullWindows, 1, 0, part.p,
-                  nullptr, nullptr, raw.p, c->st);
-  g_launches += 3;
-  uint32_t xyzt[32];
-  c->d2h(xyzt, raw.p, 128);
-  std::vector<uint8_t> out(32);
-  h64::compress_xyz(xyzt, out.data());
-  return out;
+  return msm_rows(c, g, canon.p, 8, (size_t)ncols, nrows, ncols, kMsmFullWindows, true);
 }
 
 // DensePolynomial::commit (dense_mlpoly.rs:152-181) for an integer-valued polynomial of 2^nv entries viewed as
@@ -352,21 +403,37 @@ static std::vector<uint8_t> commit_u32(Ctx* c, const Gens& g, const uint32_t* d_
   if (R + 2 > g.n_points) throw std::runtime_error("generator stream too short for this polynomial");
   int nw = msm_windows_for_bits(max_bits);
   if (nw > 5) throw std::runtime_error("u32 MSM path: scalars wider than 32 bits");
+  const int G = c->world;
   size_t R_loc = loc(c, R);
-  if (c->world == 1 && g.d_multiples.p && R <= g.n_direct && L > 8) {
-    // single GPU: rows as direct sums over the digit-multiples table (msm_kernels.cu), normalised on the device
+  if (g.d_multiples.p && R + 2 <= g.n_direct && L > 8) {
+    // rows as direct sums over the digit-multiples tables (msm_kernels.cu): one table entry per committed integer
     std::vector<uint8_t> out(L * 32);
     DBuf<pt_ext> part(c, L);
     DBuf<uint32_t> comp(c, L * 8);
-    const bool wide = R <= g.n_direct16;
-    launch_msm_rows_direct_u32(g.d_multiples.p, g.n_direct, wide ? g.d_multiples16.p : nullptr,
-                               wide ? g.d_centre.p + (nv - nv / 2) : nullptr, d_vals_loc, R, (int)L, (int)R, nw, part.p, nullptr,
-                               comp.p, nullptr, c->st);
-    g_launches += 2;
+    const bool wide = R_loc <= g.n_direct16;
+    size_t lg_rloc = 0;
+    while (((size_t)1 << lg_rloc) < R_loc) lg_rloc++;
+    const pt_niels* m16 = wide ? g.d_multiples16.p : nullptr;
+    const pt_ext* k16 = wide ? g.d_centre.p + lg_rloc : nullptr;
+    if (G == 1) {  // normalised on the device
+      launch_msm_rows_direct_u32(g.d_multiples.p, g.n_direct, m16, k16, d_vals_loc, R, (int)L, (int)R, nw, 1, 0, part.p, nullptr,
+                                 comp.p, nullptr, c->st);
+      g_launches += 2;
+    } else {  // this rank's columns of every row -> partial points -> gather-then-add over the ranks
+      DBuf<uint32_t> raw(c, (size_t)(G + 1) * L * 32);
+      uint32_t* mine = raw.p + (size_t)G * L * 32;
+      launch_msm_rows_direct_u32(g.d_multiples.p, g.n_direct, m16, k16, d_vals_loc, R_loc, (int)L, (int)R_loc, nw, G, c->rank,
+                                 part.p, nullptr, nullptr, mine, c->st);
+      comm_allgather(c, mine, raw.p, L * 128);
+      launch_sum_raw_points(raw.p, G, (int)L, nullptr, comp.p, nullptr, c->st);
+      g_launches += 3;
+      c->d2h(out.data(), comp.p, out.size());
+      return out;
+    }
     c->d2h(out.data(), comp.p, out.size());
     return out;
   }
-  return msm_rows(c, g, d_vals_loc, 1, R_loc, (int)L, (int)R_loc, nw, nullptr, 0, 0);
+  return msm_rows(c, g, d_vals_loc, 1, R_loc, (int)L, (int)R_loc, nw, false);
 }
 
 // ---------------------------------------------------------------------------------------------- densify
@@ -531,7 +598,9 @@ std::vector<uint8_t> commit(Ctx* c, const Dense& d, const Gens& g) {
 // Vandermonde system is unique, so it is computed with a cached inverse matrix instead of eliminating
 // per round.
 static const std::vector<fr_t>& inv_vandermonde(size_t n) {
-  static std::map<size_t, std::vector<fr_t>> cache;
+  static std::map<size_t, std::vector<fr_t>> cache;  // shared by every context of the process: guarded
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);  // (std::map never moves its nodes: the returned reference stays valid)
   auto it = cache.find(n);
   if (it != cache.end()) return it->second;
   std::vector<fr_t> a(n * 2 * n, fr_zero());  // [V | I], Gauss-Jordan
@@ -597,8 +666,9 @@ static void ser_sumcheck(ByteWriter& w, const SumcheckProof& p) {
 
 // ---------------------------------------------------------------------------------------------- sumcheck
 // sumcheck.rs:149-260 over device polynomials W_k = base + k*stride (k <= alpha, the last is eq); `len_loc` is
-// this rank's length.  Sharded rounds: local eval -> sum over ranks -> host; local bind.  When one element
-// per rank is left the G-element remainders are all-gathered and the last log2(G) rounds run replicated.
+// this rank's length.  Sharded rounds: local eval -> every rank's partial sums to every host (tagged publication
+// into the shared host segments), added there; local bind.  When one element per rank is left the G-element
+// remainders are all-gathered and the last log2(G) rounds run replicated.
 static SumcheckProof prove_arbitrary(Ctx* c, const Strategy& S, fr_t* base, size_t stride, size_t len_loc,
                                      Transcript& transcript, std::vector<fr_t>& r) {
   SpanTimer sp(c, "Sumcheck.prove");
@@ -612,7 +682,7 @@ static SumcheckProof prove_arbitrary(Ctx* c, const Strategy& S, fr_t* base, size
   for (;;) {
     if (sharded && len == 1) {  // hand over to the replicated tail
       tail.alloc(c, (size_t)npolys * c->world);
-      comm_gather_heads(c, nullptr, base, stride, npolys, tail.p);
+      comm_gather_heads(c, nullptr, base, stride, npolys, nullptr, tail.p);
       base = tail.p;
       stride = (size_t)c->world;
       len = (size_t)c->world;
@@ -620,14 +690,10 @@ static SumcheckProof prove_arbitrary(Ctx* c, const Strategy& S, fr_t* base, size
     }
     if (len <= 1) break;
     size_t half = len / 2;
-    if (sharded) {
-      Finalize f = c->fin_begin();
+    {  // sharded: every rank's partial sums go to every process, the hosts add them; else this process only
+      Finalize f = c->fin_begin(sharded);
       launch_sumcheck_eval_arbitrary(S, base, stride, half, f, c->st);
-      c->fin_wait(f, evals.data(), npts);
-    } else {  // replicated tail of a sharded proof, or a single GPU: no cross-rank sum
-      Finalize f = c->fin_begin();
-      launch_sumcheck_eval_arbitrary(S, base, stride, half, f, c->st);
-      if (f.mapped)
+      if (f.pub.ndst)
         c->fin_wait(f, evals.data(), npts);
       else
         c->d2h(evals.data(), c->d_small, (size_t)npts * sizeof(fr_t));
@@ -652,7 +718,7 @@ static SumcheckProof prove_arbitrary(Ctx* c, const Strategy& S, fr_t* base, size
 // length G is all-gathered and the few layers above it are kept replicated on every rank.
 struct Circuit {
   DBuf<fr_t> tree;   // local shards: layer 0 at 0 (N/G elements), layer 1 after it, ...
-  DBuf<fr_t> rtree;  // replicated top: layer k_rep (G elements), k_rep + 1, ...   (empty when G == 1)
+  fr_t* rtree = nullptr;  // replicated top: layer k_rep (G elements), k_rep + 1, ... (2G slots in a shared allocation; G > 1)
   size_t N = 0, num_layers = 0;
   int G = 1;
   size_t k_rep = 0;  // first replicated layer: N >> k_rep == G
@@ -672,30 +738,73 @@ struct Circuit {
       off += len;
       len /= 2;
     }
-    return rtree.p + off;
+    return rtree + off;
   }
 };
-static void circuit_alloc(Ctx* c, Circuit& ci, size_t N) {
+static void circuit_alloc(Ctx* c, Circuit& ci, size_t N, fr_t* rtree_slot) {
   ci.N = N;
   ci.G = c->world;
   ci.num_layers = log2_exact_or_ceil(N);
   ci.tree.alloc(c, 2 * (N / ci.G));
   if (ci.G > 1) {
     ci.k_rep = ci.num_layers - (size_t)c->lg_world;
-    ci.rtree.alloc(c, 2 * (size_t)ci.G);
+    ci.rtree = rtree_slot;
   }
 }
-static void build_tree(Ctx* c, Circuit& ci) {  // grand_product.rs:38-58 (layer 0 already filled)
-  const size_t last_local = ci.G == 1 ? ci.num_layers - 1 : ci.k_rep;
-  for (size_t k = 0; k < last_local; k++) {
-    launch_product_layer(ci.layer_local(k), ci.layer_local(k + 1), ci.layer_len_global(k + 1) / ci.G, c->st);
+static void build_tree(Ctx* c, Circuit& ci) {  // grand_product.rs:38-58 (layer 0 already filled); single GPU, tree by tree
+  for (size_t k = 0; k + 1 < ci.num_layers; k++) {
+    launch_product_layer(ci.layer_local(k), ci.layer_local(k + 1), ci.layer_len_global(k + 1), c->st);
     g_launches += 1;
   }
-  if (ci.G > 1) {
-    comm_gather_heads(c, nullptr, ci.layer_local(ci.k_rep), 0, 1, ci.layer_rep(ci.k_rep));
-    for (size_t k = ci.k_rep; k + 1 < ci.num_layers; k++) {
-      launch_product_layer(ci.layer_rep(k), ci.layer_rep(k + 1), ci.layer_len_global(k + 1), c->st);
-      g_launches += 1;
+}
+// All product trees, size by size, layer by layer in batched launches (poly_kernels.cu).  groups[i] = trees of one
+// (global) size sizes[i]; tops[i][2t], tops[i][2t+1] = the two elements of tree t's top layer (grand_product.rs:60-65
+// `evaluate`).  Sharded: every rank builds the layers of its low-bit shard down to ONE element per tree (the layer
+// of global length G), publishes it to every process, and each host computes the lg G layers above it — they are
+// needed on the device too (the top layers of the grand-product argument run replicated): rtree_host mirrors the
+// circuits' rtree slots and is uploaded by the caller.
+static void build_trees(Ctx* c, std::vector<std::vector<Circuit*>>& groups, const std::vector<size_t>& sizes,
+                        std::vector<std::vector<fr_t>>& tops, std::vector<fr_t>& rtree_host, const fr_t* rtree_base) {
+  const int G = c->world;
+  struct Pending {
+    Finalize f;
+    size_t grp, t0;
+    int nt;
+  };
+  std::vector<Pending> pend;
+  for (size_t gi = 0; gi < groups.size(); gi++) {
+    tops[gi].assign(2 * groups[gi].size(), fr_zero());
+    for (size_t t0 = 0; t0 < groups[gi].size(); t0 += 32) {
+      const int nt = (int)std::min<size_t>(32, groups[gi].size() - t0);
+      TreePtrs tp;
+      for (int t = 0; t < nt; t++) tp.p[t] = groups[gi][t0 + t]->tree.p;
+      if (pend.size() >= (size_t)kPubRegions) throw std::runtime_error("too many product-tree batches in flight");
+      Finalize f = c->fin_begin(G > 1);
+      launch_product_trees(tp, nt, sizes[gi] / (size_t)G, 0, G == 1 ? 2 : 1, f, c->st);
+      g_launches += product_trees_launches(sizes[gi] / (size_t)G);
+      pend.push_back({f, gi, t0, nt});
+    }
+  }
+  for (auto& pd : pend) {
+    fr_t* tp = tops[pd.grp].data() + 2 * pd.t0;
+    if (G == 1) {
+      c->fin_wait(pd.f, tp, 2 * pd.nt);
+      continue;
+    }
+    std::vector<fr_t> rep((size_t)G * pd.nt);  // [rank][tree]: element `rank` of the layer of global length G
+    for (int w = 0; w < G; w++) c->pub_wait_raw(pd.f.pub, w, pd.nt, (uint32_t*)(rep.data() + (size_t)w * pd.nt));
+    for (int t = 0; t < pd.nt; t++) {
+      Circuit& ci = *groups[pd.grp][pd.t0 + t];
+      fr_t* h = rtree_host.data() + (ci.rtree - rtree_base);
+      for (int w = 0; w < G; w++) h[w] = rep[(size_t)w * pd.nt + t];
+      size_t off = 0, len = (size_t)G;
+      while (len > 2) {  // layer k+1[i] = layer k[i] * layer k[i + len/2]
+        for (size_t i = 0; i < len / 2; i++) h[off + len + i] = fr_mul(h[off + i], h[off + len / 2 + i]);
+        off += len;
+        len /= 2;
+      }
+      tp[2 * t] = h[off];
+      tp[2 * t + 1] = h[off + 1];
     }
   }
 }
@@ -782,8 +891,7 @@ static GPAProof prove_gpa(Ctx* c, std::vector<Circuit*>& circuits, std::vector<f
     Finalize fz = c->fin_begin();
     for (;;) {
       if (sharded && cur == 1) {  // all-gather the G-element remainders; the tail rounds run replicated
-        comm_gather_heads(c, dAB, nullptr, 0, 2 * ncirc, tail.p);
-        comm_gather_heads(c, nullptr, Ccur, 0, 1, tail.p + (size_t)2 * ncirc * G);
+        comm_gather_heads(c, dAB, nullptr, 0, 2 * ncirc, Ccur, tail.p);  // A_k, B_k and eq in one exchange
         dA = slot_A(num_layers);
         dB = slot_B(num_layers);
         dAB = slot_AB(num_layers);
@@ -795,7 +903,7 @@ static GPAProof prove_gpa(Ctx* c, std::vector<Circuit*>& circuits, std::vector<f
       }
       if (cur <= 1) break;
       if (!have_evals) {  // first round of a phase; later rounds come out of the fused bind+eval kernel
-        fz = c->fin_begin();
+        fz = c->fin_begin(sharded);
         launch_sumcheck_eval_cubic_comb(dA, dB, Ccur, ncirc, cur / 2, cf, stored_scaled ? 0 : 1, fz, c->st);
         g_launches += 1;
       }
@@ -816,7 +924,7 @@ static GPAProof prove_gpa(Ctx* c, std::vector<Circuit*>& circuits, std::vector<f
       }
       size_t half = cur / 2;
       auto tp0 = std::chrono::steady_clock::now();
-      if (sharded || fz.mapped)
+      if (fz.pub.ndst)  // sharded: the three sums of every rank, added here
         c->fin_wait(fz, ev.data(), 3);
       else
         c->d2h(ev.data(), c->d_small, ev.size() * sizeof(fr_t));
@@ -830,13 +938,13 @@ static GPAProof prove_gpa(Ctx* c, std::vector<Circuit*>& circuits, std::vector<f
       auto tp2 = std::chrono::steady_clock::now();
       if (half > 1) {
         // bind with r_j and evaluate the next round in one pass (sumcheck.rs:116-120 + 63-89)
-        fz = c->fin_begin();
+        fz = c->fin_begin(sharded);
         launch_sumcheck_bind_eval_cubic_comb(dA, dB, Ccur, Cnext, ncirc, half, r_j, cf, stored_scaled ? 0 : 1, fz, c->st);
         stored_scaled = true;
         g_launches += 1;
         std::swap(Ccur, Cnext);
         have_evals = true;
-      } else if (fz.mapped) {
+      } else if (!sharded && fz.pub.ndst) {
         // last round: bind the 2*ncirc heads and publish them (the layer's claims); eq is not needed any more
         fz = c->fin_begin();
         launch_bind_heads(dAB, 2 * ncirc, r_j, fz, c->st);
@@ -927,25 +1035,30 @@ __global__ void set_elems_kernel(fr_t* dst, fr_t a, fr_t b) {
 // PolyEvalProof::prove (dense_mlpoly.rs:301-359) -> DotProductProofLog::prove (dot_product.rs:166-249)
 // -> BulletReductionProof::prove (bullet.rs:40-154).  Z: this rank's shard of a polynomial of 2^nv elements,
 // i.e. for every one of the L rows the R/G columns congruent to the rank.
+// One proof sharded over G GPUs: LZ = L . Z is computed on the column shards and all-gathered (R elements); from
+// there on the opening runs REPLICATED on every rank — its vectors are only R = 2^(nv - nv/2) long and every round
+// is latency-bound, so splitting its two-row MSMs would add an exchange per round and save nothing.  Every rank
+// computes the same points and the same transcript.
 static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t* Z, size_t nv,
                                                const std::vector<fr_t>& r, const fr_t& Zr, Transcript& transcript,
                                                RandomTape& tape) {
   SpanTimer sp(c, "DensePolyEval.prove");
   transcript.append_protocol_name("polynomial evaluation proof");
   if (r.size() != nv) throw std::runtime_error("PolyEvalProof: r.len() != num_vars");
-  const int G = c->world, gr = c->rank;
+  const int G = c->world;
   const size_t lv = nv / 2, rv = nv - nv / 2, L_size = (size_t)1 << lv, n = (size_t)1 << rv;  // n = R_size
   if (n + 2 > g.n_points) throw std::runtime_error("generator stream too short");
-  if (n < 2 * (size_t)G) throw std::runtime_error("opening narrower than 2 x #GPUs");
+  if (n < (size_t)G) throw std::runtime_error("opening narrower than the number of GPUs");
   const size_t lg_n = rv, n_loc = n / G;
   // L, R = factored eq evals (eq_poly.rs:44-52); LZ = L . Z (dense_mlpoly.rs:183-207)
   std::unique_ptr<SpanTimer> sp1(new SpanTimer(c, "PE.1 eq+bound"));
-  DBuf<fr_t> Lvec(c, L_size), a(c, n_loc), b(c, n_loc), arep(c, 2 * (size_t)G);
-  eq_evals_dev(c, r, 0, lv, Lvec.p);          // rows are not sharded: L is replicated
-  eq_evals_shard(c, r, lv, rv, b.p);          // a_vec of the dot product proof = R (this rank's columns)
+  DBuf<fr_t> Lvec(c, L_size), a(c, n), b(c, n), a_loc(c, G > 1 ? n_loc : 0), a_gath(c, G > 1 ? n : 0);
+  eq_evals_dev(c, r, 0, lv, Lvec.p);  // rows are not sharded: L is replicated
+  eq_evals_dev(c, r, lv, rv, b.p);    // a_vec of the dot product proof = R
   if ((size_t)bound_max_chunks() * n_loc > c->partial_elems) throw std::runtime_error("bound scratch too small");
-  launch_bound(Z, Lvec.p, L_size, n_loc, c->d_partial, a.p, c->st);  // x_vec = LZ
+  launch_bound(Z, Lvec.p, L_size, n_loc, c->d_partial, G > 1 ? a_loc.p : a.p, c->st);  // x_vec = LZ (this rank's columns)
   g_launches += 2;
+  if (G > 1) comm_gather_vector(c, a_loc.p, n_loc, a_gath.p, a.p);
 
   // ---- DotProductProofLog::prove
   sp1.reset(new SpanTimer(c, "PE.2 Cx,Cy,append a"));
@@ -956,57 +1069,30 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
   std::vector<fr_t> v1 = tape.random_vector("blinds_vec_1", 2 * lg_n);
   std::vector<fr_t> v2 = tape.random_vector("blinds_vec_2", 2 * lg_n);
   DotProductProofLogBytes out;
-  // single-GPU pipeline below: needs the multiples table of the generators 0 .. n+1
-  const bool fast = G == 1 && c->h_mapped != nullptr && n * 32 <= c->h_pin_bytes && g.d_multiples.p && n + 2 <= g.n_direct;
-  DBuf<fr_t> two(c, 4);
-  if (!fast) {
-    // Cx = batch_commit(x_vec, blind_x = 0) ; Cy = y*Q + 0*h
-    std::vector<uint8_t> Cx = msm_rows_fr(c, g, a.p, 1, (int)n_loc);
-    transcript.append_point_compressed("Cx", Cx.data());
-    set_elems_kernel<<<1, 32, 0, c->st>>>(two.p, Zr, fr_zero());
-    g_launches += 1;
-    std::vector<uint8_t> Cy = msm_replicated_fr(c, g, two.p, 2, n);
-    transcript.append_point_compressed("Cy", Cy.data());
-    {  // append_scalars(b"a", a_vec): canonical bytes straight from the device (all ranks need the whole vector)
-      DBuf<fr_t> canon(c, n_loc), all(c, G > 1 ? n : 0);
-      launch_canonicalize(b.p, canon.p, n_loc, c->d_flag, c->st);
-      g_launches += 1;
-      std::vector<uint8_t> bytes(n * 32);
-      if (G == 1) {
-        c->d2h(bytes.data(), canon.p, bytes.size());
-      } else {
-        comm_allgather(c, canon.p, all.p, n_loc * 32);
-        std::vector<uint8_t> tmp(n * 32);
-        c->d2h(tmp.data(), all.p, tmp.size());
-        for (int q = 0; q < G; q++)  // rank q's local column j' is global column j'*G + q
-          for (size_t j = 0; j < n_loc; j++) memcpy(&bytes[(j * G + q) * 32], &tmp[((size_t)q * n_loc + j) * 32], 32);
-      }
-      transcript.append_scalars_bytes("a", bytes.data(), n);
-    }
-  }
+  // table pipeline below: needs the multiples table of the generators 0 .. n+1
+  const bool fast = c->h_pub != nullptr && n * 32 <= c->h_pin_bytes && g.d_multiples.p && n + 2 <= g.n_direct;
   // ---- BulletReductionProof::prove with unfolded generators (see file header)
-  if (!fast) sp1.reset(new SpanTimer(c, "PE.3 bullet rounds"));
   fr_t blind_fin = fr_zero();  // blind_Gamma = blind_x + blind_y = 0
-  const size_t ncols_main = G == 1 ? n + 2 : n_loc;  // single GPU: Q and h ride along as columns n, n+1
-  DBuf<fr_t> W0(c, n), W1(c, n), sLR(c, 2 * ncols_main), tailsc(c, 4);
-  fr_t* W = W0.p;   // weights of the unfolded generators: replicated (indexed by the HIGH column bits)
+  DBuf<fr_t> W0(c, n), W1(c, n), sLR(c, 2 * (n + 2));
+  fr_t* W = W0.p;   // weights of the unfolded generators (indexed by the HIGH column bits)
   fr_t* Wn = W1.p;
   set_elems_kernel<<<1, 32, 0, c->st>>>(W, fr_one(), fr_zero());
+  LB_LAUNCH_CHECK();
   g_launches += 1;
   fr_t* sL = sLR.p;
-  fr_t* sR = sLR.p + ncols_main;
-  fr_t* av = a.p;  // current a / b vectors: sharded while m >= 2G, replicated afterwards
+  fr_t* sR = sLR.p + (n + 2);
+  fr_t* av = a.p;  // current a / b vectors
   fr_t* bv = b.p;
   DBuf<fr_t> a_alt, b_alt;
   if (fast) {
-    // Single GPU.  Per message ONE scalar kernel + the two MSM kernels, the finish kernel publishing straight to
-    // mapped host memory; the host part of a message (compression, Fiat-Shamir) overlaps the device work of the
-    // next one wherever the transcript allows it.
+    // Per message ONE scalar kernel + the two MSM kernels, the finish kernel publishing straight to mapped host
+    // memory; the host part of a message (compression, Fiat-Shamir) overlaps the device work of the next one
+    // wherever the transcript allows it.
     //   (Cx, Cy): rows (x_vec, 0, 0) and (0.., y, 0) of one two-row MSM        (dot_product.rs:192-197)
     //   round k : fold with u_{k-1}, weights, L/R scalars, c_L, c_R -> two-row MSM   (bullet.rs:73-134)
-    auto read_two_points = [&](uint8_t* comp64) {
+    auto read_two_points = [&](const PubDst& pd, uint8_t* comp64) {
       uint32_t xyz[48];
-      c->wait_points(2, xyz);
+      c->wait_points(pd, 2, xyz);
       h64::compress_xyz_pair(xyz, xyz + 24, comp64, comp64 + 32);  // one Fq inversion for both points
     };
     a_alt.alloc(c, n);
@@ -1018,22 +1104,23 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
     // two short rows over the multiples table; len terms per row, generator index per term in cols (or identity)
     // heavy = rows that carry the terms: both in a round (L, R), one for (Cx, Cy) — Cy is a single term
     auto two_row_msm = [&](const uint32_t* d_cols, size_t len, int heavy) {
-      launch_msm_direct(g.d_multiples.p, g.n_direct, (const uint32_t*)sLR.p, d_cols, 2, (int)len, heavy, part.p, nullptr,
-                        c->d_mapped + Ctx::kTaggedWord0, c->st);
+      const PubDst pd = c->pub_begin(false);
+      launch_msm_direct(g.d_multiples.p, g.n_direct, (const uint32_t*)sLR.p, d_cols, 2, (int)len, heavy, part.p, nullptr, pd,
+                        c->st);
       g_launches += 2;
+      return pd;
     };
     launch_two_row_scalars(av, 0, fr_one(), fr_zero(), fr_zero(), Zr, fr_zero(), n, sLR.p, c->st);
-    two_row_msm(nullptr, n + 2, 1);
+    const PubDst pd_c = two_row_msm(nullptr, n + 2, 1);
     // a_vec of the transcript = canonical bytes of b; the copy is waited for only when it is appended
     launch_canonicalize(bv, canon.p, n, c->d_flag, c->st);
     LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin, canon.p, n * 32, cudaMemcpyDeviceToHost, c->st));
     LB_CUDA_CHECK(cudaEventRecord(c->ev_aux, c->st));
     g_launches += 2;
-    uint8_t CxCy[64];
-    read_two_points(CxCy);
     fr_t u = fr_one(), u_inv = fr_one();
     int fold = 0;
     size_t m = n;  // vector length entering the round (after the fold with the previous challenge)
+    PubDst pd_round;
     auto launch_round = [&](size_t round) {
       launch_bullet_round(av, bv, W, an, bn, Wn, n, m, fold, u, u_inv, v1[round], v2[round], sLR.p, cols.p, c->d_partial,
                           c->d_flag + 4, c->st);
@@ -1043,8 +1130,11 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
         std::swap(bv, bn);
         std::swap(W, Wn);
       }
-      two_row_msm(cols.p, n / 2 + 2, 2);
+      pd_round = two_row_msm(cols.p, n / 2 + 2, 2);
     };
+    // NB: the (Cx, Cy) MSM reads sLR before round 0 overwrites it: same stream, so ordered
+    uint8_t CxCy[64];
+    read_two_points(pd_c, CxCy);
     if (m != 1) launch_round(0);  // round 0 needs no challenge: it runs while the host absorbs Cx, Cy, a
     transcript.append_point_compressed("Cx", CxCy);
     transcript.append_point_compressed("Cy", CxCy + 32);
@@ -1053,7 +1143,7 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
     sp1.reset(new SpanTimer(c, "PE.3 bullet rounds"));
     for (size_t round = 0; m != 1; round++) {
       uint8_t LR[64];
-      read_two_points(LR);
+      read_two_points(pd_round, LR);
       transcript.append_point_compressed("L", LR);
       transcript.append_point_compressed("R", LR + 32);
       u = transcript.challenge_scalar("u");
@@ -1072,47 +1162,53 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
       std::swap(W, Wn);
     }
   } else {
-  bool sharded = G > 1;
-  size_t m = n, nw_count = 1;  // current (global) vector length, number of weights
-  for (size_t round = 0; m != 1; round++) {
-    if (sharded && m == (size_t)G) {  // one element per rank left: gather, finish replicated
-      comm_gather_heads(c, nullptr, av, 0, 1, arep.p);
-      comm_gather_heads(c, nullptr, bv, 0, 1, arep.p + G);
-      av = arep.p;
-      bv = arep.p + G;
-      sharded = false;
+    // no multiples table (LASSO_B200_NO_MULTIPLES=1 / not enough memory) or no mapped buffers: bucket MSMs over
+    // the window table, one kernel per step
+    DBuf<fr_t> two(c, 4);
+    {
+      // Cx = batch_commit(x_vec, blind_x = 0) ; Cy = y*Q + 0*h
+      std::vector<uint8_t> Cx = msm_rows_fr(c, g, a.p, 1, (int)n);
+      transcript.append_point_compressed("Cx", Cx.data());
+      // (0 .. 0, y, 0) on (G_0 .. G_{n-1}, Q, h)
+      launch_fill_zero(sL, n, c->st);
+      set_elems_kernel<<<1, 32, 0, c->st>>>(sL + n, Zr, fr_zero());
+      LB_LAUNCH_CHECK();
+      g_launches += 1;
+      std::vector<uint8_t> Cy = msm_rows_fr(c, g, sL, 1, (int)(n + 2));
+      transcript.append_point_compressed("Cy", Cy.data());
+      // append_scalars(b"a", a_vec): canonical bytes straight from the device
+      DBuf<fr_t> canon(c, n);
+      launch_canonicalize(b.p, canon.p, n, c->d_flag, c->st);
+      g_launches += 1;
+      std::vector<uint8_t> bytes(n * 32);
+      c->d2h(bytes.data(), canon.p, bytes.size());
+      transcript.append_scalars_bytes("a", bytes.data(), n);
     }
-    const size_t h = m / 2;
-    const size_t h_arr = sharded ? h / G : h;  // half length of the arrays this rank holds
-    launch_cross_inner_products(av, bv, h_arr, c->d_partial, c->d_small, c->st);  // c_L, c_R (bullet.rs:78-79)
-    g_launches += 2;
-    if (sharded) comm_allreduce_fr(c, c->d_small, 2);
-    launch_bullet_scalars(av, W, n_loc, m, G, gr, (G > 1 && !sharded) ? 1 : 0, sL, sR, c->st);
-    g_launches += 1;
-    std::vector<uint8_t> LR;
-    if (G == 1) {
+    sp1.reset(new SpanTimer(c, "PE.3 bullet rounds"));
+    size_t m = n, nw_count = 1;  // current vector length, number of weights
+    for (size_t round = 0; m != 1; round++) {
+      const size_t h = m / 2;
+      launch_cross_inner_products(av, bv, h, c->d_partial, c->d_small, c->st);  // c_L, c_R (bullet.rs:78-79)
+      g_launches += 2;
+      launch_bullet_scalars(av, W, n, m, 1, 0, 0, sL, sR, c->st);
       set_tail_kernel<<<1, 32, 0, c->st>>>(sL + n, sR + n, c->d_small, v1[round], v2[round]);
-      g_launches += 1;
-      LR = msm_rows_fr(c, g, sLR.p, 2, (int)(n + 2));
-    } else {
-      set_tail_kernel<<<1, 32, 0, c->st>>>(tailsc.p, tailsc.p + 2, c->d_small, v1[round], v2[round]);
-      g_launches += 1;
-      LR = msm_rows_fr(c, g, sLR.p, 2, (int)n_loc, tailsc.p, 2, n);
+      LB_LAUNCH_CHECK();
+      g_launches += 2;
+      std::vector<uint8_t> LR = msm_rows_fr(c, g, sLR.p, 2, (int)(n + 2));
+      transcript.append_point_compressed("L", LR.data());
+      transcript.append_point_compressed("R", LR.data() + 32);
+      fr_t u = transcript.challenge_scalar("u");
+      fr_t u_inv = fr_inv(u);
+      launch_fold_ab(av, bv, h, u, u_inv, c->st);  // bullet.rs:127-130 (scalars only; G stays unfolded)
+      launch_expand_weights(W, Wn, nw_count, u, u_inv, c->st);
+      g_launches += 2;
+      std::swap(W, Wn);
+      nw_count *= 2;
+      blind_fin = fr_add(blind_fin, fr_add(fr_mul(fr_mul(v1[round], u), u), fr_mul(fr_mul(v2[round], u_inv), u_inv)));
+      out.L_vec.insert(out.L_vec.end(), LR.begin(), LR.begin() + 32);
+      out.R_vec.insert(out.R_vec.end(), LR.begin() + 32, LR.begin() + 64);
+      m = h;
     }
-    transcript.append_point_compressed("L", LR.data());
-    transcript.append_point_compressed("R", LR.data() + 32);
-    fr_t u = transcript.challenge_scalar("u");
-    fr_t u_inv = fr_inv(u);
-    launch_fold_ab(av, bv, h_arr, u, u_inv, c->st);  // bullet.rs:127-130 (scalars only; G stays unfolded)
-    launch_expand_weights(W, Wn, nw_count, u, u_inv, c->st);
-    g_launches += 2;
-    std::swap(W, Wn);
-    nw_count *= 2;
-    blind_fin = fr_add(blind_fin, fr_add(fr_mul(fr_mul(v1[round], u), u), fr_mul(fr_mul(v2[round], u_inv), u_inv)));
-    out.L_vec.insert(out.L_vec.end(), LR.begin(), LR.begin() + 32);
-    out.R_vec.insert(out.R_vec.end(), LR.begin() + 32, LR.begin() + 64);
-    m = h;
-  }
   }
   sp1.reset(new SpanTimer(c, "PE.4 delta,beta"));
   fr_t ab[2];
@@ -1121,13 +1217,14 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
     // beta = d * Q + r_beta * h (dot_product.rs:229-230) as the two rows of one MSM
     launch_two_row_scalars(W, 1, d, fr_zero(), r_delta, d, r_beta, n, sLR.p, c->st);
     DBuf<pt_ext> part(c, 2 * (size_t)msm_direct_chunks((int)(n + 2), 1));
-    launch_msm_direct(g.d_multiples.p, g.n_direct, (const uint32_t*)sLR.p, nullptr, 2, (int)(n + 2), 1, part.p, nullptr,
-                      c->d_mapped + Ctx::kTaggedWord0, c->st);
+    const PubDst pd = c->pub_begin(false);
+    launch_msm_direct(g.d_multiples.p, g.n_direct, (const uint32_t*)sLR.p, nullptr, 2, (int)(n + 2), 1, part.p, nullptr, pd,
+                      c->st);
     LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin, av, 32, cudaMemcpyDeviceToHost, c->st));
     LB_CUDA_CHECK(cudaMemcpyAsync(c->h_pin + 32, bv, 32, cudaMemcpyDeviceToHost, c->st));
     g_launches += 3;
     uint32_t xyz[48];
-    c->wait_points(2, xyz);
+    c->wait_points(pd, 2, xyz);
     h64::compress_xyz_pair(xyz, xyz + 24, out.delta, out.beta);
     c->sync();
     memcpy(ab, c->h_pin, 64);
@@ -1139,24 +1236,19 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
     c->sync();
     memcpy(ab, c->h_pin, 64);
     // delta = d * g_hat + r_delta * h with g_hat = sum_j W[j] G_j  (dot_product.rs:219-227)
-    std::vector<uint8_t> delta;
-    if (G == 1) {
-      launch_scale(W, sL, n, d, c->st);
-      set_elems_kernel<<<1, 32, 0, c->st>>>(sL + n, fr_zero(), r_delta);
-      g_launches += 2;
-      delta = msm_rows_fr(c, g, sL, 1, (int)(n + 2));
-    } else {
-      launch_scale_strided(W, sL, n_loc, (size_t)G, (size_t)gr, d, c->st);
-      set_elems_kernel<<<1, 32, 0, c->st>>>(tailsc.p, fr_zero(), r_delta);
-      g_launches += 2;
-      delta = msm_rows_fr(c, g, sL, 1, (int)n_loc, tailsc.p, 2, n);
-    }
+    launch_scale(W, sL, n, d, c->st);
+    set_elems_kernel<<<1, 32, 0, c->st>>>(sL + n, fr_zero(), r_delta);
+    LB_LAUNCH_CHECK();
+    g_launches += 2;
+    std::vector<uint8_t> delta = msm_rows_fr(c, g, sL, 1, (int)(n + 2));
     memcpy(out.delta, delta.data(), 32);
     transcript.append_point_compressed("delta", out.delta);
     // beta = d * Q + r_beta * h  (dot_product.rs:229-230)
-    set_elems_kernel<<<1, 32, 0, c->st>>>(two.p, d, r_beta);
+    launch_fill_zero(sL, n, c->st);
+    set_elems_kernel<<<1, 32, 0, c->st>>>(sL + n, d, r_beta);
+    LB_LAUNCH_CHECK();
     g_launches += 1;
-    std::vector<uint8_t> beta = msm_replicated_fr(c, g, two.p, 2, n);
+    std::vector<uint8_t> beta = msm_rows_fr(c, g, sL, 1, (int)(n + 2));
     memcpy(out.beta, beta.data(), 32);
     transcript.append_point_compressed("beta", out.beta);
   }
@@ -1278,15 +1370,18 @@ std::vector<uint8_t> prove(Ctx* c, const Strategy& S, Dense& dense, const std::v
     SpanTimer sp(c, "ProductLayer.prove");
     // Subtables::to_grand_products (subtables/mod.rs:133-175) + GrandProducts::new (memory_checking.rs:175-217)
     std::vector<std::unique_ptr<Circuit>> init(alpha), rd(alpha), wr(alpha), fin(alpha);
+    DBuf<fr_t> rtree_all(c, G > 1 ? 4 * alpha * 2 * (size_t)G : 0);  // the replicated top layers of every tree
+    std::vector<fr_t> rtree_host(G > 1 ? 4 * alpha * 2 * (size_t)G : 0, fr_zero());
+    size_t slot = 0;
     for (size_t i = 0; i < alpha; i++) {
       size_t j = (size_t)S.memory_to_dimension_index((int)i), k = (size_t)S.memory_to_subtable_index((int)i);
       for (auto* pc : {&init[i], &fin[i]}) {
         pc->reset(new Circuit());
-        circuit_alloc(c, **pc, M);
+        circuit_alloc(c, **pc, M, G > 1 ? rtree_all.p + (slot++) * 2 * (size_t)G : nullptr);
       }
       for (auto* pc : {&rd[i], &wr[i]}) {
         pc->reset(new Circuit());
-        circuit_alloc(c, **pc, s);
+        circuit_alloc(c, **pc, s, G > 1 ? rtree_all.p + (slot++) * 2 * (size_t)G : nullptr);
       }
       launch_gp_fingerprints_mem(tables_fr.p + k * M, dense.fin(j), M_loc, G, gr, gamma, tau, init[i]->tree.p,
                                  fin[i]->tree.p, c->st);
@@ -1294,23 +1389,22 @@ std::vector<uint8_t> prove(Ctx* c, const Strategy& S, Dense& dense, const std::v
                                  wr[i]->tree.p, c->st);
       g_launches += 2;
     }
-    // all trees of a size at once + the top layers straight to the host (single GPU); else tree by tree
-    const bool batched = G == 1 && c->h_mapped && 2 * alpha <= 32;
-    std::vector<fr_t> tops(8 * alpha);
+    // all trees of a size at once + the top layers straight to the host; without the mapped buffers: tree by tree
+    const bool batched = c->h_pub != nullptr;
+    std::vector<std::vector<fr_t>> tops(2);  // [0]: init_i, final_i interleaved; [1]: read_i, write_i interleaved
     if (batched) {
-      TreePtrs tm, to;
+      std::vector<std::vector<Circuit*>> groups(2);
       for (size_t i = 0; i < alpha; i++) {
-        tm.p[2 * i] = init[i]->tree.p;
-        tm.p[2 * i + 1] = fin[i]->tree.p;
-        to.p[2 * i] = rd[i]->tree.p;
-        to.p[2 * i + 1] = wr[i]->tree.p;
+        groups[0].push_back(init[i].get());
+        groups[0].push_back(fin[i].get());
+        groups[1].push_back(rd[i].get());
+        groups[1].push_back(wr[i].get());
       }
-      Finalize f = c->fin_begin();
-      launch_product_trees(tm, (int)(2 * alpha), M, 0, f, c->st);
-      launch_product_trees(to, (int)(2 * alpha), s, (int)(2 * alpha), f, c->st);
-      g_launches += product_trees_launches(M) + product_trees_launches(s);
-      c->fin_wait(f, tops.data(), (int)(8 * alpha));
+      build_trees(c, groups, {M, s}, tops, rtree_host, rtree_all.p);
+      if (G > 1)  // pageable source: the copy is staged before the call returns
+        LB_CUDA_CHECK(cudaMemcpyAsync(rtree_all.p, rtree_host.data(), rtree_host.size() * sizeof(fr_t), cudaMemcpyHostToDevice, c->st));
     } else {
+      if (G > 1) throw std::runtime_error("sharded proof without publication buffers");
       for (size_t i = 0; i < alpha; i++) {
         build_tree(c, *init[i]);
         build_tree(c, *fin[i]);
@@ -1320,16 +1414,16 @@ std::vector<uint8_t> prove(Ctx* c, const Strategy& S, Dense& dense, const std::v
     }
     // ProductLayerProof::prove (memory_checking.rs:673-731)
     transcript.append_protocol_name("Lasso ProductLayerProof");
-    auto evaluate = [&](Circuit& ci, size_t slot) {  // grand_product.rs:60-65 (the top layer is replicated when G > 1)
-      if (batched) return fr_mul(tops[2 * slot], tops[2 * slot + 1]);
+    auto evaluate = [&](Circuit& ci, int grp, size_t t) {  // grand_product.rs:60-65
+      if (batched) return fr_mul(tops[grp][2 * t], tops[grp][2 * t + 1]);
       fr_t top[2];
-      c->d2h(top, G == 1 ? ci.layer_local(ci.num_layers - 1) : ci.layer_rep(ci.num_layers - 1), 64);
+      c->d2h(top, ci.layer_local(ci.num_layers - 1), 64);
       return fr_mul(top[0], top[1]);
     };
     std::vector<fr_t> claims_rw, claims_if;
     for (size_t i = 0; i < alpha; i++) {
-      fr_t hi = evaluate(*init[i], 2 * i), hr = evaluate(*rd[i], 2 * alpha + 2 * i),
-           hw = evaluate(*wr[i], 2 * alpha + 2 * i + 1), hf = evaluate(*fin[i], 2 * i + 1);
+      fr_t hi = evaluate(*init[i], 0, 2 * i), hr = evaluate(*rd[i], 1, 2 * i), hw = evaluate(*wr[i], 1, 2 * i + 1),
+           hf = evaluate(*fin[i], 0, 2 * i + 1);
       if (!fr_eq(fr_mul(hi, hw), fr_mul(hr, hf))) throw std::runtime_error("multiset hash check failed (memory_checking.rs:689)");
       transcript.append_scalar("claim_hash_init", hi);
       transcript.append_scalar("claim_hash_read", hr);

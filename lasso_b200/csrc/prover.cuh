@@ -1,6 +1,7 @@
 // lasso_b200 — host-side prover objects: context, device buffers, generator tables, the
 // densified representation and the proof byte writer.  The prover logic is in prover.cu.
 #pragma once
+#include <atomic>
 #include <chrono>
 #include <map>
 #include <memory>
@@ -12,7 +13,7 @@
 
 namespace lb {
 
-extern unsigned long long g_launches;  // kernels launched by this process (bench.py's gpu_launches)
+extern std::atomic<unsigned long long> g_launches;  // kernels launched by this process (bench.py's gpu_launches)
 
 struct Ctx {
   int device = 0;
@@ -31,6 +32,7 @@ struct Ctx {
     if (elems > h_stage_elems) {
       if (h_stage) cudaFreeHost(h_stage);
       h_stage = nullptr;
+      h_stage_elems = 0;  // a failed allocation below must not leave a stale size behind
       LB_CUDA_CHECK(cudaMallocHost((void**)&h_stage, elems * sizeof(uint32_t)));
       h_stage_elems = elems;
     }
@@ -38,7 +40,8 @@ struct Ctx {
   }
   // ---- single proof sharded over `world` GPUs (comm.cu); world == 1: everything below is inert
   int world = 1, rank = 0, lg_world = 0;
-  void* nccl_comm = nullptr;
+  void* xchg = nullptr;  // comm.cu: shared host segments + peer exchange buffers
+  bool h_pub_owned = false;
   fr_t* d_gather = nullptr;  // all-gather landing zone
   size_t gather_elems = 0;
   double t_densify_ms = 0, t_commit_ms = 0, t_prove_ms = 0;
@@ -46,37 +49,60 @@ struct Ctx {
   bool span_sync = false;
 
   void sync() { LB_CUDA_CHECK(cudaStreamSynchronize(st)); }
-  // Round messages (<= 4 KiB): a one-warp kernel copies the result into mapped pinned host memory and then
-  // raises a sequence flag; the host spins on the flag.  ~10-15 us cheaper per sumcheck round than
-  // cudaMemcpyAsync + cudaStreamSynchronize, and a proof has ~400 such rounds.
+  // Small results (<= 4 KiB) that are not round messages: a one-warp kernel copies the result into mapped pinned
+  // host memory and then raises a sequence flag (system-scope fence); the host spins on the flag.  ~10-15 us
+  // cheaper than cudaMemcpyAsync + cudaStreamSynchronize.
   uint32_t* h_mapped = nullptr;  // [0..1024) payload words, [1024] flag
   uint32_t* d_mapped = nullptr;
   uint32_t mapped_seq = 0;
-  // tagged region of the mapped buffer (round messages of Fr elements, see common.cuh Finalize): words
-  // [kTaggedWord0, kTaggedWord0 + 8 * kTaggedElems); the flag-based payload [0, 1024) + flag word 1024 stay separate
-  static constexpr size_t kTaggedWord0 = 2048, kTaggedElems = 512, kMappedBytes = (kTaggedWord0 + 8 * kTaggedElems) * 4;
-  uint32_t fin_seq = 0;
+  static constexpr size_t kMappedBytes = 8192;
+  // Tagged publication of round messages and MSM points (common.cuh PubDst): this process's receive buffer
+  // [writer][region][element][kPubSlotWords] and the device view of every reader's buffer (world == 1: only its
+  // own, plain cudaHostAlloc; world > 1: shared pinned host segments mapped by every process, comm.cu)
+  unsigned long long* h_pub = nullptr;
+  unsigned long long* d_pub_reader[kPubMaxReaders] = {};
+  uint32_t pub_seq = 0;
+  static constexpr size_t kPubBytes = (size_t)kPubMaxReaders * kPubRegions * kPubElems * kPubSlotWords * 8;  // 1 MiB
   cudaEvent_t ev_aux = nullptr;  // marks a device->host copy that overlaps later launches on the same stream
   void d2h_small(void* dst, const void* src, size_t bytes);  // prover.cu
   void wait_flag(uint32_t seq);                               // prover.cu
-  // a round message produced by a single launch (common.cuh Finalize): results land in d_small and, on a single
-  // GPU, directly in the mapped host buffer
-  Finalize fin_begin() {
+  // next message: `all` = every rank stores into every reader's buffer and the readers add the G residues
+  // (the per-round exchange of a sharded proof); otherwise the message goes to this process only
+  PubDst pub_begin(bool all) {
+    PubDst p;
+    p.ndst = 0;
+    p.tag = 0;
+    p.region = 0;
+    p.all = 0;
+    for (int i = 0; i < kPubMaxReaders; i++) p.dst[i] = nullptr;
+    if (!h_pub) return p;
+    const uint32_t seq = pub_seq++;
+    p.region = (int)(seq % kPubRegions);
+    p.tag = 1 + seq % kPubTagMod;
+    p.all = (all && world > 1) ? 1 : 0;
+    const size_t off = ((size_t)rank * kPubRegions + p.region) * kPubElems * kPubSlotWords;
+    if (p.all) {
+      for (int r = 0; r < world; r++) p.dst[p.ndst++] = d_pub_reader[r] + off;
+    } else {
+      p.dst[p.ndst++] = d_pub_reader[rank] + off;
+    }
+    return p;
+  }
+  // count elements of 8 x u32 words from one writer's region; blocks until every word carries the tag
+  void pub_wait_raw(const PubDst& p, int writer, int count, uint32_t* out);  // prover.cu
+  // a round message produced by a single launch (common.cuh Finalize): results land in d_small and directly in
+  // the mapped host buffer(s); reduce = sum over the ranks of a sharded proof
+  Finalize fin_begin(bool reduce = false) {
     Finalize f;
     f.partial = d_partial;
     f.counter = d_flag + 4;
     f.out_dev = d_small;
-    f.mapped = nullptr;
-    f.tag = 0;
-    if (h_mapped && world == 1) {
-      f.mapped = d_mapped + kTaggedWord0;
-      f.tag = 1 + (fin_seq++ % 7);
-    }
+    f.pub = pub_begin(reduce);
     return f;
   }
-  void fin_wait(const Finalize& f, fr_t* dst, int count);  // prover.cu (sums over ranks when sharded)
-  // npoints x (X, Y, Z) canonical Fq limbs published by msm_finish_quad_kernel (tag = bit 255 of each coordinate)
-  void wait_points(int npoints, uint32_t* xyz /* npoints x 24 words */);
+  void fin_wait(const Finalize& f, fr_t* dst, int count);  // prover.cu (adds the residues of all ranks when f.pub.all)
+  // npoints x (X, Y, Z) canonical Fq limbs published by msm_finish_quad_kernel
+  void wait_points(const PubDst& p, int npoints, uint32_t* xyz /* npoints x 24 words */);
   // device -> host through the pinned buffer (small) or directly (large)
   void d2h(void* dst, const void* src, size_t bytes) {
     if (bytes <= 4096 && h_mapped) {
@@ -219,6 +245,7 @@ inline size_t next_pow2(size_t x) {
 }
 
 // entry points implemented in prover.cu
+int bind_host_threads(int device);  // -> NUMA node or -1
 Ctx* ctx_create(int device);
 void ctx_destroy(Ctx*);
 Gens* gens_create(Ctx*, const uint64_t* stream_affine, size_t n_points, size_t c, size_t s, size_t num_memories,
@@ -236,10 +263,12 @@ void comm_unique_id(uint8_t out[128]);
 void comm_init(Ctx*, const uint8_t id[128], int rank, int world);
 void comm_destroy(Ctx*);
 void comm_allgather(Ctx*, const void* d_send, void* d_recv, size_t bytes_per_rank);
-void comm_allreduce_fr(Ctx*, fr_t* d_buf, int count);
+// every rank holds the low-bit shard (n_loc elements) of a vector; d_out <- the whole vector (n_loc * G), on every rank
+void comm_gather_vector(Ctx*, const fr_t* d_shard, size_t n_loc, fr_t* d_scratch, fr_t* d_out);
 // every rank holds one element per polynomial (ptrs[k][0], or base[k*stride] when ptrs == null);
 // d_out[k*G + g] <- rank g's element of polynomial k
-void comm_gather_heads(Ctx*, fr_t* const* d_ptrs, const fr_t* base, size_t stride, int npolys, fr_t* d_out);
+// `extra` (may be null): one more single-element polynomial, gathered as polynomial number npolys
+void comm_gather_heads(Ctx*, fr_t* const* d_ptrs, const fr_t* base, size_t stride, int npolys, const fr_t* extra, fr_t* d_out);
 void pack_heads(Ctx*, fr_t* const* d_ptrs, const fr_t* base, size_t stride, int npolys, fr_t* d_out);
 
 }  // namespace lb

@@ -1,5 +1,9 @@
-"""Run under torchrun with WORLD_SIZE GPUs: ONE proof sharded over all ranks; rank 0 checks that commitment,
+"""Run under torchrun with WORLD_SIZE ranks: ONE proof sharded over all ranks; rank 0 checks that commitment,
 challenges and proof bytes equal the CPU oracle's (and therefore the single-GPU path's).
+One GPU per rank by default (torch.distributed over NCCL carries the job id and the barriers); with
+LASSO_SHARD_SAME_GPU=1 every rank uses GPU 0 (gloo for the plumbing) — the exchanges of the sharded proof (shared
+host segments + CUDA IPC exchange buffers, csrc/comm.cu) do not need one device per rank, so a single-GPU box can
+run this check too.
 usage: torchrun --nproc-per-node N tools/sharded_check.py [kind C log_m log_r lookups same]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -11,8 +15,14 @@ import lasso_b200 as lb
 import oracle_lib as ol
 
 rank = int(os.environ.get("RANK", 0)); local = int(os.environ.get("LOCAL_RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
-torch.cuda.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+same_gpu = os.environ.get("LASSO_SHARD_SAME_GPU") == "1"
+if same_gpu:
+    local = 0
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo")
+else:
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 cases = [(2, 4, 16, 0, 1 << 12, 1), (3, 4, 4, 0, 128, 0), (0, 1, 16, 0, 1 << 10, 1), (4, 3, 8, 40, 256, 0), (3, 8, 8, 0, 512, 0),
          (1, 2, 8, 0, 700, 0)]
 if len(sys.argv) > 6:
