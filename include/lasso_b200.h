@@ -96,6 +96,20 @@ int lasso_gather_lookup_polys(lasso_ctx*, int strategy, int C, int log_M, int lo
  * (and lasso_commit_rows) is collective: each rank passes ITS SHARD of the terms (any split), partial points are
  * all-gathered over NCCL and added, every rank receives the full sum. */
 int lasso_msm(lasso_ctx*, const uint64_t* bases_affine, const uint64_t* scalars, size_t n, uint64_t out_xytz[16]);
+/* BASELINE config 5 — the same VariableBaseMSM::msm on DEVICE-RESIDENT inputs, as a reusable job: `n` terms, term i
+ * uses base i % n_pool (n_pool == n: one base per term; smaller: a pool of distinct points tiled, for benchmarks).
+ * lasso_msm_job_run runs the whole MSM (scalars -> canonical integers, bases -> internal form, Pippenger with the
+ * reference's window rule, msm/mod.rs:91-164) `iters` times between two CUDA events on the context's stream and
+ * returns the average ms and the normalised point; info (may be null) = {window bits c, windows, widest scalar bits,
+ * unit size, L, T2, world, 0}.  On a sharded context every rank passes ITS terms and the call is collective.
+ * lasso_msm_job_naive evaluates the same sum by per-term double-and-add + a tree sum (an independent cross-check
+ * for sizes the CPU oracle cannot reach). */
+typedef struct lasso_msm_job lasso_msm_job;
+int lasso_msm_job_create(lasso_ctx*, const uint64_t* bases_affine, size_t n_pool, const uint64_t* scalars, size_t n,
+                         lasso_msm_job** out);
+int lasso_msm_job_run(lasso_ctx*, lasso_msm_job*, int iters, double* avg_ms, uint64_t out_xytz[16], int info[8]);
+int lasso_msm_job_naive(lasso_ctx*, lasso_msm_job*, uint64_t out_xytz[16]);
+void lasso_msm_job_destroy(lasso_msm_job*);
 /* DensePolynomial::commit_inner  poly/dense_mlpoly.rs:109-128 (+ Commitments::batch_commit
  * poly/commitments.rs:84-93 with blind = 0): Z viewed as L_size rows of R_size; gens_affine holds the
  * R_size generators followed by h.  out_points = L_size extended points (z = 1). */

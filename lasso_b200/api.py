@@ -211,6 +211,44 @@ def msm(ctx, bases_affine, scalars):
     return out
 
 
+class MsmJob:
+    """One VariableBaseMSM (msm/mod.rs:36-40) on device-resident inputs: n terms, term i uses base i % len(bases)."""
+
+    def __init__(self, ctx, bases_affine, scalars):
+        bases = _fr(bases_affine, 8)
+        sc = _fr(scalars)
+        h = C.c_void_p()
+        _chk(lib().lasso_msm_job_create(ctx._h, _p(bases), C.c_size_t(bases.shape[0]), _p(sc), C.c_size_t(sc.shape[0]),
+                                        C.byref(h)))
+        self.ctx, self._h, self.n = ctx, h, sc.shape[0]
+
+    def run(self, iters=1):
+        """-> (extended point (16 u64), average ms per MSM, info dict)"""
+        out = np.zeros(16, dtype=np.uint64)
+        ms = C.c_double(0)
+        info = (C.c_int * 8)()
+        _chk(lib().lasso_msm_job_run(self.ctx._h, self._h, int(iters), C.byref(ms), _p(out), info))
+        return out, ms.value, dict(c=info[0], windows=info[1], scalar_bits=info[2], unit=info[3], L=info[4], T2=info[5],
+                                   world=info[6])
+
+    def naive(self):
+        out = np.zeros(16, dtype=np.uint64)
+        _chk(lib().lasso_msm_job_naive(self.ctx._h, self._h, _p(out)))
+        return out
+
+    def close(self):
+        if self._h:
+            lib().lasso_msm_job_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if self.ctx._h:
+                self.close()
+        except Exception:
+            pass
+
+
 def commit_rows(ctx, gens_affine, Z, L_size, R_size):
     g = _fr(gens_affine, 8)
     Z = _fr(Z)

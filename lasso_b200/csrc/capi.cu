@@ -16,6 +16,20 @@ struct lasso_dense {
   Dense* d;
 };
 
+struct lasso_msm_job {
+  Ctx* c = nullptr;
+  size_t n = 0, n_pool = 0;
+  DBuf<fq_t> bases;     // n_pool x (x, y) arkworks limbs
+  DBuf<fr_t> scalars;   // n Montgomery scalars
+  DBuf<pt_niels> niels; // n
+  DBuf<fr_t> canon;     // n
+  DBuf<uint8_t> scratch;
+  DBuf<fq_t> out_ext;
+  DBuf<uint32_t> raw;   // (G + 1) x 32 words: partial points of the ranks
+  DBuf<pt_ext> naive_part;
+  MsmLargePlan plan;    // of the last run
+};
+
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -35,6 +49,7 @@ static int fail(int code, const std::string& msg) {
   }
 
 static bool is_pow2(size_t x) { return x && !(x & (x - 1)); }
+static constexpr size_t kMsmLargeMin = 1 << 14;  // below this the row kernels (c = 8, buckets in shared memory) win
 static Strategy mkS(int kind, int C, int log_M, int log_R) { return Strategy{kind, C, log_M, log_R}; }
 
 extern "C" {
@@ -242,9 +257,116 @@ static void msm_variable_base(Ctx* c, const uint64_t* bases_affine, size_t nbase
   LB_CUDA_CHECK(cudaMemcpyAsync(out_ext, oe.p, nrows * 128, cudaMemcpyDeviceToHost, c->st));
   c->sync();
 }
+// ---- one large MSM on device-resident inputs (msm_large.cu)
+static lasso_msm_job* msm_job_make(Ctx* c, const uint64_t* bases_affine, size_t n_pool, const uint64_t* scalars, size_t n) {
+  std::unique_ptr<lasso_msm_job> j(new lasso_msm_job());
+  j->c = c;
+  j->n = n;
+  j->n_pool = n_pool;
+  j->bases.alloc(c, n_pool * 2);
+  j->scalars.alloc(c, n);
+  j->niels.alloc(c, n);
+  j->canon.alloc(c, n);
+  j->scratch.alloc(c, msm_large_scratch_bytes(msm_large_plan(n, 253)));
+  j->out_ext.alloc(c, 4);
+  j->raw.alloc(c, (size_t)(c->world + 1) * 32);
+  LB_CUDA_CHECK(cudaMemcpyAsync(j->bases.p, bases_affine, n_pool * 64, cudaMemcpyHostToDevice, c->st));
+  LB_CUDA_CHECK(cudaMemcpyAsync(j->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, c->st));
+  c->sync();
+  return j.release();
+}
+// one MSM: prep (canonical scalars, niels bases, widest scalar) -> plan -> Pippenger; sharded: every rank's partial
+// point is all-gathered and added ("final bucket-sum reduce over NVLink" = gather-then-add)
+static void msm_job_once(lasso_msm_job* j) {
+  Ctx* c = j->c;
+  LB_CUDA_CHECK(cudaMemsetAsync(c->d_flag, 0, 4, c->st));
+  launch_msm_large_prep(j->bases.p, j->scalars.p, j->n, j->n_pool == j->n ? 0 : j->n_pool, j->niels.p, j->canon.p, c->d_flag, c->st);
+  unsigned max_bits = 0;
+  c->d2h(&max_bits, c->d_flag, 4);
+  // the reference's small-scalar shortcut (msm/mod.rs:95-106) only changes the schedule, not the result: here the
+  // window count simply follows the widest scalar
+  j->plan = msm_large_plan(j->n, max_bits);
+  if (c->world == 1) {
+    g_launches += 2 + launch_msm_large(j->plan, j->niels.p, j->canon.p, j->scratch.p, j->out_ext.p, nullptr, c->st);
+    return;
+  }
+  uint32_t* mine = j->raw.p + (size_t)c->world * 32;
+  g_launches += 2 + launch_msm_large(j->plan, j->niels.p, j->canon.p, j->scratch.p, nullptr, mine, c->st);
+  comm_allgather(c, mine, j->raw.p, 128);
+  launch_sum_raw_points(j->raw.p, c->world, 1, nullptr, nullptr, j->out_ext.p, c->st);
+  g_launches += 1;
+}
+int lasso_msm_job_create(lasso_ctx* h, const uint64_t* bases_affine, size_t n_pool, const uint64_t* scalars, size_t n,
+                         lasso_msm_job** out) {
+  LB_TRY_CTX(h)
+  *out = nullptr;
+  if (n == 0 || n >= ((size_t)1 << 31) || n_pool == 0 || n_pool > n) return fail(LASSO_ERR_LENGTH, "msm job: 1 <= n_pool <= n < 2^31");
+  *out = msm_job_make(h->c, bases_affine, n_pool, scalars, n);
+  return 0;
+  LB_CATCH
+}
+int lasso_msm_job_run(lasso_ctx* h, lasso_msm_job* j, int iters, double* avg_ms, uint64_t out_xytz[16], int info[8]) {
+  LB_TRY_CTX(h)
+  if (!j || j->c != h->c || iters < 1) return fail(LASSO_ERR_LENGTH, "msm job: bad arguments");
+  Ctx* c = h->c;
+  cudaEvent_t e0, e1;
+  LB_CUDA_CHECK(cudaEventCreate(&e0));
+  LB_CUDA_CHECK(cudaEventCreate(&e1));
+  LB_CUDA_CHECK(cudaEventRecord(e0, c->st));
+  for (int i = 0; i < iters; i++) msm_job_once(j);
+  LB_CUDA_CHECK(cudaEventRecord(e1, c->st));
+  LB_CUDA_CHECK(cudaEventSynchronize(e1));
+  float ms = 0;
+  LB_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (avg_ms) *avg_ms = ms / iters;
+  if (out_xytz) {
+    LB_CUDA_CHECK(cudaMemcpyAsync(out_xytz, j->out_ext.p, 128, cudaMemcpyDeviceToHost, c->st));
+    c->sync();
+  }
+  if (info) {
+    info[0] = j->plan.c;
+    info[1] = j->plan.nw;
+    info[2] = j->plan.nbits;
+    info[3] = (int)j->plan.S;
+    info[4] = (int)j->plan.L;
+    info[5] = (int)j->plan.T2;
+    info[6] = c->world;
+    info[7] = 0;
+  }
+  return 0;
+  LB_CATCH
+}
+int lasso_msm_job_naive(lasso_ctx* h, lasso_msm_job* j, uint64_t out_xytz[16]) {
+  LB_TRY_CTX(h)
+  if (!j || j->c != h->c) return fail(LASSO_ERR_LENGTH, "msm job: bad arguments");
+  Ctx* c = h->c;
+  if (c->world > 1) return fail(LASSO_ERR_LENGTH, "msm job: the naive cross-check is single-GPU");
+  if (!j->naive_part.p) j->naive_part.alloc(c, (size_t)kNumSMs * 8);
+  launch_msm_naive(j->bases.p, j->scalars.p, j->n, j->n_pool == j->n ? 0 : j->n_pool, j->naive_part.p, j->out_ext.p, c->st);
+  g_launches += 2;
+  LB_CUDA_CHECK(cudaMemcpyAsync(out_xytz, j->out_ext.p, 128, cudaMemcpyDeviceToHost, c->st));
+  c->sync();
+  return 0;
+  LB_CATCH
+}
+void lasso_msm_job_destroy(lasso_msm_job* j) {
+  if (!j) return;
+  cudaSetDevice(j->c->device);
+  delete j;
+}
+
 int lasso_msm(lasso_ctx* h, const uint64_t* bases_affine, const uint64_t* scalars, size_t n, uint64_t out_xytz[16]) {
   LB_TRY_CTX(h)
   if (n == 0 || n > (1u << 30)) return fail(LASSO_ERR_LENGTH, "msm: 1 <= n <= 2^30");
+  if (n >= kMsmLargeMin) {  // one large MSM: the large-window Pippenger (msm_large.cu); collective when sharded
+    std::unique_ptr<lasso_msm_job> j(msm_job_make(h->c, bases_affine, n, scalars, n));
+    msm_job_once(j.get());
+    LB_CUDA_CHECK(cudaMemcpyAsync(out_xytz, j->out_ext.p, 128, cudaMemcpyDeviceToHost, h->c->st));
+    h->c->sync();
+    return 0;
+  }
   msm_variable_base(h->c, bases_affine, n, scalars, 1, n, out_xytz);
   return 0;
   LB_CATCH

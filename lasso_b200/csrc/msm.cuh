@@ -51,6 +51,29 @@ void launch_msm_rows_direct_u32(const pt_niels* M, size_t npts, const pt_niels* 
 void msm_init_device();
 void launch_combine_points(const fq_t* in_ext, int n, fq_t* out_ext, uint32_t* out_comp, cudaStream_t st);
 
+// ---- one large variable-base MSM (msm_large.cu): the reference's Pippenger with a large window, buckets in HBM
+struct MsmLargePlan {
+  size_t n = 0;
+  int nbits = 0, c = 0, nw = 0;  // widest scalar, window bits, windows
+  uint32_t NB = 0, NB1 = 0;      // buckets per window (|digit| = 1..NB), NB + 1
+  uint32_t T2 = 0, L = 0, lgL = 0;  // bucket reduction: T2 blocks of L buckets per window
+  uint32_t S = 0;                // entries per accumulation unit (a larger bucket is split)
+  uint32_t total = 0;            // nw * NB1 counters
+  size_t max_entries = 0, max_units = 0;
+};
+int msm_large_window_bits(size_t n);
+MsmLargePlan msm_large_plan(size_t n, unsigned max_bits);
+size_t msm_large_scratch_bytes(const MsmLargePlan& p);
+void msm_large_init_device();
+// bases: arkworks affine (x, y) Montgomery limbs; term i uses base i % n_pool when n_pool != 0 (bench inputs), else base i
+void launch_msm_large_prep(const fq_t* bases_ark, const fr_t* scalars_mont, size_t n, size_t n_pool, pt_niels* niels,
+                           fr_t* canon, unsigned* d_max_bits, cudaStream_t st);
+int launch_msm_large(const MsmLargePlan& p, const pt_niels* niels, const fr_t* canon, void* scratch, fq_t* out_ext,
+                     uint32_t* out_raw, cudaStream_t st);
+// independent evaluation for the parity tests: per-term double-and-add + tree sum (partial: 148 * 8 points of scratch)
+void launch_msm_naive(const fq_t* bases_ark, const fr_t* scalars_mont, size_t n, size_t n_pool, pt_ext* partial, fq_t* out_ext,
+                      cudaStream_t st);
+
 inline int msm_windows_for_bits(unsigned max_bits) {
   int nw = (int)((max_bits + 2 + kMsmWindowBits - 1) / kMsmWindowBits);
   return nw < 1 ? 1 : nw;

@@ -197,6 +197,7 @@ Ctx* ctx_create(int device) {
     }
   }
   msm_init_device();      // per-device function attributes (dynamic shared memory opt-in)
+  msm_large_init_device();
   densify_init_device();
   LB_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming));
   const char* sp = getenv("LASSO_B200_SPANS");
