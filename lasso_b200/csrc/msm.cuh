@@ -37,6 +37,16 @@ void launch_build_multiples(const pt_niels* T, size_t table_stride, size_t npts,
 int msm_direct_chunks(int len, int heavy_rows);
 void launch_msm_direct(const pt_niels* M, size_t npts, const uint32_t* scalars, const uint32_t* cols, int nrows, int len,
                        int heavy_rows, pt_ext* partials, uint32_t* out_raw, const PubDst& pub, cudaStream_t st);
+// One Bulletproofs round (bullet.rs:73-134, unfolded generators) in ONE launch over the multiples table: scalars from
+// the (folded) a, b, w vectors, both rows L / R summed, tail terms c * Q + blind * h, publication of the two points.
+// a_in / b_in: 2m elements when fold != 0 (folded with u / uinv into a_out / b_out, m elements), else m;
+// w_in: n / (2m) weights when fold (expanded into w_out, n / m), else n / m.
+// partials: 2 * bullet_fused_chunks(n) points; ip_partial: 2 * bullet_fused_chunks(n) elements; counter: zeroed u32.
+int bullet_fused_chunks(int n);
+void launch_bullet_fused(const pt_niels* M, size_t npts, const fr_t* a_in, const fr_t* b_in, const fr_t* w_in, fr_t* a_out,
+                         fr_t* b_out, fr_t* w_out, size_t n, size_t m, int fold, const fr_t& u, const fr_t& uinv,
+                         const fr_t& blind_L, const fr_t& blind_R, pt_ext* partials, fr_t* ip_partial, unsigned* counter,
+                         const PubDst& pub, cudaStream_t st);
 // Hyrax row commitments of integer-valued polynomials as direct sums over the multiples table (no buckets)
 // M16 (may be null): 16-bit multiples M16[j][d-1] = d * G_j, d = 1..32768, of the generators 0 .. ncols-1
 // local column jl <-> generator jl * col_mul + col_add (one proof sharded over col_mul GPUs: this rank's columns)

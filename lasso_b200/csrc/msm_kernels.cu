@@ -713,6 +713,224 @@ __global__ void __launch_bounds__(MSMD_T)
     st_fq(out + role, mine);
   }
 }
+// ---------------------------------------------------------------- one Bulletproofs round in ONE launch
+// bullet.rs:73-134 with unfolded generators (prover.cu file header).  Replaces bullet_round_kernel (scalars) +
+// msm_direct_kernel (both rows) + msm_finish_quad_kernel (sum + publication): three dependent launches on the
+// critical path of each of the ~43 rounds of a proof.
+//   grid (nchunks, 2): row 0 = L, row 1 = R.  CTA (chunk, row) owns the main terms k = chunk + nchunks * q of its row:
+//     k = t * h + p (h = m / 2, t < n / m):   L: generator t*m + h + p, scalar a'[p]     * w'[t]
+//                                             R: generator t*m + p,     scalar a'[p + h] * w'[t]
+//     a' / b' = the vectors folded with the previous challenge (bullet.rs:127-130), w' = the expanded weights.
+//   phase 1: thread q forms the scalar of the CTA's q-th term in shared memory; the threads with t = 0 also own one
+//            element of a', b' each (stored for the next round) and one product of c_L = <a'_lo, b'_hi> (row 0) or
+//            c_R = <a'_hi, b'_lo> (row 1); the CTA's partial inner product goes to `ip_partial`.
+//   phase 2: the quad-lane sum over the multiples table, exactly msm_direct_kernel's, digits read from shared memory.
+//   phase 3: the LAST CTA (ticket) finishes both rows: c_L, c_R from the partial inner products, the two tail terms
+//            c * Q + blind * h of each row (generators n, n + 1) as 128 more table entries — one per quad —, the
+//            per-CTA partial points, a tree over its 64 quads per row, and the tagged publication of X, Y, Z.
+static constexpr int kBulletMaxTerms = MSMD_T;  // main terms per CTA (one thread each in phase 1)
+__global__ void __launch_bounds__(MSMD_T)
+    bullet_fused_kernel(const pt_niels* M, size_t npts, const fr_t* a_in, const fr_t* b_in, const fr_t* w_in, fr_t* a_out,
+                        fr_t* b_out, fr_t* w_out, int n, int m, int fold, fr_t u, fr_t uinv, fr_t blind_L, fr_t blind_R,
+                        pt_ext* partials, fr_t* ip_partial, unsigned* counter, PubDst pub) {
+  __shared__ fq_t sm_pt[128 * 4];
+  __shared__ uint32_t s_sc[kBulletMaxTerms * 8];
+  __shared__ uint32_t s_col[kBulletMaxTerms];
+  __shared__ fr_t s_red[MSMD_T / 32];
+  __shared__ fr_t s_tail[4];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, lane = tid & 31, role = tid & 3, quad = tid >> 2;
+  const int w = quad & 31, sub = quad >> 5;
+  const int chunk = blockIdx.x, nchunks = gridDim.x, row = blockIdx.y;
+  const int h = m >> 1, nmain = n >> 1;
+  const int lg_h = 31 - __clz(h);  // h is a power of two (h >= 1)
+  // ---- phase 1: scalars of this CTA's terms (+ fold bookkeeping)
+  const int nterms = chunk < nmain ? (nmain - chunk + nchunks - 1) / nchunks : 0;
+  fr_t ipv[1] = {fr_zero()};
+  if (tid < nterms) {
+    const int k = chunk + nchunks * tid;
+    const int t = k >> lg_h, p = k & (h - 1);
+    const int ia = row == 0 ? p : p + h;  // index into a' of this term's factor
+    auto folded = [&](const fr_t* v, int i, const fr_t& c0, const fr_t& c1) {
+      return fold ? fr_add(fr_mul(ld_fr(v + i), c0), fr_mul(c1, ld_fr(v + m + i))) : ld_fr(v + i);
+    };
+    const fr_t ai = folded(a_in, ia, u, uinv);
+    const fr_t wt = fold ? fr_mul(ld_fr(w_in + (t >> 1)), (t & 1) ? u : uinv) : ld_fr(w_in + t);
+    const fr_t sc = fr_to_canonical(fr_mul(ai, wt));
+#pragma unroll
+    for (int l = 0; l < 8; l++) s_sc[tid * 8 + l] = sc.v[l];
+    s_col[tid] = (uint32_t)(t * m + (row == 0 ? h + p : p));
+    if (t == 0) {
+      // row 0 owns (a'[p], b'[p + h]) and the product of c_L; row 1 owns (a'[p + h], b'[p]) and the product of c_R
+      const int ib = row == 0 ? p + h : p;
+      const fr_t bi = folded(b_in, ib, uinv, u);
+      if (fold) {
+        st_fr(a_out + ia, ai);
+        st_fr(b_out + ib, bi);
+      }
+      ipv[0] = fr_mul(ai, bi);
+    }
+    if (p == 0 && row == 1 && fold) st_fr(w_out + t, wt);
+  }
+  block_sum_fr<1>(ipv, s_red);
+  if (tid == 0) ip_partial[row * nchunks + chunk] = ipv[0];
+  __syncthreads();
+  // ---- phase 2: quad (w, sub) adds window w of the terms sub, sub + 4, ...
+  fq_t mine = (role == 1 || role == 2) ? fq_one() : fq_zero();  // identity (0, 1, 1, 0)
+  auto operand = [&](const uint32_t* sw, uint32_t col, fq_t& op) -> bool {
+    uint32_t any = 0;
+#pragma unroll
+    for (int l = 0; l < 8; l++) any |= sw[l];
+    if (any == 0) return false;
+    const MsmDigits<8> dg(sw);
+    uint32_t limb = 0;
+#pragma unroll
+    for (int l = 0; l < 8; l++) limb = (l == (w >> 2)) ? dg.b[l] : limb;
+    const int d = (int)((limb >> (8 * (w & 3))) & 0xff) - 128;
+    const int ad = d < 0 ? -d : d;
+    op = role == 3 ? fq_zero() : fq_one();
+    if (ad != 0 && role != 2) {
+      const pt_niels* e = M + ((size_t)w * npts + col) * 128 + (ad - 1);
+      const bool neg = d < 0;
+      if (role == 0) op = ld_fq(neg ? &e->yplusx : &e->yminusx);
+      else if (role == 1) op = ld_fq(neg ? &e->yminusx : &e->yplusx);
+      else {
+        op = ld_fq(&e->t2d);
+        if (neg) op = fq_neg(op);
+      }
+    }
+    return true;
+  };
+  {
+    int q = sub;
+    fq_t op, op_next;
+    uint32_t sw[8];
+    auto fetch = [&](int qq, fq_t& o) -> bool {
+#pragma unroll
+      for (int l = 0; l < 8; l++) sw[l] = s_sc[qq * 8 + l];
+      return operand(sw, s_col[qq], o);
+    };
+    bool have = q < nterms ? fetch(q, op) : false;
+    while (q < nterms) {  // uniform per warp: its 8 quads share sub
+      const int qn = q + 4;
+      const bool have_next = qn < nterms ? fetch(qn, op_next) : false;
+      if (have) mine = quad_madd(0xffffffffu, lane, mine, op);
+      op = op_next;
+      have = have_next;
+      q = qn;
+    }
+  }
+  fq_t* slot = sm_pt + quad * 4;
+  slot[role] = mine;
+  __syncthreads();
+  for (int d = 64; d >= 1; d >>= 1) {
+    fq_t r = mine;
+    if (quad < d) r = quad_add(d >= 8 ? 0xffffffffu : (0xfu << (lane & ~3)), lane, mine, slot + 4 * d);
+    __syncthreads();
+    if (quad < d) {
+      mine = r;
+      slot[role] = mine;
+    }
+    __syncthreads();
+  }
+  if (quad == 0) {
+    fq_t* out = reinterpret_cast<fq_t*>(partials + (size_t)row * nchunks + chunk);
+    st_fq(out + role, mine);
+  }
+  // ---- ticket
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_last = (atomicAdd(counter, 1u) == (unsigned)(gridDim.x * gridDim.y) - 1u);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // ---- phase 3 (last CTA): tail scalars, tail entries, row sums, publication
+  {
+    const int warp = tid >> 5;
+    if (warp < 2) {
+      fr_t v = fr_zero();
+      for (int i = lane; i < nchunks; i += 32) v = fr_add(v, ld_fr_cg(ip_partial + warp * nchunks + i));
+      v = warp_sum_fr(v);
+      if (lane == 0) {
+        s_tail[warp * 2] = fr_to_canonical(v);                                      // c_L / c_R on Q
+        s_tail[warp * 2 + 1] = fr_to_canonical(warp == 0 ? blind_L : blind_R);      // blind on h
+      }
+    }
+  }
+  __syncthreads();
+  const int prow = quad >> 6, pq = quad & 63;  // 64 quads per row
+  {
+    // quad pq of a row: tail term (pq >> 5) of that row, window pq & 31 — one table entry
+    const int term = pq >> 5;
+    fq_t op;
+    mine = (role == 1 || role == 2) ? fq_one() : fq_zero();
+    // (w == pq & 31 == quad & 31 holds: the window used by `operand` is this quad's)
+    if (operand(s_tail[prow * 2 + term].v, (uint32_t)(n + term), op)) mine = quad_madd(0xffffffffu, lane, mine, op);
+  }
+  {
+    const fq_t* prow_p = reinterpret_cast<const fq_t*>(partials + (size_t)prow * nchunks);
+    for (int i0 = 0; i0 < nchunks; i0 += 64) {  // uniform trip count: full-warp shuffles inside
+      const int i = i0 + pq;
+      fq_t q4[4];
+      const bool ok = i < nchunks;
+      if (ok) {
+        const fq_t* src = prow_p + 4 * (size_t)i;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {  // written by other CTAs of this launch: bypass L1
+          asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(q4[k].v[0]), "=r"(q4[k].v[1]), "=r"(q4[k].v[2]), "=r"(q4[k].v[3]) : "l"(src + k));
+          asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(q4[k].v[4]), "=r"(q4[k].v[5]), "=r"(q4[k].v[6]), "=r"(q4[k].v[7]) : "l"((const char*)(src + k) + 16));
+        }
+      } else {  // identity
+        q4[0] = fq_zero();
+        q4[1] = fq_one();
+        q4[2] = fq_one();
+        q4[3] = fq_zero();
+      }
+      const fq_t r = quad_add(0xffffffffu, lane, mine, q4);
+      if (ok) mine = r;
+    }
+  }
+  slot[role] = mine;
+  __syncthreads();
+  for (int d = 32; d >= 1; d >>= 1) {  // tree inside each row: quads prow*64 + [0, 64)
+    fq_t r = mine;
+    if (pq < d) r = quad_add(d >= 8 ? 0xffffffffu : (0xfu << (lane & ~3)), lane, mine, slot + 4 * d);
+    __syncthreads();
+    if (pq < d) {
+      mine = r;
+      slot[role] = mine;
+    }
+    __syncthreads();
+  }
+  if (pq == 0 && role < 3) {
+    const fq_t c = fq_canonical(mine);
+    pub_store(pub, prow * 3 + role, c.v);
+  }
+  if (tid == 0) *counter = 0;
+}
+// chunks of the fused round: as msm_direct_chunks for two heavy rows, and few enough that a CTA's main terms fit
+// its phase-1 threads
+int bullet_fused_chunks(int n) {
+  int c = msm_direct_chunks(n / 2 + 2, 2);
+  while ((n / 2 + c - 1) / c > kBulletMaxTerms) c += 2;
+  return c;
+}
+void launch_bullet_fused(const pt_niels* M, size_t npts, const fr_t* a_in, const fr_t* b_in, const fr_t* w_in, fr_t* a_out,
+                         fr_t* b_out, fr_t* w_out, size_t n, size_t m, int fold, const fr_t& u, const fr_t& uinv,
+                         const fr_t& blind_L, const fr_t& blind_R, pt_ext* partials, fr_t* ip_partial, unsigned* counter,
+                         const PubDst& pub, cudaStream_t st) {
+  if (m < 2 || n < m) throw std::runtime_error("bullet_fused: m >= 2");
+  dim3 grid(bullet_fused_chunks((int)n), 2);
+  bullet_fused_kernel<<<grid, MSMD_T, 0, st>>>(M, npts, a_in, b_in, w_in, a_out, b_out, w_out, (int)n, (int)m, fold, u, uinv,
+                                               blind_L, blind_R, partials, ip_partial, counter, pub);
+  LB_LAUNCH_CHECK();
+}
+
 // nrows (<= 8) short MSMs over the multiples table; the points go to mapped host memory (msm_finish_quad_kernel)
 int msm_direct_chunks(int len, int heavy_rows) {
   int c = (len * kMsmFullWindows + 128 * 4 - 1) / (128 * 4);  // ~4 entries per quad

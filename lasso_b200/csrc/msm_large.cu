@@ -218,12 +218,43 @@ __global__ void __launch_bounds__(128)
 }
 
 // ---------------------------------------------------------------------------------------------- 6. bucket reduction
-// B_b of (window w, bucket b): the sum of its units (one unit unless the bucket was split)
+// A bucket that was split into several units (skewed scalars: e.g. the top window of 20-bit scalars has a handful of
+// non-empty buckets holding all n terms) is combined here, one WARP per bucket: lanes stride over the units, then a
+// shuffle tree; the sum replaces the bucket's first unit.  Buckets with <= 1 unit (all of them for uniform scalars)
+// leave immediately.
+__global__ void __launch_bounds__(256)
+    msm_unit_combine_kernel(pt_ext* unit_sum, const uint32_t* uoff, uint32_t total) {
+  const uint32_t bi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (bi >= total) return;
+  const uint32_t u0 = uoff[bi], u1 = uoff[bi + 1];
+  if (u1 - u0 <= 1) return;  // warp-uniform
+  pt_ext acc = pt_identity();
+  bool any = false;
+  for (uint32_t u = u0 + lane; u < u1; u += 32) {
+    const pt_ext p = ldp(unit_sum + u);
+    acc = any ? pt_add(acc, p) : p;
+    any = true;
+  }
+#pragma unroll 1
+  for (int d = 16; d >= 1; d >>= 1) {
+    pt_ext o;
+#pragma unroll
+    for (int l = 0; l < 8; l++) {
+      o.X.v[l] = __shfl_down_sync(0xffffffffu, acc.X.v[l], d);
+      o.Y.v[l] = __shfl_down_sync(0xffffffffu, acc.Y.v[l], d);
+      o.Z.v[l] = __shfl_down_sync(0xffffffffu, acc.Z.v[l], d);
+      o.T.v[l] = __shfl_down_sync(0xffffffffu, acc.T.v[l], d);
+    }
+    acc = pt_add(acc, o);
+  }
+  if (lane == 0) stp(unit_sum + u0, acc);
+}
+// B_b of (window w, bucket b): its first unit (the whole bucket after msm_unit_combine_kernel)
 __device__ __forceinline__ bool bucket_sum(const pt_ext* unit_sum, const uint32_t* uoff, size_t bi, pt_ext& out) {
   const uint32_t u0 = uoff[bi], u1 = uoff[bi + 1];
   if (u0 == u1) return false;
   out = ldp(unit_sum + u0);
-  for (uint32_t u = u0 + 1; u < u1; u++) out = pt_add(out, ldp(unit_sum + u));
   return true;
 }
 // thread (w, t): buckets t*L + 1 .. t*L + L.  acc = sum_j j * B_{tL+j}, run = sum_j B_{tL+j}
@@ -512,6 +543,8 @@ int launch_msm_large(const MsmLargePlan& p, const pt_niels* niels, const fr_t* c
   msm_accum_kernel<<<(unsigned)((p.max_units + 127) / 128), 128, 0, st>>>(niels, entries, cnt, off, uoff, unit_bucket, totals, p.S,
                                                                         unit_sum);
   LB_LAUNCH_CHECK();
+  msm_unit_combine_kernel<<<(unsigned)(((size_t)p.total * 32 + 255) / 256), 256, 0, st>>>(unit_sum, uoff, p.total);
+  LB_LAUNCH_CHECK();
   msm_r1_kernel<<<(unsigned)(((size_t)p.nw * p.T2 + 127) / 128), 128, 0, st>>>(unit_sum, uoff, p.nw, p.NB1, p.L, p.T2, r1_acc,
                                                                                r1_run);
   LB_LAUNCH_CHECK();
@@ -519,7 +552,7 @@ int launch_msm_large(const MsmLargePlan& p, const pt_niels* niels, const fr_t* c
   LB_LAUNCH_CHECK();
   msm_final_kernel<<<1, 32, 0, st>>>(win_total, p.nw, out_ext, out_raw);
   LB_LAUNCH_CHECK();
-  return 8;
+  return 9;
 }
 
 }  // namespace lb

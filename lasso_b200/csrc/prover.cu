@@ -1122,16 +1122,29 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
     int fold = 0;
     size_t m = n;  // vector length entering the round (after the fold with the previous challenge)
     PubDst pd_round;
+    static const bool unfused = [] {
+      const char* e = getenv("LASSO_B200_UNFUSED_ROUNDS");
+      return e && e[0] == '1';
+    }();
+    DBuf<pt_ext> part_f(c, 2 * (size_t)bullet_fused_chunks((int)n));
     auto launch_round = [&](size_t round) {
-      launch_bullet_round(av, bv, W, an, bn, Wn, n, m, fold, u, u_inv, v1[round], v2[round], sLR.p, cols.p, c->d_partial,
-                          c->d_flag + 4, c->st);
-      g_launches += 1;
+      if (!unfused) {
+        // the whole round in ONE launch: scalars, both rows over the multiples table, tail terms, publication
+        pd_round = c->pub_begin(false);
+        launch_bullet_fused(g.d_multiples.p, g.n_direct, av, bv, W, an, bn, Wn, n, m, fold, u, u_inv, v1[round], v2[round],
+                            part_f.p, c->d_partial, c->d_flag + 4, pd_round, c->st);
+        g_launches += 1;
+      } else {
+        launch_bullet_round(av, bv, W, an, bn, Wn, n, m, fold, u, u_inv, v1[round], v2[round], sLR.p, cols.p, c->d_partial,
+                            c->d_flag + 4, c->st);
+        g_launches += 1;
+      }
       if (fold) {
         std::swap(av, an);
         std::swap(bv, bn);
         std::swap(W, Wn);
       }
-      pd_round = two_row_msm(cols.p, n / 2 + 2, 2);
+      if (unfused) pd_round = two_row_msm(cols.p, n / 2 + 2, 2);
     };
     // NB: the (Cx, Cy) MSM reads sLR before round 0 overwrites it: same stream, so ordered
     uint8_t CxCy[64];
