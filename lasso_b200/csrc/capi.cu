@@ -330,8 +330,8 @@ int lasso_msm_job_run(lasso_ctx* h, lasso_msm_job* j, int iters, double* avg_ms,
     info[1] = j->plan.nw;
     info[2] = j->plan.nbits;
     info[3] = (int)j->plan.S;
-    info[4] = (int)j->plan.L;
-    info[5] = (int)j->plan.T2;
+    info[4] = (int)j->plan.lev_L[0];
+    info[5] = j->plan.nlev;
     info[6] = c->world;
     info[7] = 0;
   }

@@ -1,119 +1,268 @@
 // lasso_b200 — DensifiedRepresentation::from_lookup_indices on the GPU (src/lasso/densified.rs:33-56;
 // SURVEY.md §8f-2).  The reference's timestamp loop is sequential per dimension:
 //     ts = final[addr]; read[k] = ts; final[addr] = ts + 1
-// i.e. read[k] = #{ j < k : addr[j] == addr[k] } and final[a] = #{ k : addr[k] == a }.  Here, per dimension:
-//   1. chunk_hist_kernel : the access sequence is cut into <= 512 chunks; one CTA per chunk histograms its
-//                          addresses in a shared-memory table (two 16-bit counters per word) -> P[chunk][addr];
-//   2. col_scan_kernel   : one thread per address turns the column P[.][addr] into exclusive prefix counts
-//                          (coalesced across addresses) and emits final[addr] = the column total;
-//   3. rank_kernel       : one warp per chunk walks its chunk IN ORDER, 32 accesses at a time:
-//                          read[k] = P[chunk][addr] + (count of addr so far in this chunk, shared-memory table)
-//                                    + (rank among equal addresses inside the warp, __match_any_sync).
-// Integer, order-preserving, bit-identical to the sequential scan.  Needs the 2^log_m-entry table in shared
-// memory as 16-bit counters: log_m <= 16 (every BASELINE config); larger memories use the host scan.
+// i.e. read[k] = #{ j < k : addr[j] == addr[k] } and final[a] = #{ k : addr[k] == a }.  Equivalent, and parallel:
+// STABLY sort the accesses of a dimension by address; the element at sorted position p (address a, original
+// index k) then has read[k] = p - start[a], start = the exclusive scan of the per-address counts (= final).
+// The stable sort is an LSD radix sort with 8-bit digits over packed (address << 32 | k) words, all C dimensions
+// in the same launches (blockIdx.y = dimension):
+//   extract_kernel   column `dim` of the row-major index matrix -> packed words (zero-padded to s, densified.rs:33-37),
+//                    this rank's shard of dim, per-address counts (RED atomics)
+//   per 8-bit digit (ceil(log_m / 8) passes):
+//     radix_hist_kernel     digit histogram of every tile of 2048 elements -> H[dim][bin][tile]
+//     scan_*_kernel         exclusive scan of H in (bin, tile) order = where each tile's run of each digit starts
+//     radix_scatter_kernel  every tile IN ORDER, 256 elements per step: rank among equal digits by __match_any_sync
+//                           inside the warp + warp-count prefix across the 8 warps + the tile's running count
+//   scan_*_kernel    start[a] from the counts; final_ts (this rank's shard) = the counts
+//   read_kernel      read[k] = p - start[a] for this rank's k
+// Integer, order-preserving, bit-identical to the sequential scan for every input (skew included: nothing here depends
+// on how the addresses are distributed).  A few launches of ~10-40 us for 2^20 accesses x 4 dimensions where the host
+// scan needs ~3 ms on C threads; no 2^log_m table in shared memory, so any log_m <= 31.
 #include "kernels.cuh"
 
 namespace lb {
 
-static constexpr int kDenseThreads = 1024;
+static constexpr int kRadixThreads = 256;
+static constexpr int kRadixRounds = 8;
+static constexpr int kRadixTile = kRadixThreads * kRadixRounds;  // 2048 elements per tile
+static constexpr uint32_t kDzScanTile = 4096;
 
-// column `dim` of the row-major n x C index matrix (already narrowed to u32 and range-checked on the host while
-// staging it into pinned memory), zero-padded to s (densified.rs:33-37)
+// ---------------------------------------------------------------------------------------------- extract
+// idx: n x C u32 row-major (already narrowed and range-checked on the host while staging it into pinned memory)
 __global__ void __launch_bounds__(256)
-    extract_dim_kernel(const uint32_t* idx, size_t n, size_t s, int C, int dim, uint32_t* addr) {
-  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < s; k += (size_t)gridDim.x * blockDim.x)
-    addr[k] = k < n ? idx[k * C + dim] : 0u;
+    dz_extract_kernel(const uint32_t* idx, size_t n, size_t s, int C, uint32_t m, int G, int g, unsigned long long* packed,
+                      uint32_t* count, uint32_t* dim_loc_base, size_t dim_stride) {
+  const int dim = blockIdx.y;
+  unsigned long long* out = packed + (size_t)dim * s;
+  uint32_t* cnt = count + (size_t)dim * m;
+  uint32_t* dim_loc = dim_loc_base + (size_t)dim * dim_stride;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < s; k += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t a = k < n ? idx[k * C + dim] : 0u;
+    out[k] = ((unsigned long long)a << 32) | (unsigned long long)k;
+    atomicAdd(cnt + a, 1u);
+    if ((int)(k % G) == g) dim_loc[k / G] = a;
+  }
 }
 
-__global__ void __launch_bounds__(kDenseThreads)
-    chunk_hist_kernel(const uint32_t* addr, size_t B, uint32_t m, uint32_t* P) {
-  extern __shared__ uint32_t tab[];  // m/2 words, two 16-bit counters each (B <= 32768 so a counter cannot overflow)
-  const uint32_t words = (m + 1) / 2;
-  for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) tab[w] = 0;
+// ---------------------------------------------------------------------------------------------- radix pass
+// H[dim][bin][tile]
+__global__ void __launch_bounds__(kRadixThreads)
+    dz_radix_hist_kernel(const unsigned long long* in, size_t s, int shift, uint32_t ntiles, uint32_t* H) {
+  __shared__ uint32_t h[256];
+  const int dim = blockIdx.y;
+  const uint32_t tile = blockIdx.x, t = threadIdx.x;
+  h[t] = 0;
   __syncthreads();
-  const uint32_t* a = addr + (size_t)blockIdx.x * B;
-  for (size_t k = threadIdx.x; k < B; k += blockDim.x) {
-    uint32_t x = a[k];
-    atomicAdd(&tab[x >> 1], (x & 1) ? 0x10000u : 1u);
+  const unsigned long long* src = in + (size_t)dim * s + (size_t)tile * kRadixTile;
+  const size_t left = s - (size_t)tile * kRadixTile;
+#pragma unroll
+  for (int r = 0; r < kRadixRounds; r++) {
+    const size_t i = (size_t)r * kRadixThreads + t;
+    if (i < left) atomicAdd(&h[(uint32_t)(src[i] >> shift) & 0xffu], 1u);
   }
   __syncthreads();
-  uint32_t* row = P + (size_t)blockIdx.x * m;
-  for (uint32_t x = threadIdx.x; x < m; x += blockDim.x) row[x] = (tab[x >> 1] >> ((x & 1) * 16)) & 0xffffu;
+  H[((size_t)dim * 256 + t) * ntiles + tile] = h[t];
 }
-
-// P[c][a] <- sum_{c' < c} P[c'][a];  final_ts (this rank's shard: addresses a = i*G + g) <- column total
-__global__ void __launch_bounds__(256)
-    col_scan_kernel(uint32_t* P, size_t nchunks, uint32_t m, int G, int g, uint32_t* final_loc) {
-  uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= m) return;
-  uint32_t run = 0;
-  for (size_t c = 0; c < nchunks; c++) {
-    uint32_t v = P[c * m + a];
-    P[c * m + a] = run;
-    run += v;
-  }
-  if ((int)(a % G) == g) final_loc[a / G] = run;
-}
-
-// one warp per chunk; writes this rank's shard of dim / read (access k is local iff k % G == g, at k / G).
-// Two different addresses can share a table WORD (x >> 1): their leaders would race on the read-modify-write above.
-// Serialise the two halves: even addresses first, then odd ones.
-__global__ void __launch_bounds__(32)
-    rank_kernel(const uint32_t* addr, size_t B, uint32_t m, const uint32_t* P, int G, int g, uint32_t* dim_loc,
-                     uint32_t* read_loc) {
-  extern __shared__ uint32_t tab[];
-  const uint32_t words = (m + 1) / 2;
-  const int lane = threadIdx.x;
-  for (uint32_t w = lane; w < words; w += 32) tab[w] = 0;
-  __syncwarp();
-  const size_t k0 = (size_t)blockIdx.x * B;
-  const uint32_t* prow = P + (size_t)blockIdx.x * m;
-  for (size_t t = 0; t < B; t += 32) {
-    const size_t k = k0 + t + lane;
-    const uint32_t x = addr[k];
-    const unsigned same = __match_any_sync(0xffffffffu, x);
-    const unsigned before = same & ((1u << lane) - 1u);
-    const uint32_t in_chunk = (tab[x >> 1] >> ((x & 1) * 16)) & 0xffffu;
-    const uint32_t ts = prow[x] + in_chunk + __popc(before);
-    __syncwarp();
-    if (before == 0 && (x & 1) == 0) tab[x >> 1] += (uint32_t)__popc(same);
-    __syncwarp();
-    if (before == 0 && (x & 1) == 1) tab[x >> 1] += (uint32_t)__popc(same) << 16;
-    __syncwarp();
-    if ((int)(k % G) == g) {
-      dim_loc[k / G] = x;
-      read_loc[k / G] = ts;
+// stable scatter of one tile; O = exclusive scan of H
+__global__ void __launch_bounds__(kRadixThreads)
+    dz_radix_scatter_kernel(const unsigned long long* in, unsigned long long* out, size_t s, int shift, uint32_t ntiles,
+                            const uint32_t* O) {
+  __shared__ uint32_t run[256];    // where the tile's next element of each digit goes
+  __shared__ uint32_t wc[8][256];  // per-warp digit counts of the current step
+  const int dim = blockIdx.y;
+  const uint32_t tile = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  run[t] = O[((size_t)dim * 256 + t) * ntiles + tile];
+  const unsigned long long* src = in + (size_t)dim * s + (size_t)tile * kRadixTile;
+  unsigned long long* dst = out + (size_t)dim * s;
+  const size_t left = s - (size_t)tile * kRadixTile;
+  for (int r = 0; r < kRadixRounds; r++) {
+#pragma unroll
+    for (int w = 0; w < 8; w++) wc[w][t] = 0;
+    __syncthreads();
+    const size_t i = (size_t)r * kRadixThreads + t;
+    const bool ok = i < left;
+    const unsigned long long e = ok ? src[i] : 0ull;
+    // lanes without an element take a value no real digit has (256 + lane): they match nobody
+    const uint32_t d = ok ? ((uint32_t)(e >> shift) & 0xffu) : 256u + lane;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const uint32_t before = __popc(peers & ((1u << lane) - 1u));
+    if (ok && before == 0) wc[warp][d] = (uint32_t)__popc(peers);
+    __syncthreads();
+    if (ok) {
+      uint32_t pos = run[d] + before;
+      for (uint32_t w = 0; w < warp; w++) pos += wc[w][d];
+      dst[pos] = e;
     }
+    __syncthreads();
+    uint32_t add = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) add += wc[w][t];
+    run[t] += add;
+    __syncthreads();
   }
 }
 
-// function attributes are per device: called from ctx_create for the context's device
-void densify_init_device() {
-  LB_CUDA_CHECK(cudaFuncSetAttribute(chunk_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  LB_CUDA_CHECK(cudaFuncSetAttribute(rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+// ---------------------------------------------------------------------------------------------- scans
+// exclusive scan of `len` counters per dimension (blockIdx.y), in place: tiles of 4096, tile sums, apply
+__global__ void __launch_bounds__(1024)
+    dz_scan_tiles_kernel(uint32_t* data, size_t len, uint32_t ntiles, uint32_t* tile_sums) {
+  __shared__ uint32_t w1[32];
+  uint32_t* v = data + (size_t)blockIdx.y * len;
+  const uint32_t t = threadIdx.x;
+  const size_t base = (size_t)blockIdx.x * kDzScanTile + (size_t)t * 4;
+  uint32_t x[4], a = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    x[k] = base + k < len ? v[base + k] : 0u;
+    a += x[k];
+  }
+  uint32_t ia = a;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t ta = __shfl_up_sync(0xffffffffu, ia, d);
+    if ((t & 31) >= (uint32_t)d) ia += ta;
+  }
+  if ((t & 31) == 31) w1[t >> 5] = ia;
+  __syncthreads();
+  if (t < 32) {
+    uint32_t va = w1[t];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t ta = __shfl_up_sync(0xffffffffu, va, d);
+      if (t >= (uint32_t)d) va += ta;
+    }
+    w1[t] = va;
+  }
+  __syncthreads();
+  uint32_t r = ((t >> 5) ? w1[(t >> 5) - 1] : 0u) + ia - a;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (base + k < len) v[base + k] = r;
+    r += x[k];
+  }
+  if (t == 1023) tile_sums[(size_t)blockIdx.y * ntiles + blockIdx.x] = w1[31];
 }
-bool densify_gpu_supported(size_t s, size_t log_m) { return log_m <= 16 && s >= 32; }
-size_t densify_chunk(size_t s) {
-  size_t B = s / 512;
-  if (B < 32) B = 32;
-  if (B > 32768) B = 32768;
-  return B;
+__global__ void __launch_bounds__(1024) dz_scan_sums_kernel(uint32_t* tile_sums, uint32_t ntiles) {
+  __shared__ uint32_t s1[1024];
+  uint32_t* ts = tile_sums + (size_t)blockIdx.y * ntiles;
+  const uint32_t t = threadIdx.x;
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < ntiles; base += 1024) {
+    const uint32_t v = base + t < ntiles ? ts[base + t] : 0u;
+    s1[t] = v;
+    __syncthreads();
+    for (uint32_t d = 1; d < 1024; d <<= 1) {
+      uint32_t x = 0;
+      if (t >= d) x = s1[t - d];
+      __syncthreads();
+      s1[t] += x;
+      __syncthreads();
+    }
+    if (base + t < ntiles) ts[base + t] = carry + s1[t] - v;
+    carry += s1[1023];
+    __syncthreads();
+  }
 }
-// d_idx: n x C u32 on the device.  Scratch: d_addr (s u32), d_P (nchunks * m u32).  Outputs are this rank's shards.
-int launch_densify_dim(const uint32_t* d_idx, size_t n, size_t s, int C, int dim, size_t log_m, int G, int g,
-                       uint32_t* d_addr, uint32_t* d_P, uint32_t* dim_loc, uint32_t* read_loc, uint32_t* final_loc,
-                       cudaStream_t st) {
-  const uint32_t m = 1u << log_m;
-  const size_t B = densify_chunk(s), nchunks = s / B;
-  const size_t smem = (size_t)((m + 1) / 2) * 4;
-  size_t eb = (s + 255) / 256;
-  if (eb > (size_t)kNumSMs * 8) eb = kNumSMs * 8;
-  extract_dim_kernel<<<(unsigned)eb, 256, 0, st>>>(d_idx, n, s, C, dim, d_addr);
-  chunk_hist_kernel<<<(unsigned)nchunks, kDenseThreads, smem, st>>>(d_addr, B, m, d_P);
-  col_scan_kernel<<<(m + 255) / 256, 256, 0, st>>>(d_P, nchunks, m, G, g, final_loc);
-  rank_kernel<<<(unsigned)nchunks, 32, smem, st>>>(d_addr, B, m, d_P, G, g, dim_loc, read_loc);
+__global__ void __launch_bounds__(1024)
+    dz_scan_apply_kernel(uint32_t* data, size_t len, uint32_t ntiles, const uint32_t* tile_sums) {
+  uint32_t* v = data + (size_t)blockIdx.y * len;
+  const uint32_t o = tile_sums[(size_t)blockIdx.y * ntiles + blockIdx.x];
+  const size_t base = (size_t)blockIdx.x * kDzScanTile + (size_t)threadIdx.x * 4;
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (base + k < len) v[base + k] += o;
+}
+static int scan_exclusive(uint32_t* data, size_t len, int C, uint32_t* tile_sums, cudaStream_t st) {
+  const uint32_t ntiles = (uint32_t)((len + kDzScanTile - 1) / kDzScanTile);
+  dim3 grid(ntiles, (unsigned)C);
+  dz_scan_tiles_kernel<<<grid, 1024, 0, st>>>(data, len, ntiles, tile_sums);
   LB_LAUNCH_CHECK();
-  return 4;
+  if (ntiles == 1) return 1;  // a single tile per dimension: its scan is the result
+  dz_scan_sums_kernel<<<dim3(1, (unsigned)C), 1024, 0, st>>>(tile_sums, ntiles);
+  LB_LAUNCH_CHECK();
+  dz_scan_apply_kernel<<<grid, 1024, 0, st>>>(data, len, ntiles, tile_sums);
+  LB_LAUNCH_CHECK();
+  return 3;
+}
+
+// ---------------------------------------------------------------------------------------------- results
+// final_ts (this rank's shard: addresses a = i*G + g) = the counts, copied out BEFORE the counts are scanned in place
+__global__ void __launch_bounds__(256)
+    dz_final_kernel(const uint32_t* count, uint32_t m, int G, int g, uint32_t* final_base, size_t final_stride) {
+  const int dim = blockIdx.y;
+  const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= m) return;
+  if ((int)(a % G) == g) final_base[(size_t)dim * final_stride + a / G] = count[(size_t)dim * m + a];
+}
+// read[k] = p - start[a] (this rank's k: k % G == g, stored at k / G)
+__global__ void __launch_bounds__(256)
+    dz_read_kernel(const unsigned long long* sorted, size_t s, uint32_t m, const uint32_t* start, int G, int g, uint32_t* read_base,
+                   size_t read_stride) {
+  const int dim = blockIdx.y;
+  const unsigned long long* src = sorted + (size_t)dim * s;
+  const uint32_t* st = start + (size_t)dim * m;
+  uint32_t* rd = read_base + (size_t)dim * read_stride;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < s; p += (size_t)gridDim.x * blockDim.x) {
+    const unsigned long long e = src[p];
+    const uint32_t a = (uint32_t)(e >> 32), k = (uint32_t)e;
+    if ((int)(k % G) == g) rd[k / G] = (uint32_t)p - st[a];
+  }
+}
+
+// function attributes are per device: called from ctx_create for the context's device (nothing to opt into any more)
+void densify_init_device() {}
+bool densify_gpu_supported(size_t s, size_t log_m) { return log_m >= 1 && log_m <= 31 && s >= 1 && s < ((size_t)1 << 32); }
+// scratch (u32 words) for all C dimensions at once
+size_t densify_scratch_words(size_t s, int C, size_t log_m) {
+  const size_t m = (size_t)1 << log_m;
+  const size_t ntiles = (s + kRadixTile - 1) / kRadixTile;
+  const size_t H = (size_t)C * 256 * ntiles;
+  const size_t scan_len = std::max((size_t)256 * ntiles, m);
+  const size_t tsums = (size_t)C * ((scan_len + kDzScanTile - 1) / kDzScanTile + 1);
+  return 2 * 2 * (size_t)C * s /* two packed arrays of u64 */ + (size_t)C * m /* counts / start */ + H + tsums + 64;
+}
+// d_idx: n x C u32 on the device.  Outputs are this rank's shards: dim_i at dim_loc + i * dim_stride (likewise
+// read, final).  Returns the number of kernels launched.
+int launch_densify(const uint32_t* d_idx, size_t n, size_t s, int C, size_t log_m, int G, int g, uint32_t* scratch,
+                   uint32_t* dim_loc, size_t dim_stride, uint32_t* read_loc, size_t read_stride, uint32_t* final_loc,
+                   size_t final_stride, cudaStream_t st) {
+  const uint32_t m = 1u << log_m;
+  const uint32_t ntiles = (uint32_t)((s + kRadixTile - 1) / kRadixTile);
+  unsigned long long* pa = reinterpret_cast<unsigned long long*>(scratch);
+  unsigned long long* pb = pa + (size_t)C * s;
+  uint32_t* count = reinterpret_cast<uint32_t*>(pb + (size_t)C * s);
+  uint32_t* H = count + (size_t)C * m;
+  uint32_t* tsums = H + (size_t)C * 256 * ntiles;
+  int launches = 0;
+  LB_CUDA_CHECK(cudaMemsetAsync(count, 0, (size_t)C * m * 4, st));
+  {
+    size_t bx = (s + 255) / 256;
+    if (bx > (size_t)kNumSMs * 8) bx = kNumSMs * 8;
+    dz_extract_kernel<<<dim3((unsigned)bx, (unsigned)C), 256, 0, st>>>(d_idx, n, s, C, m, G, g, pa, count, dim_loc, dim_stride);
+    LB_LAUNCH_CHECK();
+    launches++;
+  }
+  unsigned long long *cur = pa, *nxt = pb;
+  for (int shift = 0; shift < (int)log_m; shift += 8) {  // LSD: least significant digit first, every pass stable
+    dz_radix_hist_kernel<<<dim3(ntiles, (unsigned)C), kRadixThreads, 0, st>>>(cur, s, 32 + shift, ntiles, H);
+    LB_LAUNCH_CHECK();
+    launches += 1 + scan_exclusive(H, (size_t)256 * ntiles, C, tsums, st);
+    dz_radix_scatter_kernel<<<dim3(ntiles, (unsigned)C), kRadixThreads, 0, st>>>(cur, nxt, s, 32 + shift, ntiles, H);
+    LB_LAUNCH_CHECK();
+    launches++;
+    std::swap(cur, nxt);
+  }
+  dz_final_kernel<<<dim3((m + 255) / 256, (unsigned)C), 256, 0, st>>>(count, m, G, g, final_loc, final_stride);
+  LB_LAUNCH_CHECK();
+  launches += 1 + scan_exclusive(count, m, C, tsums, st);
+  {
+    size_t bx = (s + 255) / 256;
+    if (bx > (size_t)kNumSMs * 8) bx = kNumSMs * 8;
+    dz_read_kernel<<<dim3((unsigned)bx, (unsigned)C), 256, 0, st>>>(cur, s, m, count, G, g, read_loc, read_stride);
+    LB_LAUNCH_CHECK();
+    launches++;
+  }
+  return launches;
 }
 
 }  // namespace lb

@@ -136,12 +136,14 @@ void launch_bullet_scalars(const fr_t* a, const fr_t* w, size_t n_loc, size_t m,
 void launch_scale_strided(const fr_t* in, fr_t* out, size_t n, size_t stride, size_t off, const fr_t& k, cudaStream_t st);
 void launch_scale(const fr_t* in, fr_t* out, size_t n, const fr_t& k, cudaStream_t st);
 
-// ---- densify on the GPU (densify_kernels.cu; densified.rs:33-56) ----
+// ---- densify on the GPU (densify_kernels.cu; densified.rs:33-56): stable LSD radix sort by address ----
 void densify_init_device();
 bool densify_gpu_supported(size_t s, size_t log_m);
-size_t densify_chunk(size_t s);
-int launch_densify_dim(const uint32_t* d_idx, size_t n, size_t s, int C, int dim, size_t log_m, int G, int g,
-                       uint32_t* d_addr, uint32_t* d_P, uint32_t* dim_loc, uint32_t* read_loc, uint32_t* final_loc,
-                       cudaStream_t st);
+size_t densify_scratch_words(size_t s, int C, size_t log_m);
+// d_idx: n x C u32 (device).  All C dimensions at once; outputs are this rank's shards (rank g of G: accesses k = i*G + g,
+// addresses a = i*G + g): dim_i at dim_loc + i*dim_stride, read_i at read_loc + i*read_stride, final_i likewise.
+int launch_densify(const uint32_t* d_idx, size_t n, size_t s, int C, size_t log_m, int G, int g, uint32_t* scratch,
+                   uint32_t* dim_loc, size_t dim_stride, uint32_t* read_loc, size_t read_stride, uint32_t* final_loc,
+                   size_t final_stride, cudaStream_t st);
 
 }  // namespace lb

@@ -66,7 +66,9 @@ struct MsmLargePlan {
   size_t n = 0;
   int nbits = 0, c = 0, nw = 0;  // widest scalar, window bits, windows
   uint32_t NB = 0, NB1 = 0;      // buckets per window (|digit| = 1..NB), NB + 1
-  uint32_t T2 = 0, L = 0, lgL = 0;  // bucket reduction: T2 blocks of L buckets per window
+  int nlev = 0;                  // bucket reduction: levels of running sums over groups of lev_L items
+  uint32_t lev_L[8] = {}, lev_n[8] = {};  // group size and number of groups (outputs) per level
+  size_t level_pts = 0;          // sum of lev_n
   uint32_t S = 0;                // entries per accumulation unit (a larger bucket is split)
   uint32_t total = 0;            // nw * NB1 counters
   size_t max_entries = 0, max_units = 0;

@@ -8,19 +8,20 @@
 //   2. msm_hist_kernel     signed digits by the offset trick (digit_w = c-bit field of s + sum_w 2^(c-1) 2^(cw), minus
 //                          2^(c-1): no carry chain, msm/mod.rs:277-316 yields the same digits), histogram of
 //                          (window, |digit|) with RED atomics
-//   3. msm_scan_kernel     exclusive scan -> bucket offsets; a bucket with more than S entries (skewed scalars) is
-//                          split into units of <= S entries so that no thread walks a long chain
+//   3. msm_scan_*_kernel   exclusive scan (tiles, tile sums, apply) -> bucket offsets; a bucket with more than S entries
+//                          (skewed scalars) is split into units of <= S entries so that no thread walks a long chain
 //   4. msm_scatter_kernel  counting-sort scatter of (term | sign) by (window, bucket), one window at a time so that
 //                          the window's slice of the list stays in L2
 //   5. msm_accum_kernel    one THREAD per unit: a chain of mixed additions over its entries (7 Fq mul each), the
-//                          next entry's 96 B in flight during the current addition
-//   6. msm_r1_kernel       bucket reduction sum_b b * B_b, level 1: a thread per L consecutive buckets keeps the
-//                          running sum / weighted sum of msm/mod.rs:139-145 locally
-//      msm_r2_kernel       level 2: one CTA per window combines the L-blocks with a tree that carries
-//                          (sum, index-weighted sum): w = w_l + w_r + h * sum_r, h = 2^k by k doublings; then the
-//                          window's weight 2^(c w) by c*w doublings (msm/mod.rs:150-163 does the same c doublings per
-//                          window, serially over the windows)
-//   7. msm_final_kernel    adds the window totals, normalises.
+//                          next entry's 96 B in flight during the current addition;
+//      msm_unit_combine    the units of a split bucket are added by one warp per bucket (none for uniform scalars)
+//   6. msm_wsum_kernel     bucket reduction sum_b b * B_b: the running sum / weighted sum of msm/mod.rs:139-145 over
+//                          groups of 16, applied recursively (2^16 buckets -> 4096 -> 256 -> 16 -> 1 groups), so the
+//                          longest dependent chain is 32 additions per level instead of 2^17;
+//      msm_psum_kernel     plain sums of every level's weighted parts
+//   7. msm_final_kernel    per window W = A_0 + 16 (A_1 + 16 (...)), then the window combination sum_w 2^(c w) W_w
+//                          (msm/mod.rs:150-163: c doublings per window, ~250 dependent doublings) by Horner on one QUAD
+//                          of lanes (quad.cuh), then normalisation.
 // Integer-ALU bound: reported as mixed additions/s against the 7.2 G/s the row-commitment kernel reaches.
 // Same group element as msm_bigint_wnaf for every input; outputs are compared after affine normalisation.
 #if defined(__CUDACC__)
@@ -29,6 +30,7 @@
 #endif
 #include "kernels.cuh"
 #include "msm.cuh"
+#include "quad.cuh"
 
 namespace lb {
 
@@ -125,55 +127,115 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------------------------- 3. scan
-// off[i] = sum_{j < i} cnt[j], uoff[i] = sum_{j < i} units(cnt[j]) with units(x) = ceil(x / S); one CTA.
-// totals[0] = number of entries, totals[1] = number of units.
+// off[i] = sum_{j < i} cnt[j], uoff[i] = sum_{j < i} units(cnt[j]) with units(x) = ceil(x / S).  Three small kernels:
+// tiles of 4096 counters scanned by one CTA each (coalesced), the tile sums scanned by one CTA, the tile offsets added.
+// totals[0] = number of entries, totals[1] = number of units, totals[2] = number of multi-unit buckets (filled later).
+static constexpr uint32_t kScanTile = 4096;
 __global__ void __launch_bounds__(1024)
-    msm_scan_kernel(const uint32_t* cnt, uint32_t total, uint32_t S, uint32_t* off, uint32_t* uoff, uint32_t* totals) {
-  __shared__ uint32_t s1[1024], s2[1024];
-  const uint32_t t = threadIdx.x, chunk = (total + 1023u) / 1024u;
-  const uint32_t lo = min(total, t * chunk), hi = min(total, lo + chunk);
-  uint32_t a = 0, b = 0;
-  for (uint32_t i = lo; i < hi; i++) {
-    const uint32_t x = cnt[i];
-    a += x;
-    b += (x + S - 1) / S;
+    msm_scan_tiles_kernel(const uint32_t* cnt, uint32_t total, uint32_t S, uint32_t* off, uint32_t* uoff, uint2* tile_sums) {
+  __shared__ uint32_t w1[32], w2[32];
+  const uint32_t t = threadIdx.x, base = blockIdx.x * kScanTile + t * 4;
+  uint32_t x[4], a = 0, b = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    x[k] = base + k < total ? cnt[base + k] : 0u;
+    a += x[k];
+    b += (x[k] + S - 1) / S;
   }
-  s1[t] = a;
-  s2[t] = b;
-  __syncthreads();
-  for (uint32_t d = 1; d < 1024; d <<= 1) {  // inclusive Hillis-Steele scan
-    uint32_t x1 = 0, x2 = 0;
-    if (t >= d) {
-      x1 = s1[t - d];
-      x2 = s2[t - d];
+  // inclusive scan of (a, b) over the 1024 threads: warp shuffles, then the 32 warp totals
+  uint32_t ia = a, ib = b;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t ta = __shfl_up_sync(0xffffffffu, ia, d), tb = __shfl_up_sync(0xffffffffu, ib, d);
+    if ((t & 31) >= (uint32_t)d) {
+      ia += ta;
+      ib += tb;
     }
+  }
+  if ((t & 31) == 31) {
+    w1[t >> 5] = ia;
+    w2[t >> 5] = ib;
+  }
+  __syncthreads();
+  if (t < 32) {
+    uint32_t va = w1[t], vb = w2[t];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t ta = __shfl_up_sync(0xffffffffu, va, d), tb = __shfl_up_sync(0xffffffffu, vb, d);
+      if (t >= (uint32_t)d) {
+        va += ta;
+        vb += tb;
+      }
+    }
+    w1[t] = va;
+    w2[t] = vb;
+  }
+  __syncthreads();
+  const uint32_t wa = (t >> 5) ? w1[(t >> 5) - 1] : 0u, wb = (t >> 5) ? w2[(t >> 5) - 1] : 0u;
+  uint32_t r1 = wa + ia - a, r2 = wb + ib - b;  // exclusive prefix inside the tile
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (base + k < total) {
+      off[base + k] = r1;
+      uoff[base + k] = r2;
+    }
+    r1 += x[k];
+    r2 += (x[k] + S - 1) / S;
+  }
+  if (t == 1023) tile_sums[blockIdx.x] = make_uint2(w1[31], w2[31]);
+}
+__global__ void __launch_bounds__(1024)
+    msm_scan_sums_kernel(uint2* tile_sums, uint32_t ntiles, uint32_t total, uint32_t* off, uint32_t* uoff, uint32_t* totals) {
+  __shared__ uint32_t s1[1024], s2[1024];
+  const uint32_t t = threadIdx.x;
+  uint32_t carry1 = 0, carry2 = 0;
+  for (uint32_t base = 0; base < ntiles; base += 1024) {  // ntiles <= 1024 in practice: one pass
+    const uint2 v = base + t < ntiles ? tile_sums[base + t] : make_uint2(0u, 0u);
+    s1[t] = v.x;
+    s2[t] = v.y;
     __syncthreads();
-    s1[t] += x1;
-    s2[t] += x2;
+    for (uint32_t d = 1; d < 1024; d <<= 1) {
+      uint32_t x1 = 0, x2 = 0;
+      if (t >= d) {
+        x1 = s1[t - d];
+        x2 = s2[t - d];
+      }
+      __syncthreads();
+      s1[t] += x1;
+      s2[t] += x2;
+      __syncthreads();
+    }
+    if (base + t < ntiles) tile_sums[base + t] = make_uint2(carry1 + s1[t] - v.x, carry2 + s2[t] - v.y);  // exclusive
+    carry1 += s1[1023];
+    carry2 += s2[1023];
     __syncthreads();
   }
-  uint32_t r1 = s1[t] - a, r2 = s2[t] - b;
-  for (uint32_t i = lo; i < hi; i++) {
-    const uint32_t x = cnt[i];
-    off[i] = r1;
-    uoff[i] = r2;
-    r1 += x;
-    r2 += (x + S - 1) / S;
-  }
-  if (t == 1023) {
-    off[total] = s1[1023];
-    uoff[total] = s2[1023];
-    totals[0] = s1[1023];
-    totals[1] = s2[1023];
+  if (t == 0) {
+    off[total] = carry1;
+    uoff[total] = carry2;
+    totals[0] = carry1;
+    totals[1] = carry2;
   }
 }
-// unit -> bucket map
+__global__ void __launch_bounds__(1024)
+    msm_scan_apply_kernel(const uint2* tile_sums, uint32_t total, uint32_t* off, uint32_t* uoff) {
+  const uint2 o = tile_sums[blockIdx.x];
+  const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * 4;
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (base + k < total) {
+      off[base + k] += o.x;
+      uoff[base + k] += o.y;
+    }
+}
+// unit -> bucket map; buckets split into several units are also listed (multi, totals[2]) for the combine kernel
 __global__ void __launch_bounds__(256)
-    msm_unit_map_kernel(const uint32_t* uoff, uint32_t total, uint32_t* unit_bucket) {
+    msm_unit_map_kernel(const uint32_t* uoff, uint32_t total, uint32_t* unit_bucket, uint32_t* multi, uint32_t* totals) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const uint32_t u0 = uoff[i], u1 = uoff[i + 1];
   for (uint32_t u = u0; u < u1; u++) unit_bucket[u] = i;
+  if (u1 - u0 > 1) multi[atomicAdd(totals + 2, 1u)] = i;
 }
 
 // ---------------------------------------------------------------------------------------------- 4. scatter
@@ -219,36 +281,37 @@ __global__ void __launch_bounds__(128)
 
 // ---------------------------------------------------------------------------------------------- 6. bucket reduction
 // A bucket that was split into several units (skewed scalars: e.g. the top window of 20-bit scalars has a handful of
-// non-empty buckets holding all n terms) is combined here, one WARP per bucket: lanes stride over the units, then a
-// shuffle tree; the sum replaces the bucket's first unit.  Buckets with <= 1 unit (all of them for uniform scalars)
-// leave immediately.
+// non-empty buckets holding all n terms) is combined here, one WARP per listed bucket: lanes stride over the units,
+// then a shuffle tree; the sum replaces the bucket's first unit.  Uniform scalars: the list is empty.
 __global__ void __launch_bounds__(256)
-    msm_unit_combine_kernel(pt_ext* unit_sum, const uint32_t* uoff, uint32_t total) {
-  const uint32_t bi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    msm_unit_combine_kernel(pt_ext* unit_sum, const uint32_t* uoff, const uint32_t* multi, const uint32_t* totals) {
+  const uint32_t nmulti = totals[2];
   const int lane = threadIdx.x & 31;
-  if (bi >= total) return;
-  const uint32_t u0 = uoff[bi], u1 = uoff[bi + 1];
-  if (u1 - u0 <= 1) return;  // warp-uniform
-  pt_ext acc = pt_identity();
-  bool any = false;
-  for (uint32_t u = u0 + lane; u < u1; u += 32) {
-    const pt_ext p = ldp(unit_sum + u);
-    acc = any ? pt_add(acc, p) : p;
-    any = true;
-  }
-#pragma unroll 1
-  for (int d = 16; d >= 1; d >>= 1) {
-    pt_ext o;
-#pragma unroll
-    for (int l = 0; l < 8; l++) {
-      o.X.v[l] = __shfl_down_sync(0xffffffffu, acc.X.v[l], d);
-      o.Y.v[l] = __shfl_down_sync(0xffffffffu, acc.Y.v[l], d);
-      o.Z.v[l] = __shfl_down_sync(0xffffffffu, acc.Z.v[l], d);
-      o.T.v[l] = __shfl_down_sync(0xffffffffu, acc.T.v[l], d);
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < nmulti; m += nwarps) {
+    const uint32_t bi = multi[m];
+    const uint32_t u0 = uoff[bi], u1 = uoff[bi + 1];
+    pt_ext acc = pt_identity();
+    bool any = false;
+    for (uint32_t u = u0 + lane; u < u1; u += 32) {
+      const pt_ext p = ldp(unit_sum + u);
+      acc = any ? pt_add(acc, p) : p;
+      any = true;
     }
-    acc = pt_add(acc, o);
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+      pt_ext o;
+#pragma unroll
+      for (int l = 0; l < 8; l++) {
+        o.X.v[l] = __shfl_down_sync(0xffffffffu, acc.X.v[l], d);
+        o.Y.v[l] = __shfl_down_sync(0xffffffffu, acc.Y.v[l], d);
+        o.Z.v[l] = __shfl_down_sync(0xffffffffu, acc.Z.v[l], d);
+        o.T.v[l] = __shfl_down_sync(0xffffffffu, acc.T.v[l], d);
+      }
+      acc = pt_add(acc, o);
+    }
+    if (lane == 0) stp(unit_sum + u0, acc);
   }
-  if (lane == 0) stp(unit_sum + u0, acc);
 }
 // B_b of (window w, bucket b): its first unit (the whole bucket after msm_unit_combine_kernel)
 __device__ __forceinline__ bool bucket_sum(const pt_ext* unit_sum, const uint32_t* uoff, size_t bi, pt_ext& out) {
@@ -257,25 +320,38 @@ __device__ __forceinline__ bool bucket_sum(const pt_ext* unit_sum, const uint32_
   out = ldp(unit_sum + u0);
   return true;
 }
-// thread (w, t): buckets t*L + 1 .. t*L + L.  acc = sum_j j * B_{tL+j}, run = sum_j B_{tL+j}
+// sum_b b * B_b per window by the reference's running sums (msm/mod.rs:139-145), applied recursively so that no
+// thread walks more than L items:
+//   level 0: thread (w, t) walks the buckets t*L+1 .. t*L+L: run = sum B, acc = sum j * B_{tL+j}
+//            => W = sum_t acc_t + L * Y_1,  Y_1 = sum_t t * run_t                      (a weighted sum again, 0-based)
+//   level k: thread (w, u) walks the items u*L .. u*L+L-1 of level k-1's `run`: the same with 0-based weights
+//   ... until one item is left:  W = A_0 + L_0 (A_1 + L_1 (A_2 + ...)),  A_k = the plain sum of level k's `acc`.
 __global__ void __launch_bounds__(128)
-    msm_r1_kernel(const pt_ext* unit_sum, const uint32_t* uoff, int nw, uint32_t NB1, uint32_t L, uint32_t T2, pt_ext* r1_acc,
-                  pt_ext* r1_run) {
-  const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= (uint32_t)nw * T2) return;
-  const uint32_t w = id / T2, t = id - w * T2;
+    msm_wsum_kernel(const pt_ext* unit_sum, const uint32_t* uoff, uint32_t NB1, const pt_ext* in_run, int level, int nw,
+                    uint32_t n_in, uint32_t L, pt_ext* out_run, pt_ext* out_acc) {
+  const uint32_t n_out = n_in / L, id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= (uint32_t)nw * n_out) return;
+  const uint32_t w = id / n_out, t = id - w * n_out;
   pt_ext run = pt_identity(), acc = pt_identity();
   bool any = false;
-  for (uint32_t j = L; j >= 1; j--) {
+  for (uint32_t jj = L; jj >= 1; jj--) {
+    const uint32_t j = jj - 1;  // item t*L + j, weight j + 1 at level 0 (buckets are 1-based), j above
     pt_ext B;
-    if (bucket_sum(unit_sum, uoff, (size_t)w * NB1 + (size_t)t * L + j, B)) {
+    bool have;
+    if (level == 0) {
+      have = bucket_sum(unit_sum, uoff, (size_t)w * NB1 + (size_t)t * L + j + 1, B);
+    } else {
+      B = ldp(in_run + (size_t)w * n_in + (size_t)t * L + j);
+      have = true;
+    }
+    if (have) {
       run = any ? pt_add(run, B) : B;
       any = true;
     }
-    if (any) acc = pt_add(acc, run);
+    if (any && (level == 0 || j > 0)) acc = pt_add(acc, run);
   }
-  stp(r1_acc + id, acc);
-  stp(r1_run + id, run);
+  stp(out_run + id, run);
+  stp(out_acc + id, acc);
 }
 // shared-memory point storage (SoA): element (coord c, limb l) of point idx at base[(c*8 + l) * n + idx]
 __device__ __forceinline__ void sm_st(uint32_t* base, int n, int idx, const pt_ext& p) {
@@ -298,65 +374,67 @@ __device__ __forceinline__ pt_ext sm_ld(const uint32_t* base, int n, int idx) {
   }
   return p;
 }
-// one CTA per window, T2 threads (a power of two <= 512).  Tree over the L-blocks carrying
-//   x = sum of acc, s = sum of run, y = sum_t t * run_t (index inside the current subtree):
-//   merging [left | right] of h blocks each: y = y_l + y_r + h * s_r.
-// window total = x + L * y, times 2^(c w).
-__global__ void __launch_bounds__(512)
-    msm_r2_kernel(const pt_ext* r1_acc, const pt_ext* r1_run, uint32_t T2, uint32_t lgL, int c, pt_ext* win_total) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t* sx = reinterpret_cast<uint32_t*>(smem_raw);
-  uint32_t* ss = sx + 32 * T2;
-  uint32_t* sy = ss + 32 * T2;
-  const int w = blockIdx.x, t = threadIdx.x, n = (int)T2;
-  pt_ext x = ldp(r1_acc + (size_t)w * T2 + t), s = ldp(r1_run + (size_t)w * T2 + t), y = pt_identity();
-  sm_st(sx, n, t, x);
-  sm_st(ss, n, t, s);
-  sm_st(sy, n, t, y);
+// A[w][k] = the plain sum of level k's acc[w][0 .. n_k): CTA (w, k), 256 threads + shared-memory tree
+struct MsmLevels {
+  const pt_ext* acc[8];
+  uint32_t n[8];
+};
+__global__ void __launch_bounds__(256) msm_psum_kernel(MsmLevels lv, int nlev, pt_ext* A) {
+  __shared__ uint32_t buf[32 * 256];
+  const int w = blockIdx.x, k = blockIdx.y, tid = threadIdx.x;
+  const pt_ext* src = lv.acc[k] + (size_t)w * lv.n[k];
+  pt_ext acc = pt_identity();
+  bool any = false;
+  for (uint32_t i = tid; i < lv.n[k]; i += 256) {
+    const pt_ext p = ldp(src + i);
+    acc = any ? pt_add(acc, p) : p;
+    any = true;
+  }
+  sm_st(buf, 256, tid, acc);
   __syncthreads();
-  int lg = 0;
-  for (uint32_t h = 1; h < T2; h <<= 1, lg++) {
-    const bool act = (t & (2 * h - 1)) == 0;
-    if (act) {
-      const pt_ext xr = sm_ld(sx, n, t + h), sr = sm_ld(ss, n, t + h), yr = sm_ld(sy, n, t + h);
-      pt_ext hs = sr;
-      for (int k = 0; k < lg; k++) hs = pt_dbl(hs);  // h * s_r
-      x = pt_add(x, xr);
-      y = pt_add(pt_add(y, yr), hs);
-      s = pt_add(s, sr);
-    }
-    __syncthreads();
-    if (act) {
-      sm_st(sx, n, t, x);
-      sm_st(ss, n, t, s);
-      sm_st(sy, n, t, y);
+  for (int d = 128; d >= 1; d >>= 1) {
+    if (tid < d) {
+      acc = pt_add(acc, sm_ld(buf, 256, tid + d));
+      sm_st(buf, 256, tid, acc);
     }
     __syncthreads();
   }
-  if (t == 0) {
-    for (uint32_t k = 0; k < lgL; k++) y = pt_dbl(y);  // L * y
-    pt_ext tot = pt_add(x, y);
-    for (int k = 0; k < c * w; k++) tot = pt_dbl(tot);  // 2^(c w)
-    stp(win_total + w, tot);
-  }
+  if (tid == 0) stp(A + (size_t)w * nlev + k, acc);
 }
 // ---------------------------------------------------------------------------------------------- 7. final
+// One warp.  Lane w: W_w = A_0 + L_0 (A_1 + L_1 (...)) (a few doublings).  Then the window combination
+// sum_w 2^(c w) W_w (msm/mod.rs:150-163) by Horner from the top window — c doublings per window, ~250 dependent
+// doublings in all — on ONE QUAD of lanes (quad.cuh: two multiplication levels per doubling instead of a lone
+// thread's ~2000 issued instructions).  Then normalise.
+struct MsmLgL {
+  int v[8];
+};
 __global__ void __launch_bounds__(32)
-    msm_final_kernel(const pt_ext* win_total, int nw, fq_t* out_ext, uint32_t* out_raw) {
-  const int lane = threadIdx.x;
-  pt_ext acc = lane < nw ? ldp(win_total + lane) : pt_identity();
-#pragma unroll 1
-  for (int d = 16; d >= 1; d >>= 1) {
-    pt_ext o;
-#pragma unroll
-    for (int l = 0; l < 8; l++) {
-      o.X.v[l] = __shfl_down_sync(0xffffffffu, acc.X.v[l], d);
-      o.Y.v[l] = __shfl_down_sync(0xffffffffu, acc.Y.v[l], d);
-      o.Z.v[l] = __shfl_down_sync(0xffffffffu, acc.Z.v[l], d);
-      o.T.v[l] = __shfl_down_sync(0xffffffffu, acc.T.v[l], d);
+    msm_final_kernel(const pt_ext* A, int nlev, MsmLgL lgL, int nw, int c, fq_t* out_ext, uint32_t* out_raw) {
+  __shared__ fq_t sw[32 * 4];
+  const int lane = threadIdx.x, role = lane & 3;
+  if (lane < nw) {
+    pt_ext v = ldp(A + (size_t)lane * nlev + (nlev - 1));
+    for (int k = nlev - 2; k >= 0; k--) {
+      for (int d = 0; d < lgL.v[k]; d++) v = pt_dbl(v);
+      v = pt_add(v, ldp(A + (size_t)lane * nlev + k));
     }
-    acc = pt_add(acc, o);
+    sw[lane * 4 + 0] = v.X;
+    sw[lane * 4 + 1] = v.Y;
+    sw[lane * 4 + 2] = v.Z;
+    sw[lane * 4 + 3] = v.T;
   }
+  __syncwarp();
+  fq_t mine = sw[(nw - 1) * 4 + role];  // every quad runs the same chain (uniform control flow); quad 0's result is used
+  for (int w = nw - 2; w >= 0; w--) {
+    for (int d = 0; d < c; d++) mine = quad_dbl(0xffffffffu, lane, mine);
+    mine = quad_add(0xffffffffu, lane, mine, sw + w * 4);
+  }
+  pt_ext acc;
+  acc.X = shfl_fq(0xffffffffu, mine, 0);
+  acc.Y = shfl_fq(0xffffffffu, mine, 1);
+  acc.Z = shfl_fq(0xffffffffu, mine, 2);
+  acc.T = shfl_fq(0xffffffffu, mine, 3);
   if (lane == 0) {
     if (out_raw) {
 #pragma unroll
@@ -463,10 +541,18 @@ MsmLargePlan msm_large_plan(size_t n, unsigned max_bits) {
   if (p.c * p.nw > 9 * 32 - 1) throw std::runtime_error("msm_large: biased scalar wider than 9 limbs");
   p.NB = 1u << (p.c - 1);
   p.NB1 = p.NB + 1;
-  p.T2 = p.NB < 512 ? p.NB : 512;
-  p.L = p.NB / p.T2;
-  p.lgL = 0;
-  while ((1u << p.lgL) < p.L) p.lgL++;
+  // reduction levels: groups of (up to) 16 items until one is left
+  p.nlev = 0;
+  p.level_pts = 0;
+  for (uint32_t items = p.NB; items > 1;) {
+    const uint32_t L = items >= 16 ? 16 : items;
+    if (p.nlev >= 8) throw std::runtime_error("msm_large: too many reduction levels");
+    p.lev_L[p.nlev] = L;
+    p.lev_n[p.nlev] = items / L;
+    p.level_pts += items / L;
+    items /= L;
+    p.nlev++;
+  }
   const size_t avg = (n + p.NB - 1) / p.NB;
   p.S = (uint32_t)std::max<size_t>(64, 4 * avg);
   p.total = (uint32_t)p.nw * p.NB1;
@@ -477,17 +563,16 @@ MsmLargePlan msm_large_plan(size_t n, unsigned max_bits) {
 }
 size_t msm_large_scratch_bytes(const MsmLargePlan& p) {
   size_t b = 0;
-  b += 3 * ((size_t)p.total + 1) * 4 + 16;  // cnt/fill, off, uoff (+ totals)
-  b += (size_t)p.total * 4;
-  b += p.max_entries * 4;                    // entries
-  b += p.max_units * 4;                      // unit_bucket
-  b += p.max_units * sizeof(pt_ext);         // unit_sum
-  b += 2 * (size_t)p.nw * p.T2 * sizeof(pt_ext) + 64 * sizeof(pt_ext);
+  b += 5 * (((size_t)p.total + 1) * 4 + 256);  // cnt, fill, off, uoff, multi
+  b += ((size_t)p.total / kScanTile + 2) * 8 + 256 + 64;  // tile sums, totals
+  b += p.max_entries * 4 + 256;                // entries
+  b += p.max_units * 4 + 256;                  // unit_bucket
+  b += p.max_units * sizeof(pt_ext) + 256;     // unit_sum
+  b += 2 * (size_t)p.nw * p.level_pts * sizeof(pt_ext) + 512;  // run / acc of every level
+  b += (size_t)p.nw * 8 * sizeof(pt_ext) + 256;                // A
   return b + 4096;
 }
-void msm_large_init_device() {
-  LB_CUDA_CHECK(cudaFuncSetAttribute(msm_r2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 32 * 512 * 4));
-}
+void msm_large_init_device() {}
 void launch_msm_large_prep(const fq_t* bases_ark, const fr_t* scalars_mont, size_t n, size_t n_pool, pt_niels* niels,
                            fr_t* canon, unsigned* d_max_bits, cudaStream_t st) {
   size_t b = (n + 255) / 256;
@@ -506,33 +591,43 @@ int launch_msm_large(const MsmLargePlan& p, const pt_niels* niels, const fr_t* c
     s += (bytes + 255) & ~(size_t)255;
     return r;
   };
+  const uint32_t ntiles = (p.total + kScanTile - 1) / kScanTile;
   uint32_t* cnt = (uint32_t*)take(((size_t)p.total + 1) * 4);
   uint32_t* fill = (uint32_t*)take(((size_t)p.total + 1) * 4);
   uint32_t* off = (uint32_t*)take(((size_t)p.total + 1) * 4);
   uint32_t* uoff = (uint32_t*)take(((size_t)p.total + 1) * 4);
+  uint32_t* multi = (uint32_t*)take(((size_t)p.total + 1) * 4);
+  uint2* tile_sums = (uint2*)take(((size_t)ntiles + 1) * 8);
   uint32_t* totals = (uint32_t*)take(16);
   uint32_t* entries = (uint32_t*)take(p.max_entries * 4);
   uint32_t* unit_bucket = (uint32_t*)take(p.max_units * 4);
   pt_ext* unit_sum = (pt_ext*)take(p.max_units * sizeof(pt_ext));
-  pt_ext* r1_acc = (pt_ext*)take((size_t)p.nw * p.T2 * sizeof(pt_ext));
-  pt_ext* r1_run = (pt_ext*)take((size_t)p.nw * p.T2 * sizeof(pt_ext));
-  pt_ext* win_total = (pt_ext*)take(64 * sizeof(pt_ext));
+  pt_ext* lev_run = (pt_ext*)take((size_t)p.nw * p.level_pts * sizeof(pt_ext));
+  pt_ext* lev_acc = (pt_ext*)take((size_t)p.nw * p.level_pts * sizeof(pt_ext));
+  pt_ext* A = (pt_ext*)take((size_t)p.nw * 8 * sizeof(pt_ext));
   BiasOff bo;  // sum_{w < nw} 2^(c-1) * 2^(c w)
   for (int l = 0; l < 9; l++) bo.v[l] = 0;
   for (int w = 0; w < p.nw; w++) {
     const int bit = w * p.c + p.c - 1;
     bo.v[bit >> 5] |= 1u << (bit & 31);
   }
+  int launches = 0;
   LB_CUDA_CHECK(cudaMemsetAsync(cnt, 0, ((size_t)p.total + 1) * 4, st));
   LB_CUDA_CHECK(cudaMemsetAsync(fill, 0, ((size_t)p.total + 1) * 4, st));
+  LB_CUDA_CHECK(cudaMemsetAsync(totals, 0, 16, st));
   size_t b = (p.n + 255) / 256;
   if (b > (size_t)kNumSMs * 8) b = kNumSMs * 8;
   msm_hist_kernel<<<(unsigned)b, 256, 0, st>>>(canon, p.n, p.c, p.nw, p.NB1, bo, cnt);
   LB_LAUNCH_CHECK();
-  msm_scan_kernel<<<1, 1024, 0, st>>>(cnt, p.total, p.S, off, uoff, totals);
+  msm_scan_tiles_kernel<<<ntiles, 1024, 0, st>>>(cnt, p.total, p.S, off, uoff, tile_sums);
   LB_LAUNCH_CHECK();
-  msm_unit_map_kernel<<<(p.total + 255) / 256, 256, 0, st>>>(uoff, p.total, unit_bucket);
+  msm_scan_sums_kernel<<<1, 1024, 0, st>>>(tile_sums, ntiles, p.total, off, uoff, totals);
   LB_LAUNCH_CHECK();
+  msm_scan_apply_kernel<<<ntiles, 1024, 0, st>>>(tile_sums, p.total, off, uoff);
+  LB_LAUNCH_CHECK();
+  msm_unit_map_kernel<<<(p.total + 255) / 256, 256, 0, st>>>(uoff, p.total, unit_bucket, multi, totals);
+  LB_LAUNCH_CHECK();
+  launches += 5;
   {
     size_t bx = (p.n + 255) / 256;
     if (bx > (size_t)kNumSMs * 4) bx = kNumSMs * 4;
@@ -543,16 +638,44 @@ int launch_msm_large(const MsmLargePlan& p, const pt_niels* niels, const fr_t* c
   msm_accum_kernel<<<(unsigned)((p.max_units + 127) / 128), 128, 0, st>>>(niels, entries, cnt, off, uoff, unit_bucket, totals, p.S,
                                                                         unit_sum);
   LB_LAUNCH_CHECK();
-  msm_unit_combine_kernel<<<(unsigned)(((size_t)p.total * 32 + 255) / 256), 256, 0, st>>>(unit_sum, uoff, p.total);
+  msm_unit_combine_kernel<<<kNumSMs * 4, 256, 0, st>>>(unit_sum, uoff, multi, totals);
   LB_LAUNCH_CHECK();
-  msm_r1_kernel<<<(unsigned)(((size_t)p.nw * p.T2 + 127) / 128), 128, 0, st>>>(unit_sum, uoff, p.nw, p.NB1, p.L, p.T2, r1_acc,
-                                                                               r1_run);
+  launches += 3;
+  // bucket reduction, level by level
+  MsmLevels lv;
+  MsmLgL lg;
+  size_t pts_off = 0;
+  const pt_ext* prev_run = nullptr;
+  uint32_t items = p.NB;
+  for (int k = 0; k < p.nlev; k++) {
+    const uint32_t L = p.lev_L[k], n_out = p.lev_n[k];
+    pt_ext* run_k = lev_run + (size_t)p.nw * pts_off;
+    pt_ext* acc_k = lev_acc + (size_t)p.nw * pts_off;
+    msm_wsum_kernel<<<(unsigned)(((size_t)p.nw * n_out + 127) / 128), 128, 0, st>>>(unit_sum, uoff, p.NB1, prev_run, k, p.nw, items, L,
+                                                                                   run_k, acc_k);
+    LB_LAUNCH_CHECK();
+    launches++;
+    lv.acc[k] = acc_k;
+    lv.n[k] = n_out;
+    lg.v[k] = 0;
+    while ((1u << lg.v[k]) < L) lg.v[k]++;
+    prev_run = run_k;
+    pts_off += n_out;
+    items = n_out;
+  }
+  for (int k = p.nlev; k < 8; k++) {
+    lv.acc[k] = nullptr;
+    lv.n[k] = 0;
+    lg.v[k] = 0;
+  }
+  {
+    dim3 grid((unsigned)p.nw, (unsigned)p.nlev);
+    msm_psum_kernel<<<grid, 256, 0, st>>>(lv, p.nlev, A);
+    LB_LAUNCH_CHECK();
+  }
+  msm_final_kernel<<<1, 32, 0, st>>>(A, p.nlev, lg, p.nw, p.c, out_ext, out_raw);
   LB_LAUNCH_CHECK();
-  msm_r2_kernel<<<p.nw, p.T2, 3 * 32 * (size_t)p.T2 * 4, st>>>(r1_acc, r1_run, p.T2, p.lgL, p.c, win_total);
-  LB_LAUNCH_CHECK();
-  msm_final_kernel<<<1, 32, 0, st>>>(win_total, p.nw, out_ext, out_raw);
-  LB_LAUNCH_CHECK();
-  return 9;
+  return launches + 2;
 }
 
 }  // namespace lb

@@ -466,12 +466,14 @@ Dense* densify(Ctx* c, const uint64_t* indices, size_t n, size_t C, size_t log_m
   {
     const char* hd = getenv("LASSO_B200_HOST_DENSIFY");
     const char* gd = getenv("LASSO_B200_GPU_DENSIFY");
-    // measured on B200 (profiles/README.md): the device path wins from 2^22 lookups up (53 vs 73 ms at 2^24) and
-    // whenever one proof is sharded (no replicated host scan); below that the 3 ms host scan + pinned upload wins
-    const bool want_gpu = (gd && gd[0] == '1') || s >= ((size_t)1 << 22) || G > 1;
+    // The device path (a stable radix sort by address, densify_kernels.cu) replaces the C host threads of the
+    // sequential scan: ~0.5 ms of kernels instead of ~3 ms of host time at 2^20 lookups, and nothing that slows
+    // down when several processes share the host (one process per GPU).  Tiny inputs stay on the host (the ~20
+    // launches cost more than the scan).
+    const bool want_gpu = (gd && gd[0] == '1') || s >= ((size_t)1 << 15) || G > 1;
     if (densify_gpu_supported(s, log_m) && want_gpu && !(hd && hd[0] == '1')) {
-      // GPU path (densify_kernels.cu): upload the raw index matrix, derive dim / read / final on the device.
-      // When one proof is sharded every rank does this for the whole sequence and stores only its shard.
+      // upload the raw index matrix, derive dim / read / final on the device.  When one proof is sharded every rank
+      // does this for the whole sequence and stores only its shard.
       d->d_l_u32.alloc(c, nl);
       d->d_m_u32.alloc(c, nm);
       d->d_l_fr.alloc(c, nl);
@@ -503,16 +505,12 @@ Dense* densify(Ctx* c, const uint64_t* indices, size_t n, size_t C, size_t log_m
             return nullptr;
           }
       }
-      DBuf<uint32_t> d_idx(c, n * C);
+      DBuf<uint32_t> d_idx(c, n * C), scratch(c, densify_scratch_words(s, (int)C, log_m));
       LB_CUDA_CHECK(cudaMemcpyAsync(d_idx.p, stage, n * C * sizeof(uint32_t), cudaMemcpyHostToDevice, c->st));
-      const size_t B = densify_chunk(s);
-      DBuf<uint32_t> d_addr(c, s), d_P(c, (s / B) * m);
       if (nl > 2 * C * s_loc) LB_CUDA_CHECK(cudaMemsetAsync(d->d_l_u32.p + 2 * C * s_loc, 0, (nl - 2 * C * s_loc) * 4, c->st));
       if (nm > C * m_loc) LB_CUDA_CHECK(cudaMemsetAsync(d->d_m_u32.p + C * m_loc, 0, (nm - C * m_loc) * 4, c->st));
-      for (size_t i = 0; i < C; i++)
-        g_launches += launch_densify_dim(d_idx.p, n, s, (int)C, (int)i, log_m, (int)G, (int)gr, d_addr.p, d_P.p,
-                                         d->d_l_u32.p + i * s_loc, d->d_l_u32.p + (C + i) * s_loc,
-                                         d->d_m_u32.p + i * m_loc, c->st);
+      g_launches += launch_densify(d_idx.p, n, s, (int)C, log_m, (int)G, (int)gr, scratch.p, d->d_l_u32.p, s_loc,
+                                   d->d_l_u32.p + C * s_loc, s_loc, d->d_m_u32.p, m_loc, c->st);
       launch_from_u32(d->d_l_u32.p, d->d_l_fr.p, nl, c->st);  // DensePolynomial::from_usize + merge
       launch_from_u32(d->d_m_u32.p, d->d_m_fr.p, nm, c->st);
       g_launches += 2;
