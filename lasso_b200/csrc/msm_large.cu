@@ -30,7 +30,6 @@
 #endif
 #include "kernels.cuh"
 #include "msm.cuh"
-#include "quad.cuh"
 
 namespace lb {
 
@@ -402,60 +401,8 @@ __global__ void __launch_bounds__(256) msm_psum_kernel(MsmLevels lv, int nlev, p
   if (tid == 0) stp(A + (size_t)w * nlev + k, acc);
 }
 // ---------------------------------------------------------------------------------------------- 7. final
-// One warp.  Lane w: W_w = A_0 + L_0 (A_1 + L_1 (...)) (a few doublings).  Then the window combination
-// sum_w 2^(c w) W_w (msm/mod.rs:150-163) by Horner from the top window — c doublings per window, ~250 dependent
-// doublings in all — on ONE QUAD of lanes (quad.cuh: two multiplication levels per doubling instead of a lone
-// thread's ~2000 issued instructions).  Then normalise.
-struct MsmLgL {
-  int v[8];
-};
-__global__ void __launch_bounds__(32)
-    msm_final_kernel(const pt_ext* A, int nlev, MsmLgL lgL, int nw, int c, fq_t* out_ext, uint32_t* out_raw) {
-  __shared__ fq_t sw[32 * 4];
-  const int lane = threadIdx.x, role = lane & 3;
-  if (lane < nw) {
-    pt_ext v = ldp(A + (size_t)lane * nlev + (nlev - 1));
-    for (int k = nlev - 2; k >= 0; k--) {
-      for (int d = 0; d < lgL.v[k]; d++) v = pt_dbl(v);
-      v = pt_add(v, ldp(A + (size_t)lane * nlev + k));
-    }
-    sw[lane * 4 + 0] = v.X;
-    sw[lane * 4 + 1] = v.Y;
-    sw[lane * 4 + 2] = v.Z;
-    sw[lane * 4 + 3] = v.T;
-  }
-  __syncwarp();
-  fq_t mine = sw[(nw - 1) * 4 + role];  // every quad runs the same chain (uniform control flow); quad 0's result is used
-  for (int w = nw - 2; w >= 0; w--) {
-    for (int d = 0; d < c; d++) mine = quad_dbl(0xffffffffu, lane, mine);
-    mine = quad_add(0xffffffffu, lane, mine, sw + w * 4);
-  }
-  pt_ext acc;
-  acc.X = shfl_fq(0xffffffffu, mine, 0);
-  acc.Y = shfl_fq(0xffffffffu, mine, 1);
-  acc.Z = shfl_fq(0xffffffffu, mine, 2);
-  acc.T = shfl_fq(0xffffffffu, mine, 3);
-  if (lane == 0) {
-    if (out_raw) {
-#pragma unroll
-      for (int l = 0; l < 8; l++) {
-        out_raw[l] = acc.X.v[l];
-        out_raw[8 + l] = acc.Y.v[l];
-        out_raw[16 + l] = acc.Z.v[l];
-        out_raw[24 + l] = acc.T.v[l];
-      }
-    }
-    if (out_ext) {
-      fq_t x, y;
-      pt_to_affine_canonical(acc, x, y);
-      out_ext[0] = fq_to_ark(x);
-      out_ext[1] = fq_to_ark(y);
-      out_ext[2] = fq_to_ark(fq_mul(x, y));
-      out_ext[3] = fq_to_ark(fq_one());
-    }
-  }
-}
-
+// msm_final.cu (its own translation unit: a single warp walks ~250 dependent doublings there, and wants the field
+// multiplication inlined instead of the out-of-line calls that keep the big kernels of this file small)
 // ---------------------------------------------------------------------------------------------- naive cross-check
 // An independent evaluation of the same sum for the parity tests at sizes the CPU oracle cannot reach: every term
 // by plain double-and-add over the bits of its canonical scalar (no digits, no buckets, no tables), then a tree sum.
@@ -643,7 +590,9 @@ int launch_msm_large(const MsmLargePlan& p, const pt_niels* niels, const fr_t* c
   launches += 3;
   // bucket reduction, level by level
   MsmLevels lv;
-  MsmLgL lg;
+  struct {
+    int v[8];
+  } lg;
   size_t pts_off = 0;
   const pt_ext* prev_run = nullptr;
   uint32_t items = p.NB;
@@ -673,8 +622,7 @@ int launch_msm_large(const MsmLargePlan& p, const pt_niels* niels, const fr_t* c
     msm_psum_kernel<<<grid, 256, 0, st>>>(lv, p.nlev, A);
     LB_LAUNCH_CHECK();
   }
-  msm_final_kernel<<<1, 32, 0, st>>>(A, p.nlev, lg, p.nw, p.c, out_ext, out_raw);
-  LB_LAUNCH_CHECK();
+  launch_msm_final(A, p.nlev, lg.v, p.nw, p.c, out_ext, out_raw, st);
   return launches + 2;
 }
 

@@ -200,6 +200,7 @@ Ctx* ctx_create(int device) {
   msm_large_init_device();
   densify_init_device();
   LB_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming));
+  LB_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming));
   const char* sp = getenv("LASSO_B200_SPANS");
   c->span_sync = sp && sp[0] == '1';
   return c.release();
@@ -213,6 +214,7 @@ void ctx_destroy(Ctx* c) {
   cudaFree(c->d_eq_scratch);
   cudaFree(c->d_flag);
   if (c->ev_aux) cudaEventDestroy(c->ev_aux);
+  if (c->ev_stage) cudaEventDestroy(c->ev_stage);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->h_mapped) cudaFreeHost(c->h_mapped);
   if (c->h_pub && c->h_pub_owned) cudaFreeHost(c->h_pub);
@@ -478,35 +480,58 @@ Dense* densify(Ctx* c, const uint64_t* indices, size_t n, size_t C, size_t log_m
       d->d_m_u32.alloc(c, nm);
       d->d_l_fr.alloc(c, nl);
       d->d_m_fr.alloc(c, nm);
-      // narrow usize -> u32 (and range-check, densified.rs:46) while staging into pinned memory: half the
-      // PCIe bytes and a full-rate copy; a few host threads keep up with the link
+      // narrow usize -> u32 (and range-check, densified.rs:46) while staging into pinned memory: half the PCIe
+      // bytes and a full-rate copy.  Pipelined: the matrix is cut into pieces, a few host threads narrow them
+      // round-robin, and the upload of a piece starts as soon as it is staged (the copy of the early pieces overlaps
+      // the narrowing of the later ones).
+      if (c->stage_busy) {  // the previous call's upload may still be reading the staging buffer
+        LB_CUDA_CHECK(cudaEventSynchronize(c->ev_stage));
+        c->stage_busy = false;
+      }
       uint32_t* stage = c->stage(n * C);
+      DBuf<uint32_t> d_idx(c, n * C), scratch(c, densify_scratch_words(s, (int)C, log_m));
       {
-        const size_t total = n * C, nthreads = total >= (1u << 20) ? 4 : 1;
-        std::vector<int> bad(nthreads, 0);
+        const size_t total = n * C;
+        const size_t npieces = total >= (1u << 20) ? 16 : 1, nthreads = npieces > 1 ? 4 : 1;
+        std::vector<std::atomic<int>> done(npieces);
+        for (auto& f : done) f.store(0);
+        std::atomic<int> bad{0};
         auto conv = [&](size_t t) {
-          size_t lo = total * t / nthreads, hi = total * (t + 1) / nthreads;
-          for (size_t k = lo; k < hi; k++) {
-            uint64_t a = indices[k];
-            if (a >= m) {
-              bad[t] = 1;
-              a = 0;
+          for (size_t p = t; p < npieces; p += nthreads) {
+            const size_t lo = total * p / npieces, hi = total * (p + 1) / npieces;
+            int b = 0;
+            for (size_t k = lo; k < hi; k++) {
+              uint64_t a = indices[k];
+              if (a >= m) {
+                b = 1;
+                a = 0;
+              }
+              stage[k] = (uint32_t)a;
             }
-            stage[k] = (uint32_t)a;
+            if (b) bad.store(1);
+            done[p].store(1, std::memory_order_release);
           }
         };
         std::vector<std::thread> th;
         for (size_t t = 1; t < nthreads; t++) th.emplace_back(conv, t);
-        conv(0);
+        if (nthreads == 1) conv(0);
+        std::thread t0;
+        if (nthreads > 1) t0 = std::thread(conv, 0);
+        for (size_t p = 0; p < npieces; p++) {  // this thread feeds the copy engine in order
+          while (!done[p].load(std::memory_order_acquire)) __builtin_ia32_pause();
+          const size_t lo = total * p / npieces, hi = total * (p + 1) / npieces;
+          LB_CUDA_CHECK(cudaMemcpyAsync(d_idx.p + lo, stage + lo, (hi - lo) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->st));
+        }
+        if (t0.joinable()) t0.join();
         for (auto& t : th) t.join();
-        for (int bflag : bad)
-          if (bflag) {
-            *err = 3;
-            return nullptr;
-          }
+        LB_CUDA_CHECK(cudaEventRecord(c->ev_stage, c->st));
+        c->stage_busy = true;
+        if (bad.load()) {
+          c->sync();
+          *err = 3;
+          return nullptr;
+        }
       }
-      DBuf<uint32_t> d_idx(c, n * C), scratch(c, densify_scratch_words(s, (int)C, log_m));
-      LB_CUDA_CHECK(cudaMemcpyAsync(d_idx.p, stage, n * C * sizeof(uint32_t), cudaMemcpyHostToDevice, c->st));
       if (nl > 2 * C * s_loc) LB_CUDA_CHECK(cudaMemsetAsync(d->d_l_u32.p + 2 * C * s_loc, 0, (nl - 2 * C * s_loc) * 4, c->st));
       if (nm > C * m_loc) LB_CUDA_CHECK(cudaMemsetAsync(d->d_m_u32.p + C * m_loc, 0, (nm - C * m_loc) * 4, c->st));
       g_launches += launch_densify(d_idx.p, n, s, (int)C, log_m, (int)G, (int)gr, scratch.p, d->d_l_u32.p, s_loc,
@@ -514,11 +539,15 @@ Dense* densify(Ctx* c, const uint64_t* indices, size_t n, size_t C, size_t log_m
       launch_from_u32(d->d_l_u32.p, d->d_l_fr.p, nl, c->st);  // DensePolynomial::from_usize + merge
       launch_from_u32(d->d_m_u32.p, d->d_m_fr.p, nm, c->st);
       g_launches += 2;
-      c->sync();  // the pinned staging buffer is reused by the next call
+      // no stream sync here: everything downstream is stream-ordered, and the staging buffer is guarded by ev_stage
       return d.release();
     }
   }
   // host path (memories larger than 2^16 cells): pinned staging, reused across calls: no per-call page faults, and the upload runs at full PCIe rate
+  if (c->stage_busy) {
+    LB_CUDA_CHECK(cudaEventSynchronize(c->ev_stage));
+    c->stage_busy = false;
+  }
   uint32_t* l_host = c->stage(nl + nm + (G > 1 ? (2 * s + m) * C : 0));
   uint32_t* m_host = l_host + nl;
   uint32_t* full = m_host + nm;  // G > 1: whole-sequence scratch (every rank runs the full scan, keeps its shard)

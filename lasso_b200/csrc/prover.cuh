@@ -64,6 +64,8 @@ struct Ctx {
   uint32_t pub_seq = 0;
   static constexpr size_t kPubBytes = (size_t)kPubMaxReaders * kPubRegions * kPubElems * kPubSlotWords * 8;  // 1 MiB
   cudaEvent_t ev_aux = nullptr;  // marks a device->host copy that overlaps later launches on the same stream
+  cudaEvent_t ev_stage = nullptr;  // recorded after the last upload out of h_stage (the buffer is reused by the next densify)
+  bool stage_busy = false;
   void d2h_small(void* dst, const void* src, size_t bytes);  // prover.cu
   void wait_flag(uint32_t seq);                               // prover.cu
   // next message: `all` = every rank stores into every reader's buffer and the readers add the G residues
