@@ -204,7 +204,7 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def prove_config(lb, ctx, name, steps, stream_cache):
+def prove_config(lb, ctx, name, steps, stream_cache, sync=lambda: None):
     """ONE proof of a BASELINE configuration on `ctx` (single GPU, or sharded when the context has a communicator):
     1 warm-up, then `steps` timed end-to-end runs (densify + commit + prove, host buffers); returns the timings of the
     library's own spans and the hashes of the bytes."""
@@ -222,6 +222,7 @@ def prove_config(lb, ctx, name, steps, stream_cache):
     for it in range(1 + steps):
         t0 = time.perf_counter()
         dense = lb.DensifiedRepresentation.from_lookup_indices(ctx, idx, log_m)
+        sync()  # the upload and the sort are asynchronous; sharded: every rank starts the commitment together
         t1 = time.perf_counter()
         com = dense.commit(gens)
         t2 = time.perf_counter()
@@ -442,12 +443,12 @@ def main():
             # reference bytes for the sharded proofs: a single-GPU proof of the same inputs, made by rank 0 right here
             if rank == 0:
                 for n in names:
-                    single[n] = prove_config(lb, ctx, n, 1, streams)
+                    single[n] = prove_config(lb, ctx, n, 1, streams, torch.cuda.synchronize)
             dist.barrier()
             sctx = lb.Context(local_rank)
             sctx.init_comm(rank, world)
         for n in names:
-            row = prove_config(lb, sctx if world > 1 else ctx, n, max(1, min(args.steps, 3)), streams)
+            row = prove_config(lb, sctx if world > 1 else ctx, n, max(1, min(args.steps, 3)), streams, barrier)
             row["mode"] = "one proof sharded over %d GPUs (low index bits)" % world if world > 1 else "one proof on one GPU"
             if world > 1:
                 tm = parallel.max_over_ranks([row["ms_per_proof"], row["e2e_ms_per_proof"]])

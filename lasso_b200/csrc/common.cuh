@@ -8,6 +8,7 @@
 #include <string>
 
 #include "ed25519.cuh"
+#include "pub_codec.hpp"
 
 namespace lb {
 
@@ -127,18 +128,14 @@ struct PubDst {
 };
 // x = 8 x u32 little-endian, x < 2^255
 __device__ __forceinline__ void pub_store(const PubDst& p, int v, const uint32_t x[8]) {
-  const unsigned long long q0 = x[0] | ((unsigned long long)x[1] << 32), q1 = x[2] | ((unsigned long long)x[3] << 32),
-                           q2 = x[4] | ((unsigned long long)x[5] << 32), q3 = x[6] | ((unsigned long long)x[7] << 32);
-  const unsigned long long M = (1ull << 51) - 1, T = (unsigned long long)p.tag << 51;
-  const unsigned long long w0 = (q0 & M) | T, w1 = (((q0 >> 51) | (q1 << 13)) & M) | T,
-                           w2 = (((q1 >> 38) | (q2 << 26)) & M) | T, w3 = (((q2 >> 25) | (q3 << 39)) & M) | T,
-                           w4 = (q3 >> 12) | T;
+  unsigned long long w[5];
+  pub_encode(x, p.tag, w);
 #pragma unroll 1
   for (int d = 0; d < p.ndst; d++) {
     unsigned long long* s = p.dst[d] + (size_t)v * kPubSlotWords;
-    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(s), "l"(w0), "l"(w1) : "memory");
-    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(s + 2), "l"(w2), "l"(w3) : "memory");
-    asm volatile("st.global.u64 [%0], %1;" ::"l"(s + 4), "l"(w4) : "memory");
+    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(s), "l"(w[0]), "l"(w[1]) : "memory");
+    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(s + 2), "l"(w[2]), "l"(w[3]) : "memory");
+    asm volatile("st.global.u64 [%0], %1;" ::"l"(s + 4), "l"(w[4]) : "memory");
   }
 }
 struct Finalize {

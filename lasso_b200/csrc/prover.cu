@@ -53,14 +53,14 @@ void Ctx::pub_wait_raw(const PubDst& p, int writer, int count, uint32_t* out) {
   if (!h_pub || !p.ndst) throw std::runtime_error("no publication buffer for this message");
   if ((size_t)count > (size_t)kPubElems) throw std::runtime_error("message larger than a publication region");
   volatile unsigned long long* base = h_pub + ((size_t)writer * kPubRegions + p.region) * kPubElems * kPubSlotWords;
-  const unsigned long long tag = p.tag, M = (1ull << 51) - 1;
+  const uint32_t tag = p.tag;
   auto t0 = std::chrono::steady_clock::now();
   unsigned spins = 0;
   for (int v = 0; v < count; v++) {
     volatile unsigned long long* s = base + (size_t)v * kPubSlotWords;
     unsigned long long w[5];
     for (int k = 0; k < 5; k++) {
-      while (((w[k] = s[k]) >> 51) != tag) {
+      while (pub_tag_of(w[k] = s[k]) != tag) {
         __builtin_ia32_pause();
         if ((++spins & 0xffff) == 0) {  // surface kernel faults instead of spinning forever
           double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -68,16 +68,10 @@ void Ctx::pub_wait_raw(const PubDst& p, int writer, int count, uint32_t* out) {
           if (dt > 120.0) throw std::runtime_error("timeout waiting for a device result");
         }
       }
-      w[k] &= M;
+      w[k] &= kPubValueMask;
     }
     for (int k = 0; k < 5; k++) s[k] = 0;  // consumed
-    const unsigned long long q0 = w[0] | (w[1] << 51), q1 = (w[1] >> 13) | (w[2] << 38), q2 = (w[2] >> 26) | (w[3] << 25),
-                             q3 = (w[3] >> 39) | (w[4] << 12);
-    uint32_t* o = out + 8 * (size_t)v;
-    o[0] = (uint32_t)q0; o[1] = (uint32_t)(q0 >> 32);
-    o[2] = (uint32_t)q1; o[3] = (uint32_t)(q1 >> 32);
-    o[4] = (uint32_t)q2; o[5] = (uint32_t)(q2 >> 32);
-    o[6] = (uint32_t)q3; o[7] = (uint32_t)(q3 >> 32);
+    pub_decode(w, out + 8 * (size_t)v);
   }
 }
 void Ctx::fin_wait(const Finalize& f, fr_t* dst, int count) {

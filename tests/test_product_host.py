@@ -1,6 +1,7 @@
 """The product's host-side pieces that need no GPU, compiled with g++ straight from the headers:
 Merlin transcript (host_transcript.hpp) against the published vector, the 64-bit host field code against the
-32-bit carry-chain code that also runs on the device (fr.cuh / fq.cuh / host_fq64.hpp)."""
+32-bit carry-chain code that also runs on the device (fr.cuh / fq.cuh / host_fq64.hpp), the wire format of the
+tagged device -> host publication (pub_codec.hpp)."""
 import os
 import subprocess
 import tempfile
@@ -12,6 +13,7 @@ PROG = r'''
 #include "host_transcript.hpp"
 #include "ed25519.cuh"
 #include "host_fq64.hpp"
+#include "pub_codec.hpp"
 #include <cstdio>
 #include <random>
 using namespace lb;
@@ -127,6 +129,28 @@ int main() {
     h64::compress_xyz(xyz2, h2);
     h64::compress_xyz_pair(xyz, xyz2, pa, pb);
     if (memcmp(pa, h, 32) || memcmp(pb, h2, 32)) bad++;
+  }
+  // 4. wire format of a tagged publication (pub_codec.hpp): encode -> five self-identifying words -> decode, for
+  // random values below 2^255, every tag class, and the edge values; a word of another message is never accepted
+  {
+    std::mt19937_64 g(99);
+    for (int it = 0; it < 20000; it++) {
+      uint32_t x[8], y[8];
+      for (int l = 0; l < 8; l++) x[l] = (uint32_t)g();
+      if (it == 0) for (int l = 0; l < 8; l++) x[l] = 0;
+      if (it == 1) for (int l = 0; l < 8; l++) x[l] = 0xffffffffu;
+      x[7] &= 0x7fffffffu;  // < 2^255
+      const uint32_t tag = 1 + (uint32_t)(g() % 8191);
+      unsigned long long w[5], v[5];
+      pub_encode(x, tag, w);
+      for (int k = 0; k < 5; k++) {
+        if (pub_tag_of(w[k]) != tag || pub_tag_of(w[k]) == 0) bad++;
+        if (pub_tag_of(w[k]) == (tag % 8191) + 1) bad++;  // the next message's tag differs in every word
+        v[k] = w[k] & kPubValueMask;
+      }
+      pub_decode(v, y);
+      if (memcmp(x, y, 32)) bad++;
+    }
   }
   printf("bad=%d\n", bad);
   return bad;
