@@ -99,6 +99,11 @@ void launch_sumcheck_claim(const Strategy& S, const fr_t* base, size_t stride, s
 void launch_bound(const fr_t* Z, const fr_t* L, size_t L_size, size_t R_size, fr_t* partial, fr_t* out,
                   cudaStream_t st);
 int bound_max_chunks();
+// the same two reductions over the u32 mirror of an INTEGER-valued polynomial (dim, read, final, E): 8 IMAD per term
+// instead of a Montgomery product, 4 B read per element instead of 32 B, one reduction at the end
+void launch_bound_u32(const uint32_t* Z, const fr_t* L, size_t L_size, size_t R_size, fr_t* partial, fr_t* out, cudaStream_t st);
+void launch_multi_dot_u32(const uint32_t* base, size_t stride, int npolys, const fr_t* eq, size_t n, fr_t* partial, fr_t* out,
+                          cudaStream_t st);
 // Reed-Solomon fingerprints (memory_checking.rs:236-310).  init/final over M cells, read/write over s ops.
 // M_local cells of this rank; local cell i = global address i*G + g; `table` is the full M-entry table
 void launch_gp_fingerprints_mem(const fr_t* table, const fr_t* final_fr, size_t M_local, int G, int g,

@@ -759,6 +759,94 @@ void launch_bound(const fr_t* Z, const fr_t* L, size_t L_size, size_t R_size, fr
   LB_LAUNCH_CHECK();
 }
 
+// ---- the same two reductions for INTEGER-valued polynomials (dim, read, final, E: everything the prover commits to and
+// opens is an index, a counter or a table value < 2^32, kept as a u32 mirror next to the field form).  A field element
+// times a 32-bit integer is 8 IMAD.WIDE instead of a ~235-instruction Montgomery product, and the sum can be carried
+// as a plain 320-bit integer (X = sum_j L_j * z_j < 2^288 * #terms) and reduced ONCE: L_j is stored as L_j*R mod l, so
+// X mod l is already the Montgomery form of the result.  Reads 4 B per element instead of 32 B.
+struct wide_t {
+  uint32_t v[10];
+};
+__device__ __forceinline__ void wide_zero(wide_t& a) {
+#pragma unroll
+  for (int l = 0; l < 10; l++) a.v[l] = 0;
+}
+__device__ __forceinline__ void wide_mad(wide_t& acc, const fr_t& a, uint32_t z) {  // acc += a * z
+  uint64_t carry = 0;
+#pragma unroll
+  for (int l = 0; l < 8; l++) {
+    const uint64_t t = (uint64_t)a.v[l] * z + acc.v[l] + carry;
+    acc.v[l] = (uint32_t)t;
+    carry = t >> 32;
+  }
+  const uint64_t t = (uint64_t)acc.v[8] + carry;
+  acc.v[8] = (uint32_t)t;
+  acc.v[9] += (uint32_t)(t >> 32);
+}
+// X mod l for X < 2^320, as a field element: X = X_lo + 2^256 * X_hi;  X_lo mod l through two Montgomery products
+// (x -> x*R -> x), X_hi * 2^256 mod l = the Montgomery form of the 64-bit integer X_hi
+__device__ __forceinline__ fr_t wide_reduce(const wide_t& a) {
+  fr_t lo;
+#pragma unroll
+  for (int l = 0; l < 8; l++) lo.v[l] = a.v[l];
+  const fr_t lo_mod = fr_to_canonical(fr_from_raw_int(lo));
+  return fr_add(lo_mod, fr_from_u64((uint64_t)a.v[8] | ((uint64_t)a.v[9] << 32)));
+}
+// LZ[i] = sum_j L[j] z[j*R + i]: thread = column, rows split into chunks over blockIdx.y (<= 2^20 rows per chunk)
+__global__ void __launch_bounds__(kThreads)
+    bound_u32_kernel(const uint32_t* Z, const fr_t* L, size_t L_size, size_t R_size, size_t rows_per_chunk, fr_t* partial) {
+  __shared__ fr_t sL[64];
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t j0 = (size_t)blockIdx.y * rows_per_chunk;
+  size_t j1 = j0 + rows_per_chunk;
+  if (j1 > L_size) j1 = L_size;
+  wide_t acc;
+  wide_zero(acc);
+  for (size_t jb = j0; jb < j1; jb += 64) {  // the row weights of 64 rows at a time through shared memory
+    __syncthreads();
+    if (threadIdx.x < 64 && jb + threadIdx.x < j1) sL[threadIdx.x] = ld_fr(L + jb + threadIdx.x);
+    __syncthreads();
+    const size_t je = jb + 64 < j1 ? jb + 64 : j1;
+    if (i < R_size)
+      for (size_t j = jb; j < je; j++) wide_mad(acc, sL[j - jb], Z[j * R_size + i]);
+  }
+  if (i < R_size) st_fr(partial + (size_t)blockIdx.y * R_size + i, wide_reduce(acc));
+}
+void launch_bound_u32(const uint32_t* Z, const fr_t* L, size_t L_size, size_t R_size, fr_t* partial, fr_t* out, cudaStream_t st) {
+  int chunks = (int)(L_size < (size_t)kBoundChunks ? L_size : (size_t)kBoundChunks);
+  size_t rows_per_chunk = (L_size + chunks - 1) / chunks;
+  if (rows_per_chunk > ((size_t)1 << 20)) throw std::runtime_error("bound_u32: too many rows per chunk");
+  dim3 grid((unsigned)((R_size + kThreads - 1) / kThreads), chunks);
+  bound_u32_kernel<<<grid, kThreads, 0, st>>>(Z, L, L_size, R_size, rows_per_chunk, partial);
+  LB_LAUNCH_CHECK();
+  bound_reduce_kernel<<<(unsigned)((R_size + kThreads - 1) / kThreads), kThreads, 0, st>>>(partial, chunks, R_size, out);
+  LB_LAUNCH_CHECK();
+}
+// out[k] = <z_k, eq>, z_k = base + k*stride (u32), k < npolys
+__global__ void __launch_bounds__(kThreads)
+    multi_dot_u32_kernel(const uint32_t* base, size_t stride, const fr_t* eq, size_t n, fr_t* partial) {
+  __shared__ fr_t scratch[kThreads / 32];
+  const uint32_t* P = base + (size_t)blockIdx.y * stride;
+  wide_t w;
+  wide_zero(w);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    wide_mad(w, ld_fr(eq + i), P[i]);  // a thread adds at most n / (gridDim.x * 256) < 2^32 terms
+  fr_t acc[1] = {wide_reduce(w)};
+  block_sum_fr<1>(acc, scratch);
+  if (threadIdx.x == 0) partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = acc[0];
+}
+void launch_multi_dot_u32(const uint32_t* base, size_t stride, int npolys, const fr_t* eq, size_t n, fr_t* partial, fr_t* out,
+                          cudaStream_t st) {
+  int per = kMaxBlocks / npolys;
+  if (per < 1) per = 1;
+  int bx = grid_for(n, kThreads, per);
+  dim3 grid(bx, npolys);
+  multi_dot_u32_kernel<<<grid, kThreads, 0, st>>>(base, stride, eq, n, partial);
+  LB_LAUNCH_CHECK();
+  reduce_partials_kernel<<<npolys, kThreads, 0, st>>>(partial, bx, out);
+  LB_LAUNCH_CHECK();
+}
+
 // memory_checking.rs:249-252: hash(a, v, t) = t*gamma^2 + v*gamma + a - tau
 __global__ void __launch_bounds__(kThreads)
     fp_mem_kernel(const fr_t* table, const fr_t* final_fr, size_t M, int G, int g, fr_t gamma, fr_t gamma2, fr_t tau,

@@ -1061,7 +1061,7 @@ __global__ void set_elems_kernel(fr_t* dst, fr_t a, fr_t b) {
 // there on the opening runs REPLICATED on every rank — its vectors are only R = 2^(nv - nv/2) long and every round
 // is latency-bound, so splitting its two-row MSMs would add an exchange per round and save nothing.  Every rank
 // computes the same points and the same transcript.
-static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t* Z, size_t nv,
+static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t* Z, const uint32_t* Z_u32, size_t nv,
                                                const std::vector<fr_t>& r, const fr_t& Zr, Transcript& transcript,
                                                RandomTape& tape) {
   SpanTimer sp(c, "DensePolyEval.prove");
@@ -1078,7 +1078,11 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
   eq_evals_dev(c, r, 0, lv, Lvec.p);  // rows are not sharded: L is replicated
   eq_evals_dev(c, r, lv, rv, b.p);    // a_vec of the dot product proof = R
   if ((size_t)bound_max_chunks() * n_loc > c->partial_elems) throw std::runtime_error("bound scratch too small");
-  launch_bound(Z, Lvec.p, L_size, n_loc, c->d_partial, G > 1 ? a_loc.p : a.p, c->st);  // x_vec = LZ (this rank's columns)
+  // x_vec = LZ (this rank's columns); the opened polynomials are integer-valued: over their u32 mirror when there is one
+  if (Z_u32)
+    launch_bound_u32(Z_u32, Lvec.p, L_size, n_loc, c->d_partial, G > 1 ? a_loc.p : a.p, c->st);
+  else
+    launch_bound(Z, Lvec.p, L_size, n_loc, c->d_partial, G > 1 ? a_loc.p : a.p, c->st);
   g_launches += 2;
   if (G > 1) comm_gather_vector(c, a_loc.p, n_loc, a_gath.p, a.p);
 
@@ -1297,7 +1301,7 @@ static DotProductProofLogBytes prove_poly_eval(Ctx* c, const Gens& g, const fr_t
 
 // CombinedTableEvalProof::prove (subtables/mod.rs:284-313 + prove_single 230-281) and the two analogous
 // n-to-1 reductions of HashLayerProof::prove: fold `evals` with bound_poly_var_bot in reverse challenge order.
-static DotProductProofLogBytes prove_joint(Ctx* c, const Gens& g, const fr_t* Z, size_t nv, std::vector<fr_t> evals,
+static DotProductProofLogBytes prove_joint(Ctx* c, const Gens& g, const fr_t* Z, const uint32_t* Z_u32, size_t nv, std::vector<fr_t> evals,
                                            bool pad_before_append, const char* evals_label, const char* chal_label,
                                            const char* joint_label, const std::vector<fr_t>& r,
                                            Transcript& transcript, RandomTape& tape) {
@@ -1317,7 +1321,7 @@ static DotProductProofLogBytes prove_joint(Ctx* c, const Gens& g, const fr_t* Z,
   std::vector<fr_t> r_joint = challenges;
   r_joint.insert(r_joint.end(), r.begin(), r.end());
   transcript.append_scalar(joint_label, joint);
-  return prove_poly_eval(c, g, Z, nv, r_joint, joint, transcript, tape);
+  return prove_poly_eval(c, g, Z, Z_u32, nv, r_joint, joint, transcript, tape);
 }
 
 // ---------------------------------------------------------------------------------------------- prove
@@ -1388,12 +1392,12 @@ std::vector<uint8_t> prove(Ctx* c, const Strategy& S, Dense& dense, const std::v
   {
     SpanTimer sp(c, "CombinedEval.prove");
     eq_evals_shard(c, r_z, 0, log_s, eqtab.p);
-    launch_multi_dot(E.p, s_loc, (int)alpha, eqtab.p, s_loc, c->d_partial, c->d_small, c->st);
+    launch_multi_dot_u32(E_u32.p, s_loc, (int)alpha, eqtab.p, s_loc, c->d_partial, c->d_small, c->st);
     g_launches += 2;
     reduce_to_host(c, c->d_small, (int)alpha, eval_derefs.data());
     w.arr_fr(eval_derefs);
     transcript.append_protocol_name("Lasso CombinedTableEvalProof");
-    ser_dpl(w, prove_joint(c, g, E.p, nv_d, eval_derefs, true, "evals_ops_val", "challenge_combine_n_to_one",
+    ser_dpl(w, prove_joint(c, g, E.p, E_u32.p, nv_d, eval_derefs, true, "evals_ops_val", "challenge_combine_n_to_one",
                            "joint_claim_eval", r_z, transcript, tape));
   }
   // ---- memory checking (surge.rs:186-198)
@@ -1491,8 +1495,8 @@ std::vector<uint8_t> prove(Ctx* c, const Strategy& S, Dense& dense, const std::v
     transcript.append_protocol_name("Lasso HashLayerProof");
     std::vector<fr_t> eval_derefs2(alpha), eval_dim(C), eval_read(C), eval_final(C);
     eq_evals_shard(c, rand_ops, 0, rand_ops.size(), eqtab.p);
-    launch_multi_dot(E.p, s_loc, (int)alpha, eqtab.p, s_loc, c->d_partial, c->d_small, c->st);
-    launch_multi_dot(dense.d_l_fr.p, s_loc, (int)(2 * C), eqtab.p, s_loc, c->d_partial + 65536, c->d_small + 64, c->st);
+    launch_multi_dot_u32(E_u32.p, s_loc, (int)alpha, eqtab.p, s_loc, c->d_partial, c->d_small, c->st);
+    launch_multi_dot_u32(dense.d_l_u32.p, s_loc, (int)(2 * C), eqtab.p, s_loc, c->d_partial + 65536, c->d_small + 64, c->st);
     g_launches += 4;
     {
       std::vector<fr_t> tmp(64 + 2 * C);
@@ -1505,20 +1509,20 @@ std::vector<uint8_t> prove(Ctx* c, const Strategy& S, Dense& dense, const std::v
     }
     transcript.append_protocol_name("Lasso CombinedTableEvalProof");
     DotProductProofLogBytes proof_derefs =
-        prove_joint(c, g, E.p, nv_d, eval_derefs2, true, "evals_ops_val", "challenge_combine_n_to_one",
+        prove_joint(c, g, E.p, E_u32.p, nv_d, eval_derefs2, true, "evals_ops_val", "challenge_combine_n_to_one",
                     "joint_claim_eval", rand_ops, transcript, tape);
     eq_evals_shard(c, rand_mem, 0, rand_mem.size(), eqtab.p);
-    launch_multi_dot(dense.d_m_fr.p, M_loc, (int)C, eqtab.p, M_loc, c->d_partial, c->d_small, c->st);
+    launch_multi_dot_u32(dense.d_m_u32.p, M_loc, (int)C, eqtab.p, M_loc, c->d_partial, c->d_small, c->st);
     g_launches += 2;
     reduce_to_host(c, c->d_small, (int)C, eval_final.data());
     std::vector<fr_t> evals_ops = eval_dim;
     evals_ops.insert(evals_ops.end(), eval_read.begin(), eval_read.end());
     DotProductProofLogBytes proof_ops =
-        prove_joint(c, g, dense.d_l_fr.p, dense.nv_l, evals_ops, true, "claim_evals_ops", "challenge_combine_n_to_one",
+        prove_joint(c, g, dense.d_l_fr.p, dense.d_l_u32.p, dense.nv_l, evals_ops, true, "claim_evals_ops", "challenge_combine_n_to_one",
                     "joint_claim_eval_ops", rand_ops, transcript, tape);
     // claim_evals_mem is appended UNPADDED and uses Math::log_2 (ceil) of C (memory_checking.rs:413-418)
     DotProductProofLogBytes proof_mem =
-        prove_joint(c, g, dense.d_m_fr.p, dense.nv_m, eval_final, false, "claim_evals_mem",
+        prove_joint(c, g, dense.d_m_fr.p, dense.d_m_u32.p, dense.nv_m, eval_final, false, "claim_evals_mem",
                     "challenge_combine_two_to_one", "joint_claim_eval_mem", rand_mem, transcript, tape);
     // field order (memory_checking.rs:313-329)
     w.arr_fr(eval_dim);
