@@ -13,6 +13,9 @@ namespace lb {
 static constexpr int kThreads = 256;
 static constexpr int kBlocksPerSM = 4;
 static constexpr int kMaxBlocks = kNumSMs * kBlocksPerSM;  // 592
+// bind_top launch shape, measured with tools/bind_sweep.py on 5 x 2^22 elements (GB/s of the 96 B per output):
+// CTAs/SM x outputs per thread: 4x1 5340, 4x2 5514, 5x1 5496, 5x2 5661, 6x1 5655, 6x2 5582
+static constexpr int kBindBlocksPerSM = 5, kBindIlp = 2;
 
 static inline int grid_for(size_t n, int threads = kThreads, int max_blocks = kMaxBlocks) {
   size_t b = (n + threads - 1) / threads;
@@ -45,12 +48,37 @@ __global__ void __launch_bounds__(kThreads) bind_bot_kernel(const fr_t* Z, fr_t*
     st_fr(out + i, fr_add(lo, fr_mul(r, fr_sub(hi, lo))));
   }
 }
+// two outputs per thread and iteration: four independent 32-byte loads in flight before the first multiplication
+__global__ void __launch_bounds__(kThreads) bind_top2_kernel(fr_t* base, size_t stride, size_t half, fr_t r) {
+  fr_t* Z = base + (size_t)blockIdx.y * stride;
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + step < half; i += 2 * step) {
+    const fr_t lo0 = ld_fr_stream(Z + i), hi0 = ld_fr_stream(Z + half + i);
+    const fr_t lo1 = ld_fr_stream(Z + i + step), hi1 = ld_fr_stream(Z + half + i + step);
+    st_fr(Z + i, fr_add(lo0, fr_mul(r, fr_sub(hi0, lo0))));
+    st_fr(Z + i + step, fr_add(lo1, fr_mul(r, fr_sub(hi1, lo1))));
+  }
+  if (i < half) {
+    const fr_t lo = ld_fr_stream(Z + i), hi = ld_fr_stream(Z + half + i);
+    st_fr(Z + i, fr_add(lo, fr_mul(r, fr_sub(hi, lo))));
+  }
+}
+// experiment knobs (tools/bind_sweep.py): resident CTAs per SM the grid is sized for, outputs per thread and iteration
+static int bind_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 void launch_bind_top(fr_t* base, size_t stride, int npolys, size_t half, const fr_t& r, cudaStream_t st) {
   if (half == 0 || npolys == 0) return;
-  int per = kMaxBlocks / npolys;
+  static const int bps = bind_env("LASSO_B200_BIND_BLOCKS", kBindBlocksPerSM), ilp = bind_env("LASSO_B200_BIND_ILP", kBindIlp);
+  int per = kNumSMs * bps / npolys;
   if (per < kNumSMs / 4) per = kNumSMs / 4;
   dim3 grid(grid_for(half, kThreads, per), npolys);
-  bind_top_kernel<<<grid, kThreads, 0, st>>>(base, stride, half, r);
+  if (ilp == 2)
+    bind_top2_kernel<<<grid, kThreads, 0, st>>>(base, stride, half, r);
+  else
+    bind_top_kernel<<<grid, kThreads, 0, st>>>(base, stride, half, r);
   LB_LAUNCH_CHECK();
 }
 void launch_bind_top_ptrs(fr_t* const* d_ptrs, int npolys, size_t half, const fr_t& r, cudaStream_t st) {
