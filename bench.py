@@ -492,11 +492,11 @@ def main():
                     "densify_ms_per_step": dens_ms / args.steps},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"kernel": "bind_top_kernel (K1)", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": "bind_top2_kernel (K1: bound_poly_var_top, two outputs per thread)", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum per launch of this exact shape, from the
-                         # ncu --set full capture in profiles/r01_bind_top_kernel_ncu_full.txt (671.1 MB + 295.5 MB)
-                         "traffic": 966613504,
+                         # ncu --set full capture in profiles/r02_bind_top2_kernel_ncu_full.txt (671.1 MB + 294.3 MB)
+                         "traffic": 965458176,
                          "peak_source": peak_src, "ms_per_launch": ms,
                          "alg_bytes_per_launch": alg_bytes},
             "throughput_batched": batched,
