@@ -263,6 +263,8 @@ def main():
     ap.add_argument("--msm-max-log", type=int, default=24)
     ap.add_argument("--batch", type=int, default=4, help="proofs in flight for the throughput_batched block (N = 1)")
     ap.add_argument("--no-batched", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not pin the host threads to the GPU's NUMA node")
+    ap.add_argument("--no-sampler", action="store_true", help="diagnosis: no nvidia-smi clock sampler during the run")
     args = ap.parse_args()
     if args.workload == "msm":
         run_msm(args)
@@ -291,7 +293,7 @@ def main():
     # independent proofs: each rank its own batch
     idx, r, tape_seed = make_inputs(log_s, C, log_m, wl.BENCH_SEED + rank)
     ctx = lb.Context(local_rank)
-    numa_node = ctx.bind_host_threads() if world > 1 else -1  # one process per GPU: keep its host side on the GPU's node
+    numa_node = -1
     need = lb.gens_points_needed(C, s, S.num_memories, log_m)
     streams = {need: generator_stream(lb, need)}
     free0 = torch.cuda.mem_get_info()[0]
@@ -320,7 +322,12 @@ def main():
     # nvidia-smi process, a line every 100 ms) is started first so that it is already emitting when the timed
     # region begins; only its samples from the loaded region on are used.
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if not args.no_sampler:
+        sampler.start()
+    # one process per GPU: the proving thread gets a dedicated core of the GPU's NUMA node, helper threads the rest of
+    # the node (after every other thread of the process exists: they keep their affinity)
+    if world > 1 and not args.no_numa_bind:
+        numa_node = ctx.bind_host_threads()
     dense = None
     for _ in range(args.warmup):
         dense, com0, proof0 = step_e2e()
@@ -359,6 +366,10 @@ def main():
         step_resident(dense)
     clocks = sampler.stop()
 
+    print("rank %d: resident %.3f ms/step, e2e %.3f ms/step, proving thread on CPUs %s" % (
+        rank, 1e3 * t_res / args.steps, 1e3 * t_e2e / args.steps,
+        sorted(os.sched_getaffinity(0)) if len(os.sched_getaffinity(0)) <= 8 else "%d CPUs" % len(os.sched_getaffinity(0))),
+        file=sys.stderr, flush=True)
     if world > 1:
         t_res, t_e2e = parallel.max_over_ranks([t_res, t_e2e])
 
@@ -447,6 +458,8 @@ def main():
             dist.barrier()
             sctx = lb.Context(local_rank)
             sctx.init_comm(rank, world)
+            if not args.no_numa_bind:
+                sctx.bind_host_threads()
         for n in names:
             row = prove_config(lb, sctx if world > 1 else ctx, n, max(1, min(args.steps, 3)), streams, barrier)
             row["mode"] = "one proof sharded over %d GPUs (low index bits)" % world if world > 1 else "one proof on one GPU"

@@ -61,9 +61,11 @@ void lasso_ctx_destroy(lasso_ctx* ctx);
  * peer-memory stores over NVLink (CUDA IPC), or ncclAllGather under LASSO_B200_XCHG=nccl. */
 int lasso_comm_unique_id(uint8_t out[128]);
 int lasso_ctx_init_comm(lasso_ctx*, const uint8_t id[128], int rank, int world);
-/* Optional: bind the calling process's host threads (Fiat-Shamir transcript, timestamp scan, pinned staging) to the
- * CPUs of the NUMA node the context's GPU hangs off (sysfs).  Returns the node id, or -1 if it is not exposed.
- * With one process per GPU on a two-socket node this keeps the per-proof host work and its pinned buffers local. */
+/* Optional host-thread placement for one process per GPU on a multi-socket node (sysfs; returns the NUMA node of the
+ * context's GPU, or -1 if the topology is not exposed): the CALLING thread — the one that will call lasso_prove and
+ * spin on the round messages — is pinned to a dedicated physical core of that node (a different one for every GPU
+ * of the node), the library's helper threads (staging of the index matrix) get the rest of the node.  Call it from
+ * the proving thread after the process has created its other threads (they keep their affinity). */
 int lasso_ctx_bind_host_threads(lasso_ctx*);
 
 /* ---------------------------------------------------------------- per-loop entry points (host buffers) */

@@ -124,8 +124,9 @@ class Context:
         self.rank, self.world = rank, world
 
     def bind_host_threads(self):
-        """Pin this process's host threads (transcript, timestamp scan, staging) to the NUMA node of the
-        context's GPU; returns the node id or -1 when the topology is not exposed."""
+        """One process per GPU: pin the CALLING thread (the one that proves and spins on the round messages) to a
+        dedicated core of the GPU's NUMA node and give the library's helper threads the rest of the node; returns the
+        node id or -1 when the topology is not exposed.  Threads created earlier keep their affinity."""
         return int(lib().lasso_ctx_bind_host_threads(self._h))
 
     @property

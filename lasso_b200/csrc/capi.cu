@@ -88,7 +88,7 @@ int lasso_ctx_init_comm(lasso_ctx* h, const uint8_t id[128], int rank, int world
 
 int lasso_ctx_bind_host_threads(lasso_ctx* h) {
   if (!h || !h->c) return -1;
-  return bind_host_threads(h->c->device);
+  return bind_host_threads(h->c->device, &h->c->helper_mask, &h->c->have_helper_mask);
 }
 
 int lasso_bind_top(lasso_ctx* h, uint64_t* Z, size_t len, const uint64_t r[4]) {

@@ -240,6 +240,84 @@ __global__ void __launch_bounds__(128)
   finalize_block<NP>(fin, acc, 0, blockIdx.x, gridDim.x, NP, gridDim.x);
 }
 
+// The same evaluation with TWO lanes per index pair, each forming half of the C+2 evaluation points: the live state per
+// thread halves (5 running products + 5 sums instead of 10 + 10 for C = 8: 255 registers and 8 warps per SM in the
+// kernel above), the two lanes of a pair load the same addresses (a warp still reads 512 contiguous bytes per array).
+// Sums over the lanes of equal parity by xor-shuffles, then as block_sum_fr.
+template <int C>
+__global__ void __launch_bounds__(128, 3)
+    sc_eval_lt2_kernel(const fr_t* base, size_t stride, size_t half, Finalize fin) {
+  constexpr int NP = C + 2, HP = (NP + 1) / 2;
+  __shared__ fr_t scratch[NP * 128 / 32];
+  const int part = threadIdx.x & 1, t0 = part * HP, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  fr_t acc[HP];
+#pragma unroll
+  for (int t = 0; t < HP; t++) acc[t] = fr_zero();
+  const fr_t* eq = base + (size_t)(2 * C) * stride;
+  const size_t pairs_per_step = ((size_t)gridDim.x * blockDim.x) >> 1;
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1; i < half; i += pairs_per_step) {
+    fr_t h[HP];
+#pragma unroll
+    for (int t = 0; t < HP; t++) h[t] = fr_zero();
+#pragma unroll 1
+    for (int k = C - 1; k >= 0; k--) {
+      const fr_t* PL = base + (size_t)(2 * k) * stride;
+      const fr_t* PE = base + (size_t)(2 * k + 1) * stride;
+      const fr_t l0 = ld_fr(PL + i), l1 = ld_fr(PL + half + i), e0 = ld_fr(PE + i), e1 = ld_fr(PE + half + i);
+      const fr_t dl = fr_sub(l1, l0), de = fr_sub(e1, e0);
+      fr_t cl = l0, ce = e0;
+      if (part) {  // start at t = HP: HP additions (cheaper than a multiplication by the constant)
+#pragma unroll
+        for (int j = 0; j < HP; j++) {
+          cl = fr_add(cl, dl);
+          ce = fr_add(ce, de);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < HP; t++) {
+        h[t] = fr_add(cl, fr_mul(ce, h[t]));
+        cl = fr_add(cl, dl);
+        ce = fr_add(ce, de);
+      }
+    }
+    const fr_t q0 = ld_fr(eq + i), q1 = ld_fr(eq + half + i), dq = fr_sub(q1, q0);
+    fr_t cq = q0;
+    if (part) {
+#pragma unroll
+      for (int j = 0; j < HP; j++) cq = fr_add(cq, dq);
+    }
+#pragma unroll
+    for (int t = 0; t < HP; t++) {
+      acc[t] = fr_add(acc[t], fr_mul(h[t], cq));
+      cq = fr_add(cq, dq);
+    }
+  }
+  // lanes of equal parity: xor-shuffles with strides 16 .. 2; lane 0 / 1 then hold the warp's sums of the two halves
+#pragma unroll
+  for (int t = 0; t < HP; t++) {
+    fr_t a = acc[t];
+#pragma unroll
+    for (int d = 16; d >= 2; d >>= 1) {
+      fr_t o;
+#pragma unroll
+      for (int l = 0; l < 8; l++) o.v[l] = __shfl_xor_sync(0xffffffffu, a.v[l], d);
+      a = fr_add(a, o);
+    }
+    if (lane < 2 && t0 + t < NP) scratch[(t0 + t) * nwarps + warp] = a;
+  }
+  __syncthreads();
+  fr_t vals[NP];
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < NP; k++) {
+      const fr_t x = lane < nwarps ? scratch[k * nwarps + lane] : fr_zero();
+      vals[k] = warp_sum_fr(x);
+    }
+  }
+  __syncthreads();
+  finalize_block<NP>(fin, vals, 0, blockIdx.x, gridDim.x, NP, gridDim.x);
+}
+
 // Any other C (the reference is generic in C, lt.rs:13-14): the C+2 evaluation points are processed TB at a time so
 // the live state stays in registers whatever C is; every pass re-reads the polynomials (a fallback, not a hot path).
 // tv.v[t] = F::from(t).
@@ -325,7 +403,14 @@ void launch_sumcheck_eval_arbitrary(const Strategy& S, const fr_t* base, size_t 
       case 2: launch_lt<2>(base, stride, half, fin, blocks, st); break;
       case 3: launch_lt<3>(base, stride, half, fin, blocks, st); break;
       case 4: launch_lt<4>(base, stride, half, fin, blocks, st); break;
-      case 8: launch_lt<8>(base, stride, half, fin, blocks, st); break;
+      case 8:
+        if (half >= 4096) {  // throughput-bound rounds: two lanes per pair (3 CTAs per SM instead of 2, no spills)
+          sc_eval_lt2_kernel<8><<<grid_for(2 * half, 128, kNumSMs * 6), 128, 0, st>>>(base, stride, half, fin);
+          LB_LAUNCH_CHECK();
+        } else {
+          launch_lt<8>(base, stride, half, fin, blocks, st);
+        }
+        break;
       default: {
         FrVec tv;
         for (int t = 0; t < 32; t++) tv.v[t] = fr_from_u64((uint64_t)t);

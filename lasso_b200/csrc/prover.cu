@@ -104,33 +104,18 @@ void Ctx::wait_flag(uint32_t seq) {
   }
   __sync_synchronize();
 }
-// Pin the calling thread (and the threads it creates later) to the CPUs of the NUMA node the device hangs off.
-int bind_host_threads(int device) {
-  try {
-    char busid[64] = {0};
-    if (cudaDeviceGetPCIBusId(busid, sizeof busid, device) != cudaSuccess) return -1;
-    for (char* p = busid; *p; p++) *p = (char)tolower(*p);
-    int node = -1;
-    {
-      std::string path = std::string("/sys/bus/pci/devices/") + busid + "/numa_node";
-      FILE* f = fopen(path.c_str(), "r");
-      if (!f) return -1;
-      if (fscanf(f, "%d", &node) != 1) node = -1;
-      fclose(f);
-    }
-    if (node < 0) return -1;
-    std::string path = "/sys/devices/system/node/node" + std::to_string(node) + "/cpulist";
-    FILE* f = fopen(path.c_str(), "r");
-    if (!f) return -1;
-    char buf[4096] = {0};
-    if (!fgets(buf, sizeof buf, f)) {
-      fclose(f);
-      return -1;
-    }
-    fclose(f);
-    cpu_set_t set;
-    CPU_ZERO(&set);
-    int count = 0;
+// ---- host-thread placement (one process per GPU on a multi-socket node) -------------------------------------------
+// The prover's host side is ONE latency-critical thread (it spins on the round messages and hashes them) plus short
+// bursts of helper threads (staging the index matrix).  bind_host_threads pins the CALLING thread to one dedicated
+// physical core of the NUMA node its GPU hangs off — a different core for every GPU of the node, spread over the
+// node's cores — and gives the helper threads the rest of the node (all its CPUs minus the dedicated cores and their
+// SMT siblings).  A spinning thread that shares a core with anything else loses milliseconds per proof.
+static std::vector<int> parse_cpulist(const std::string& path) {
+  std::vector<int> out;
+  FILE* f = fopen(path.c_str(), "r");
+  if (!f) return out;
+  char buf[4096] = {0};
+  if (fgets(buf, sizeof buf, f)) {
     for (char* tok = strtok(buf, ",\n"); tok; tok = strtok(nullptr, ",\n")) {  // "0-31,64-95"
       int lo = 0, hi = 0;
       if (sscanf(tok, "%d-%d", &lo, &hi) == 2) {
@@ -139,13 +124,71 @@ int bind_host_threads(int device) {
       } else {
         continue;
       }
-      for (int cpu = lo; cpu <= hi && cpu < CPU_SETSIZE; cpu++) {
-        CPU_SET(cpu, &set);
-        count++;
-      }
+      for (int cpu = lo; cpu <= hi; cpu++) out.push_back(cpu);
     }
-    if (count == 0) return -1;
-    if (sched_setaffinity(0, sizeof set, &set) != 0) return -1;
+  }
+  fclose(f);
+  return out;
+}
+static int numa_node_of_device(int device) {
+  char busid[64] = {0};
+  if (cudaDeviceGetPCIBusId(busid, sizeof busid, device) != cudaSuccess) return -1;
+  for (char* p = busid; *p; p++) *p = (char)tolower(*p);
+  int node = -1;
+  FILE* f = fopen((std::string("/sys/bus/pci/devices/") + busid + "/numa_node").c_str(), "r");
+  if (!f) return -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  return node;
+}
+// -> NUMA node or -1.  helper_mask (may be null) receives the CPUs for helper threads.
+int bind_host_threads(int device, cpu_set_t* helper_mask, bool* have_helper_mask) {
+  try {
+    if (have_helper_mask) *have_helper_mask = false;
+    const int node = numa_node_of_device(device);
+    if (node < 0) return -1;
+    const std::vector<int> cpus = parse_cpulist("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist");
+    if (cpus.empty()) return -1;
+    // GPUs on this node, and this GPU's index among them
+    int ndev = 0, cnt = 0, idx = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) ndev = device + 1;
+    for (int d = 0; d < ndev; d++)
+      if (numa_node_of_device(d) == node) {
+        if (d < device) idx++;
+        cnt++;
+      }
+    if (cnt < 1) cnt = 1;
+    // physical cores = CPUs that are the first of their sibling list
+    std::vector<int> phys;
+    std::map<int, std::vector<int>> sib;
+    for (int cpu : cpus) {
+      std::vector<int> s = parse_cpulist("/sys/devices/system/cpu/cpu" + std::to_string(cpu) + "/topology/thread_siblings_list");
+      if (s.empty()) s.push_back(cpu);
+      sib[cpu] = s;
+      if (s[0] == cpu) phys.push_back(cpu);
+    }
+    if (phys.empty()) phys = cpus;
+    auto dedicated = [&](int k) { return phys[(size_t)(k + 1) * phys.size() / (size_t)(cnt + 1) % phys.size()]; };
+    cpu_set_t helpers;
+    CPU_ZERO(&helpers);
+    for (int cpu : cpus)
+      if (cpu < CPU_SETSIZE) CPU_SET(cpu, &helpers);
+    for (int k = 0; k < cnt; k++)
+      for (int c2 : sib[dedicated(k)])
+        if (c2 < CPU_SETSIZE) CPU_CLR(c2, &helpers);
+    if (CPU_COUNT(&helpers) == 0)
+      for (int cpu : cpus)
+        if (cpu < CPU_SETSIZE) CPU_SET(cpu, &helpers);
+    cpu_set_t mine;
+    CPU_ZERO(&mine);
+    const int my_cpu = dedicated(idx);
+    if (my_cpu >= CPU_SETSIZE) return -1;
+    CPU_SET(my_cpu, &mine);
+    if (sched_setaffinity(0, sizeof mine, &mine) != 0) return -1;
+    if (helper_mask && have_helper_mask) {
+      *helper_mask = helpers;
+      *have_helper_mask = true;
+    }
     return node;
   } catch (...) {
     return -1;
@@ -159,11 +202,13 @@ Ctx* ctx_create(int device) {
   if (device < 0 || device >= count) throw std::runtime_error("invalid device id");
   LB_CUDA_CHECK(cudaSetDevice(device));
   {
-    const char* nb = getenv("LASSO_B200_NUMA_BIND");  // bind before the pinned buffers are first touched
-    if (nb && nb[0] == '1') bind_host_threads(device);
   }
   std::unique_ptr<Ctx> c(new Ctx());
   c->device = device;
+  {
+    const char* nb = getenv("LASSO_B200_NUMA_BIND");
+    if (nb && nb[0] == '1') bind_host_threads(device, &c->helper_mask, &c->have_helper_mask);
+  }
   LB_CUDA_CHECK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
   cudaMemPool_t pool;
   LB_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -491,6 +536,7 @@ Dense* densify(Ctx* c, const uint64_t* indices, size_t n, size_t C, size_t log_m
         for (auto& f : done) f.store(0);
         std::atomic<int> bad{0};
         auto conv = [&](size_t t) {
+          if (nthreads > 1) c->helper_thread_enter();
           for (size_t p = t; p < npieces; p += nthreads) {
             const size_t lo = total * p / npieces, hi = total * (p + 1) / npieces;
             int b = 0;
@@ -551,6 +597,7 @@ Dense* densify(Ctx* c, const uint64_t* indices, size_t n, size_t C, size_t log_m
   // counters; dimensions are independent, so one host thread each.
   std::vector<int> bad(C, 0);
   auto work = [&](size_t i) {
+    if (i > 0) c->helper_thread_enter();
     uint32_t* dim = G == 1 ? l_host + i * s : full + i * (2 * s + m);
     uint32_t* rd = G == 1 ? l_host + (C + i) * s : dim + s;
     uint32_t* fin = G == 1 ? m_host + i * m : dim + 2 * s;

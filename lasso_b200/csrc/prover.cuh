@@ -1,6 +1,8 @@
 // lasso_b200 — host-side prover objects: context, device buffers, generator tables, the
 // densified representation and the proof byte writer.  The prover logic is in prover.cu.
 #pragma once
+#include <sched.h>
+
 #include <atomic>
 #include <chrono>
 #include <map>
@@ -66,6 +68,12 @@ struct Ctx {
   cudaEvent_t ev_aux = nullptr;  // marks a device->host copy that overlaps later launches on the same stream
   cudaEvent_t ev_stage = nullptr;  // recorded after the last upload out of h_stage (the buffer is reused by the next densify)
   bool stage_busy = false;
+  // host-thread placement (bind_host_threads): the CPUs the library's helper threads may use
+  cpu_set_t helper_mask;
+  bool have_helper_mask = false;
+  void helper_thread_enter() const {
+    if (have_helper_mask) sched_setaffinity(0, sizeof helper_mask, &helper_mask);
+  }
   void d2h_small(void* dst, const void* src, size_t bytes);  // prover.cu
   void wait_flag(uint32_t seq);                               // prover.cu
   // next message: `all` = every rank stores into every reader's buffer and the readers add the G residues
@@ -247,7 +255,7 @@ inline size_t next_pow2(size_t x) {
 }
 
 // entry points implemented in prover.cu
-int bind_host_threads(int device);  // -> NUMA node or -1
+int bind_host_threads(int device, cpu_set_t* helper_mask, bool* have_helper_mask);  // -> NUMA node or -1
 Ctx* ctx_create(int device);
 void ctx_destroy(Ctx*);
 Gens* gens_create(Ctx*, const uint64_t* stream_affine, size_t n_points, size_t c, size_t s, size_t num_memories,
