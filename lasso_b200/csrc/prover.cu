@@ -553,10 +553,13 @@ Dense* densify(Ctx* c, const uint64_t* indices, size_t n, size_t C, size_t log_m
           }
         };
         std::vector<std::thread> th;
-        for (size_t t = 1; t < nthreads; t++) th.emplace_back(conv, t);
-        if (nthreads == 1) conv(0);
         std::thread t0;
-        if (nthreads > 1) t0 = std::thread(conv, 0);
+        {
+          HelperSpawnScope spawn(c, nthreads > 1);  // a pinned caller must not hand its single CPU down to the helpers
+          for (size_t t = 1; t < nthreads; t++) th.emplace_back(conv, t);
+          if (nthreads > 1) t0 = std::thread(conv, 0);
+        }
+        if (nthreads == 1) conv(0);
         for (size_t p = 0; p < npieces; p++) {  // this thread feeds the copy engine in order
           while (!done[p].load(std::memory_order_acquire)) __builtin_ia32_pause();
           const size_t lo = total * p / npieces, hi = total * (p + 1) / npieces;
@@ -626,7 +629,10 @@ Dense* densify(Ctx* c, const uint64_t* indices, size_t n, size_t C, size_t log_m
   };
   {
     std::vector<std::thread> th;
-    for (size_t i = 1; i < C; i++) th.emplace_back(work, i);
+    {
+      HelperSpawnScope spawn(c, C > 1);
+      for (size_t i = 1; i < C; i++) th.emplace_back(work, i);
+    }
     work(0);
     for (auto& t : th) t.join();
   }

@@ -134,6 +134,21 @@ struct Ctx {
   }
 };
 
+// While helper threads are being CREATED the calling thread widens its own affinity to the helper CPUs: a new thread
+// inherits its creator's mask, and a creator pinned to one core that goes on to spin there would leave its children
+// waiting for that very core before they can even move themselves (milliseconds).  Restored on scope exit.
+struct HelperSpawnScope {
+  cpu_set_t saved;
+  bool active = false;
+  HelperSpawnScope(const Ctx* c, bool spawning) {
+    if (spawning && c->have_helper_mask && sched_getaffinity(0, sizeof saved, &saved) == 0)
+      active = sched_setaffinity(0, sizeof c->helper_mask, &c->helper_mask) == 0;
+  }
+  ~HelperSpawnScope() {
+    if (active) sched_setaffinity(0, sizeof saved, &saved);
+  }
+};
+
 // stream-ordered device buffer
 template <class T>
 struct DBuf {

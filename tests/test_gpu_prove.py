@@ -129,8 +129,8 @@ def test_densified_fields(ctx):
 
 
 def test_gpu_densify_matches_host_scan(monkeypatch):
-    """densify_kernels.cu (chunk histogram + column scan + in-order warp ranking) against the host timestamp scan,
-    through the public fields of DensifiedRepresentation (densified.rs:8-18); skewed addresses included."""
+    """densify_kernels.cu (stable LSD radix sort by address, read[k] = position - start[address]) against the host
+    timestamp scan, through the public fields of DensifiedRepresentation (densified.rs:8-18); skewed addresses included."""
     import lasso_b200 as lb
 
     rng = np.random.default_rng(77)
