@@ -125,6 +125,27 @@ void comm_unique_id(uint8_t out[128]) {
   close(fd);
 }
 
+// undo whatever of a (partially) built exchange exists: imports, registrations, mappings, the own buffer and name
+static void xchg_release(Xchg* x) {
+  if (!x) return;
+  if (x->nccl_comm) nccl().CommDestroy(x->nccl_comm);
+  x->nccl_comm = nullptr;
+  for (int r = 0; r < x->world; r++) {
+    if (r != x->rank && x->xbuf[r]) cudaIpcCloseMemHandle(x->xbuf[r]);
+    if (r != x->rank) x->xbuf[r] = nullptr;
+  }
+  for (int r = 0; r < x->world; r++) {
+    if (x->registered[r]) cudaHostUnregister(x->seg[r]);
+    x->registered[r] = false;
+    if (x->seg[r]) munmap(x->seg[r], x->seg_bytes);
+    x->seg[r] = nullptr;
+  }
+  if (x->xbuf[x->rank]) cudaFree(x->xbuf[x->rank]);
+  x->xbuf[x->rank] = nullptr;
+  if (!x->name[x->rank].empty()) shm_unlink(x->name[x->rank].c_str());  // harmless if it is gone already
+}
+
+static void comm_init_impl(Ctx* c, Xchg* x, const uint8_t id_bytes[128], int rank, int world);
 void comm_init(Ctx* c, const uint8_t id_bytes[128], int rank, int world) {
   if (world < 1 || (world & (world - 1)) || world > kPubMaxReaders || rank < 0 || rank >= world)
     throw std::runtime_error("world must be a power of two <= 8 (one node)");
@@ -137,6 +158,24 @@ void comm_init(Ctx* c, const uint8_t id_bytes[128], int rank, int world) {
   if (world == 1) return;
   if (!c->h_pub) throw std::runtime_error("a sharded proof needs the mapped publication buffers (unset LASSO_B200_NO_MAPPED)");
   std::unique_ptr<Xchg> x(new Xchg());
+  try {
+    comm_init_impl(c, x.get(), id_bytes, rank, world);
+  } catch (...) {  // a failed or timed-out rendezvous must not leave mappings, registrations or a shm name behind
+    xchg_release(x.get());
+    if (!c->h_pub_owned) {  // the publication buffer had already moved into the (now unmapped) segment
+      c->h_pub = nullptr;
+      for (int r = 0; r < kPubMaxReaders; r++) c->d_pub_reader[r] = nullptr;
+    }
+    if (c->d_gather) cudaFree(c->d_gather);
+    c->d_gather = nullptr;
+    c->world = 1;
+    c->rank = 0;
+    c->lg_world = 0;
+    throw;
+  }
+  c->xchg = x.release();
+}
+static void comm_init_impl(Ctx* c, Xchg* x, const uint8_t id_bytes[128], int rank, int world) {
   x->world = world;
   x->rank = rank;
   x->seg_bytes = kSegHeaderBytes + Ctx::kPubBytes;
@@ -236,7 +275,6 @@ void comm_init(Ctx* c, const uint8_t id_bytes[128], int rank, int world) {
   c->pub_seq = 0;
   c->gather_elems = 1 << 16;
   LB_CUDA_CHECK(cudaMalloc((void**)&c->d_gather, c->gather_elems * sizeof(fr_t)));
-  c->xchg = x.release();
 }
 
 void comm_destroy(Ctx* c) {
