@@ -287,6 +287,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    if world > 1:
+        # the first collective sets the NCCL communicator up (connections, proxy threads, buffers): do that here, not
+        # in the barrier that opens the timed region
+        dist.barrier()
+        torch.cuda.synchronize()
     C, log_m, log_s = 4, 16, args.log_s
     s = 1 << log_s
     S = lb.Strategy(lb.XOR, C, log_m)
