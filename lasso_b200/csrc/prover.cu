@@ -531,7 +531,7 @@ Dense* densify(Ctx* c, const uint64_t* indices, size_t n, size_t C, size_t log_m
       DBuf<uint32_t> d_idx(c, n * C), scratch(c, densify_scratch_words(s, (int)C, log_m));
       {
         const size_t total = n * C;
-        const size_t npieces = total >= (1u << 20) ? 32 : 1, nthreads = npieces > 1 ? (total >= (1u << 22) ? 8 : 4) : 1;
+        const size_t npieces = total >= (1u << 20) ? 64 : 1, nthreads = npieces > 1 ? (total >= (1u << 25) ? 16 : total >= (1u << 22) ? 8 : 4) : 1;
         std::vector<std::atomic<int>> done(npieces);
         for (auto& f : done) f.store(0);
         std::atomic<int> bad{0};

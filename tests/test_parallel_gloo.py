@@ -24,7 +24,19 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     ident = bytes(range(128)) if rank == 0 else b""
-    got = parallel.broadcast_bytes(ident, src=0)  # how the NCCL unique id travels
+    got = parallel.broadcast_bytes(ident, src=0)  # how the job id of a sharded proof travels
+    # the real thing: rank 0 draws the id through the C-ABI (no GPU needed for that call), every rank must end up with it
+    import ctypes
+
+    import lasso_b200 as lb
+
+    real = (ctypes.c_uint8 * 128)()
+    if rank == 0:
+        assert lb.lib().lasso_comm_unique_id(real) == 0
+    real_got = parallel.broadcast_bytes(bytes(real) if rank == 0 else b"", src=0)
+    allids = [None] * world
+    dist.all_gather_object(allids, real_got)
+    assert len(real_got) == 128 and all(x == allids[0] for x in allids) and any(b != 0 for b in real_got)
     mx = parallel.max_over_ranks([1.0 + rank, 5.0 - rank])  # timings: max over ranks
     # the partition rule: rank g holds X[i*G + g]; bound_poly_var_top pairs (i, i + n/2) stay on one rank
     n = 64
