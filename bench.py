@@ -459,7 +459,7 @@ def main():
             # reference bytes for the sharded proofs: a single-GPU proof of the same inputs, made by rank 0 right here
             if rank == 0:
                 for n in names:
-                    single[n] = prove_config(lb, ctx, n, 1, streams, torch.cuda.synchronize)
+                    single[n] = prove_config(lb, ctx, n, 2, streams, torch.cuda.synchronize)
             dist.barrier()
             sctx = lb.Context(local_rank)
             sctx.init_comm(rank, world)
