@@ -107,6 +107,10 @@ int lasso_msm(lasso_ctx*, const uint64_t* bases_affine, const uint64_t* scalars,
  * lasso_msm_job_naive evaluates the same sum by per-term double-and-add + a tree sum (an independent cross-check
  * for sizes the CPU oracle cannot reach). */
 typedef struct lasso_msm_job lasso_msm_job;
+/* The schedule the large MSM would use for n terms whose widest scalar has max_bits bits (no GPU needed): out = {window
+ * bits c (the reference's rule, msm/mod.rs:112-116, capped at 17), windows, scalar bits, buckets per window 2^(c-1), unit
+ * size, reduction levels, group size of level 0.., zero padded}. */
+int lasso_msm_plan_info(size_t n, unsigned max_bits, int out[16]);
 int lasso_msm_job_create(lasso_ctx*, const uint64_t* bases_affine, size_t n_pool, const uint64_t* scalars, size_t n,
                          lasso_msm_job** out);
 int lasso_msm_job_run(lasso_ctx*, lasso_msm_job*, int iters, double* avg_ms, uint64_t out_xytz[16], int info[8]);

@@ -41,6 +41,7 @@ extern "C" {
     pub fn lasso_msm(ctx: *mut lasso_ctx, bases: *const u64, scalars: *const u64, n: usize, out_xytz: *mut u64) -> c_int;
     pub fn lasso_commit_rows(ctx: *mut lasso_ctx, gens: *const u64, z: *const u64, l_size: usize, r_size: usize,
                              out_points: *mut u64) -> c_int;
+    pub fn lasso_msm_plan_info(n: usize, max_bits: u32, out: *mut c_int) -> c_int;
     pub fn lasso_msm_job_create(ctx: *mut lasso_ctx, bases: *const u64, n_pool: usize, scalars: *const u64, n: usize,
                                 out: *mut *mut lasso_msm_job) -> c_int;
     pub fn lasso_msm_job_run(ctx: *mut lasso_ctx, job: *mut lasso_msm_job, iters: c_int, avg_ms: *mut f64, out_xytz: *mut u64,

@@ -296,6 +296,21 @@ static void msm_job_once(lasso_msm_job* j) {
   launch_sum_raw_points(j->raw.p, c->world, 1, nullptr, nullptr, j->out_ext.p, c->st);
   g_launches += 1;
 }
+int lasso_msm_plan_info(size_t n, unsigned max_bits, int out[16]) {
+  LB_TRY
+  if (n == 0) return fail(LASSO_ERR_LENGTH, "msm plan: n >= 1");
+  const MsmLargePlan p = msm_large_plan(n, max_bits);
+  for (int i = 0; i < 16; i++) out[i] = 0;
+  out[0] = p.c;
+  out[1] = p.nw;
+  out[2] = p.nbits;
+  out[3] = (int)p.NB;
+  out[4] = (int)p.S;
+  out[5] = p.nlev;
+  for (int k = 0; k < p.nlev && k < 8; k++) out[6 + k] = (int)p.lev_L[k];
+  return 0;
+  LB_CATCH
+}
 int lasso_msm_job_create(lasso_ctx* h, const uint64_t* bases_affine, size_t n_pool, const uint64_t* scalars, size_t n,
                          lasso_msm_job** out) {
   LB_TRY_CTX(h)
