@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 DOC = json.load(open(os.path.join(HERE, "golden", "big_proofs.json")))
 
 
-@pytest.mark.parametrize("name", ["xor_c4_s14", "lt_c8_s14", "rc40_c4_s14"])
+@pytest.mark.parametrize("name", ["and_c1_s10", "xor_c4_s14", "lt_c8_s14", "rc40_c4_s14"])
 def test_oracle_reproduces_reduced_golden(name):
     g = DOC["cases"][name]
     kind, C, log_m, log_r, log_s, idx, r, tape_seed = wl.config_inputs(name)

@@ -25,7 +25,7 @@ def ctx():
     c.close()
 
 
-@pytest.mark.parametrize("name", ["xor_c4_s14", "lt_c8_s14", "rc40_c4_s14", "xor_c4_s20", "lt_c8_s22", "rc40_c4_s24"])
+@pytest.mark.parametrize("name", ["and_c1_s10", "xor_c4_s14", "lt_c8_s14", "rc40_c4_s14", "xor_c4_s20", "lt_c8_s22", "rc40_c4_s24"])
 def test_config_bytes_match_golden(ctx, name):
     import lasso_b200 as lb
     import oracle_lib as ol
