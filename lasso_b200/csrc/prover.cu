@@ -527,10 +527,18 @@ Dense* densify(Ctx* c, const uint64_t* indices, size_t n, size_t C, size_t log_m
         LB_CUDA_CHECK(cudaEventSynchronize(c->ev_stage));
         c->stage_busy = false;
       }
-      uint32_t* stage = c->stage(n * C);
-      DBuf<uint32_t> d_idx(c, n * C), scratch(c, densify_scratch_words(s, (int)C, log_m));
+      // One proof sharded over G ranks: every rank stages and uploads only ITS block of rows (1/G of the host work
+      // and of the PCIe bytes), the narrowed blocks are all-gathered over NVLink, and every rank sorts the whole
+      // sequence on its device and keeps its shard.
+      const size_t rows_per = G > 1 ? (((n + G - 1) / G + 3) & ~(size_t)3) : n;  // x C x 4 B: a multiple of 16 bytes
+      const size_t row0 = std::min(n, gr * rows_per), row1 = std::min(n, row0 + rows_per);
+      const size_t total = (row1 - row0) * C;  // elements this rank stages
+      const uint64_t* src = indices + row0 * C;
+      uint32_t* stage = c->stage(std::max<size_t>(total, 1));
+      DBuf<uint32_t> d_idx(c, G * rows_per * C), d_mine(c, G > 1 ? rows_per * C : 0);
+      DBuf<uint32_t> scratch(c, densify_scratch_words(s, (int)C, log_m));
+      uint32_t* d_dst = G > 1 ? d_mine.p : d_idx.p;
       {
-        const size_t total = n * C;
         const size_t npieces = total >= (1u << 20) ? 64 : 1, nthreads = npieces > 1 ? (total >= (1u << 25) ? 16 : total >= (1u << 22) ? 8 : 4) : 1;
         std::vector<std::atomic<int>> done(npieces);
         for (auto& f : done) f.store(0);
@@ -541,7 +549,7 @@ Dense* densify(Ctx* c, const uint64_t* indices, size_t n, size_t C, size_t log_m
             const size_t lo = total * p / npieces, hi = total * (p + 1) / npieces;
             int b = 0;
             for (size_t k = lo; k < hi; k++) {
-              uint64_t a = indices[k];
+              uint64_t a = src[k];
               if (a >= m) {
                 b = 1;
                 a = 0;
@@ -560,20 +568,33 @@ Dense* densify(Ctx* c, const uint64_t* indices, size_t n, size_t C, size_t log_m
           if (nthreads > 1) t0 = std::thread(conv, 0);
         }
         if (nthreads == 1) conv(0);
+        if (G > 1 && total < rows_per * C)  // a short (or empty) last block: the gathered matrix must not carry garbage
+          LB_CUDA_CHECK(cudaMemsetAsync(d_mine.p + total, 0, (rows_per * C - total) * sizeof(uint32_t), c->st));
         for (size_t p = 0; p < npieces; p++) {  // this thread feeds the copy engine in order
           while (!done[p].load(std::memory_order_acquire)) __builtin_ia32_pause();
           const size_t lo = total * p / npieces, hi = total * (p + 1) / npieces;
-          LB_CUDA_CHECK(cudaMemcpyAsync(d_idx.p + lo, stage + lo, (hi - lo) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->st));
+          if (hi > lo)
+            LB_CUDA_CHECK(cudaMemcpyAsync(d_dst + lo, stage + lo, (hi - lo) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->st));
         }
         if (t0.joinable()) t0.join();
         for (auto& t : th) t.join();
         LB_CUDA_CHECK(cudaEventRecord(c->ev_stage, c->st));
         c->stage_busy = true;
-        if (bad.load()) {
+        bool any_bad = bad.load() != 0;
+        if (G > 1) {
+          // every rank must reach the same verdict (densified.rs:46): the flags are summed through the round-message path
+          fr_t flag = fr_zero(), sum;
+          flag.v[0] = any_bad ? 1u : 0u;
+          c->h2d(c->d_small, &flag, sizeof flag);
+          reduce_to_host(c, c->d_small, 1, &sum);
+          any_bad = !fr_is_zero(sum);
+        }
+        if (any_bad) {
           c->sync();
           *err = 3;
           return nullptr;
         }
+        if (G > 1) comm_allgather(c, d_mine.p, d_idx.p, rows_per * C * sizeof(uint32_t));
       }
       if (nl > 2 * C * s_loc) LB_CUDA_CHECK(cudaMemsetAsync(d->d_l_u32.p + 2 * C * s_loc, 0, (nl - 2 * C * s_loc) * 4, c->st));
       if (nm > C * m_loc) LB_CUDA_CHECK(cudaMemsetAsync(d->d_m_u32.p + C * m_loc, 0, (nm - C * m_loc) * 4, c->st));

@@ -53,6 +53,21 @@ for kind, C, log_m, log_r, n, same in cases:
         print("case kind=%d C=%d log_m=%d n=%d world=%d: %s (%.1f ms, commit_ok=%s, first diverging challenge=%s)" % (
             kind, C, log_m, n, world, "OK" if good else "MISMATCH", dt * 1e3, com == ref["commitment"], first_bad), flush=True)
         ok = ok and good
+# an out-of-range index (densified.rs:46) in the LAST rank's block of rows: every rank must report it (the verdict is
+# agreed through the round-message path; nobody may be left waiting in the exchange that follows)
+n_bad = 1 << 12
+bad = np.zeros((n_bad, 2), dtype=np.uint64)
+bad[n_bad - 3, 1] = 1 << 8
+try:
+    lb.DensifiedRepresentation.from_lookup_indices(ctx, bad, 8)
+    bad_ok = False
+except lb.LassoError as e:
+    bad_ok = e.code == 3
+flags = [None] * world
+dist.all_gather_object(flags, bad_ok)
+if rank == 0:
+    print("out-of-range index reported on every rank: %s" % ("OK" if all(flags) else "MISMATCH %s" % flags), flush=True)
+    ok = ok and all(flags)
 # collective MSM: each rank holds a shard of the terms; the sum over ranks must equal the oracle's MSM of all terms
 n_all = 3000
 rng = np.random.default_rng(99)
