@@ -138,7 +138,6 @@ void launch_two_row_scalars(const fr_t* v, int scale, const fr_t& k, const fr_t&
                             const fr_t& t11, size_t n, fr_t* out, cudaStream_t st);
 void launch_bullet_scalars(const fr_t* a, const fr_t* w, size_t n_loc, size_t m, int G, int g, int a_rep, fr_t* sL,
                            fr_t* sR, cudaStream_t st);
-void launch_scale_strided(const fr_t* in, fr_t* out, size_t n, size_t stride, size_t off, const fr_t& k, cudaStream_t st);
 void launch_scale(const fr_t* in, fr_t* out, size_t n, const fr_t& k, cudaStream_t st);
 
 // ---- densify on the GPU (densify_kernels.cu; densified.rs:33-56): stable LSD radix sort by address ----

@@ -59,7 +59,6 @@ void launch_msm_rows_direct_u32(const pt_niels* M, size_t npts, const pt_niels* 
                                 size_t row_stride, int nrows, int ncols, int nw, int col_mul, int col_add, pt_ext* partials,
                                 fq_t* out_ext, uint32_t* out_comp, uint32_t* out_raw, cudaStream_t st);
 void msm_init_device();
-void launch_combine_points(const fq_t* in_ext, int n, fq_t* out_ext, uint32_t* out_comp, cudaStream_t st);
 
 // ---- one large variable-base MSM (msm_large.cu): the reference's Pippenger with a large window, buckets in HBM
 struct MsmLargePlan {

@@ -1137,35 +1137,4 @@ void launch_sum_raw_points(const uint32_t* raw, int nsrc, int nrows, uint32_t* o
   LB_LAUNCH_CHECK();
 }
 
-// sum of a few extended points + normalisation (used to add a blind*h term or combine rows)
-__global__ void combine_points_kernel(const fq_t* in_ext /*n x 4 ark*/, int n, fq_t* out_ext, uint32_t* out_comp) {
-  if (threadIdx.x || blockIdx.x) return;
-  pt_ext acc = pt_identity();
-  for (int i = 0; i < n; i++) {
-    pt_ext p;
-    p.X = fq_from_ark(in_ext[4 * i + 0]);
-    p.Y = fq_from_ark(in_ext[4 * i + 1]);
-    p.T = fq_from_ark(in_ext[4 * i + 2]);
-    p.Z = fq_from_ark(in_ext[4 * i + 3]);
-    acc = pt_add(acc, p);
-  }
-  fq_t x, y;
-  pt_to_affine_canonical(acc, x, y);
-  if (out_comp) {
-    uint32_t c[8];
-    pt_compress_canonical(x, y, c);
-    for (int l = 0; l < 8; l++) out_comp[l] = c[l];
-  }
-  if (out_ext) {
-    out_ext[0] = fq_to_ark(x);
-    out_ext[1] = fq_to_ark(y);
-    out_ext[2] = fq_to_ark(fq_mul(x, y));
-    out_ext[3] = fq_to_ark(fq_one());
-  }
-}
-void launch_combine_points(const fq_t* in_ext, int n, fq_t* out_ext, uint32_t* out_comp, cudaStream_t st) {
-  combine_points_kernel<<<1, 32, 0, st>>>(in_ext, n, out_ext, out_comp);
-  LB_LAUNCH_CHECK();
-}
-
 }  // namespace lb

@@ -1250,16 +1250,6 @@ void launch_two_row_scalars(const fr_t* v, int scale, const fr_t& k, const fr_t&
   two_row_scalars_kernel<<<grid_for(n + 2), kThreads, 0, st>>>(v, scale, k, t00, t01, t10, t11, n, out);
   LB_LAUNCH_CHECK();
 }
-// out[i] = in[i*stride + off] * k
-__global__ void __launch_bounds__(kThreads)
-    scale_strided_kernel(const fr_t* in, fr_t* out, size_t n, size_t stride, size_t off, fr_t k) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    st_fr(out + i, fr_mul(ld_fr(in + i * stride + off), k));
-}
-void launch_scale_strided(const fr_t* in, fr_t* out, size_t n, size_t stride, size_t off, const fr_t& k, cudaStream_t st) {
-  scale_strided_kernel<<<grid_for(n), kThreads, 0, st>>>(in, out, n, stride, off, k);
-  LB_LAUNCH_CHECK();
-}
 __global__ void __launch_bounds__(kThreads) scale_kernel(const fr_t* in, fr_t* out, size_t n, fr_t k) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     st_fr(out + i, fr_mul(ld_fr(in + i), k));
