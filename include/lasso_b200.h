@@ -82,6 +82,12 @@ int lasso_eq_evals(lasso_ctx*, const uint64_t* r, int ell, uint64_t* out);
  * one the eq polynomial.  evals_out receives sumcheck_poly_degree()+1 elements (t = 0..deg). */
 int lasso_sumcheck_round_arbitrary(lasso_ctx*, int strategy, int C, int log_M, int log_R,
                                    const uint64_t* const* polys, size_t len, uint64_t* evals_out);
+/* The step between two rounds of prove_arbitrary as the prover runs it: bind every polynomial's top variable to r
+ * (subprotocols/sumcheck.rs:247-253, in place: polys[k][0 .. len/2) are overwritten), then evaluate the next
+ * round over the bound polynomials (sumcheck.rs:179-237).  One fused pass for the strategies with a linear g.
+ * len >= 4. */
+int lasso_sumcheck_bind_round_arbitrary(lasso_ctx*, int strategy, int C, int log_M, int log_R, uint64_t* const* polys,
+                                        size_t len, const uint64_t r[4], uint64_t* evals_out);
 /* One round of prove_cubic_batched's evaluation loop  subprotocols/sumcheck.rs:49-93:
  * e0e2e3_out[3k..3k+3) = sum_i A_k B_k Ceq at t = 0, 2, 3. */
 int lasso_sumcheck_round_cubic(lasso_ctx*, int n_circuits, const uint64_t* const* A, const uint64_t* const* B,

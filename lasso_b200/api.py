@@ -177,6 +177,16 @@ def sumcheck_round_arbitrary(ctx, S, polys):
     return out
 
 
+def sumcheck_bind_round_arbitrary(ctx, S, polys, r):
+    """Bind every polynomial's top variable to r, then evaluate the next round: (bound polys, evals)."""
+    polys = [_fr(p).copy() for p in polys]
+    out = np.zeros((S.sumcheck_poly_degree + 1, 4), dtype=np.uint64)
+    n = polys[0].shape[0]
+    _chk(lib().lasso_sumcheck_bind_round_arbitrary(ctx._h, S.kind, S.C, S.log_m, S.log_r, _ptr_array(polys),
+                                                   C.c_size_t(n), _p(_fr(r)), _p(out)))
+    return [p[: n // 2] for p in polys], out
+
+
 def sumcheck_round_cubic(ctx, A, B, Ceq):
     A = [_fr(a) for a in A]
     B = [_fr(b) for b in B]

@@ -155,6 +155,32 @@ int lasso_sumcheck_round_arbitrary(lasso_ctx* h, int strategy, int C, int log_M,
   return 0;
   LB_CATCH
 }
+int lasso_sumcheck_bind_round_arbitrary(lasso_ctx* h, int strategy, int C, int log_M, int log_R, uint64_t* const* polys,
+                                        size_t len, const uint64_t r[4], uint64_t* evals_out) {
+  LB_TRY_CTX(h)
+  Strategy S = mkS(strategy, C, log_M, log_R);
+  if (!S.valid()) return fail(LASSO_ERR_STRATEGY, "unsupported strategy parameters");
+  if (!is_pow2(len) || len < 4) return fail(LASSO_ERR_NOT_POW2, "len must be a power of two >= 4");
+  Ctx* c = h->c;
+  const int np = S.num_memories() + 1, npts = S.sumcheck_poly_degree() + 1;
+  DBuf<fr_t> d(c, (size_t)np * len);
+  for (int k = 0; k < np; k++)
+    LB_CUDA_CHECK(cudaMemcpyAsync(d.p + (size_t)k * len, polys[k], len * 32, cudaMemcpyHostToDevice, c->st));
+  fr_t rr;
+  memcpy(&rr, r, 32);
+  Finalize f = c->fin_begin();
+  f.pub.ndst = 0;  // plain device result + copy on this entry point
+  if (!launch_sumcheck_bind_eval_arbitrary(S, d.p, len, len / 4, rr, f, c->st)) {
+    launch_bind_top(d.p, len, np, len / 2, rr, c->st);
+    launch_sumcheck_eval_arbitrary(S, d.p, len, len / 4, f, c->st);
+    g_launches += 1;
+  }
+  g_launches += 1;
+  c->d2h(evals_out, c->d_small, (size_t)npts * 32);
+  for (int k = 0; k < np; k++) c->d2h(polys[k], d.p + (size_t)k * len, (len / 2) * 32);
+  return 0;
+  LB_CATCH
+}
 int lasso_sumcheck_round_cubic(lasso_ctx* h, int n_circuits, const uint64_t* const* A, const uint64_t* const* B,
                                const uint64_t* Ceq, size_t len, uint64_t* out) {
   LB_TRY_CTX(h)

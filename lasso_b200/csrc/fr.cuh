@@ -323,6 +323,52 @@ LB_HD fr_t fr_mul(const fr_t& a, const fr_t& b) {
 }
 LB_HD fr_t fr_sqr(const fr_t& a) { return fr_mul(a, a); }
 
+// a * 2^k mod l for 0 <= k <= 31, without a Montgomery multiplication (the weights of combine_lookups are powers of
+// two: and.rs:45-53, range_check.rs:78-86).  With l = 2^252 + c, c < 2^125:  a 2^k = top 2^252 + low  ==  low - top c,
+// top < 2^(k+1), top c < 2^157 < l — one conditional addition of l makes the result canonical.  The same residue as
+// fr_mul(a, fr_from_u64(1 << k)), hence the same bits.
+LB_HD fr_t fr_mul_pow2(const fr_t& a, int k) {
+  if (k == 0) return a;
+  LB_CF_DECL
+  uint32_t y[8];
+  y[0] = a.v[0] << k;
+#pragma unroll
+  for (int i = 1; i < 7; i++) y[i] = (a.v[i] << k) | (a.v[i - 1] >> (32 - k));
+  const uint64_t y78 = ((uint64_t)a.v[7] << k) | (a.v[6] >> (32 - k));  // a.v[7] < 2^29: below 2^60
+  const uint32_t top = (uint32_t)(y78 >> 28);
+  y[7] = (uint32_t)y78 & 0x0fffffffu;
+  uint32_t m[5];
+  uint64_t t = (uint64_t)top * LB_FR_P0;
+  m[0] = (uint32_t)t;
+  t = (t >> 32) + (uint64_t)top * LB_FR_P1;
+  m[1] = (uint32_t)t;
+  t = (t >> 32) + (uint64_t)top * LB_FR_P2;
+  m[2] = (uint32_t)t;
+  t = (t >> 32) + (uint64_t)top * LB_FR_P3;
+  m[3] = (uint32_t)t;
+  m[4] = (uint32_t)(t >> 32);
+  uint32_t d[8], bw;
+  LB_SUB_CC(d[0], y[0], m[0]);
+  LB_SUBC_CC(d[1], y[1], m[1]);
+  LB_SUBC_CC(d[2], y[2], m[2]);
+  LB_SUBC_CC(d[3], y[3], m[3]);
+  LB_SUBC_CC(d[4], y[4], m[4]);
+  LB_SUBC_CC(d[5], y[5], 0u);
+  LB_SUBC_CC(d[6], y[6], 0u);
+  LB_SUBC_CC(d[7], y[7], 0u);
+  LB_SUBC(bw, 0u, 0u);  // all-ones iff low < top c
+  fr_t r;
+  LB_ADD_CC(r.v[0], d[0], bw & LB_FR_P0);
+  LB_ADDC_CC(r.v[1], d[1], bw & LB_FR_P1);
+  LB_ADDC_CC(r.v[2], d[2], bw & LB_FR_P2);
+  LB_ADDC_CC(r.v[3], d[3], bw & LB_FR_P3);
+  LB_ADDC_CC(r.v[4], d[4], 0u);
+  LB_ADDC_CC(r.v[5], d[5], 0u);
+  LB_ADDC_CC(r.v[6], d[6], 0u);
+  LB_ADDC(r.v[7], d[7], bw & LB_FR_P7);
+  return r;
+}
+
 // F::from(u64): v * R mod l
 LB_HD fr_t fr_from_u64(uint64_t x) {
   fr_t t = fr_zero();

@@ -174,23 +174,61 @@ __global__ void __launch_bounds__(kThreads) reduce_partials_kernel(const fr_t* p
 // sumcheck.rs:179-237 for the strategies whose g is linear in the E_k:
 //   g(E, eq) = (sum_k 2^(k*inc) E_k) * eq      (and.rs:45-53, or.rs, xor.rs, range_check.rs:78-86)
 // degree 2 -> evaluation points t = 0, 1, 2 with P(t) = lo + t (hi - lo) built incrementally.
+// The weighted sum is a Horner chain of shifts (fr_mul_pow2: ~35 instructions against ~250 for a Montgomery
+// multiplication), which leaves 3 multiplications per index pair and makes the big rounds HBM-bound.
 // Reads 2 * 32 B per polynomial per index pair (64 B/pair/poly algorithmic).
 __global__ void __launch_bounds__(kThreads)
-    sc_eval_linear_kernel(const fr_t* base, size_t stride, int alpha, size_t half, FrVec w, Finalize fin) {
+    sc_eval_linear_kernel(const fr_t* base, size_t stride, int alpha, size_t half, int inc, Finalize fin) {
   __shared__ fr_t scratch[3 * kThreads / 32];
   fr_t acc[3] = {fr_zero(), fr_zero(), fr_zero()};
   const fr_t* eq = base + (size_t)alpha * stride;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
-    fr_t c0 = ld_fr_stream(base + i), c1 = ld_fr_stream(base + half + i);  // weight 2^0
-    for (int k = 1; k < alpha; k++) {
-      const fr_t* P = base + (size_t)k * stride;
-      c0 = fr_add(c0, fr_mul(w.v[k], ld_fr_stream(P + i)));
-      c1 = fr_add(c1, fr_mul(w.v[k], ld_fr_stream(P + half + i)));
+    const fr_t* P = base + (size_t)(alpha - 1) * stride;
+    fr_t c0 = ld_fr_stream(P + i), c1 = ld_fr_stream(P + half + i);
+    for (int k = alpha - 2; k >= 0; k--) {
+      P = base + (size_t)k * stride;
+      c0 = fr_add(fr_mul_pow2(c0, inc), ld_fr_stream(P + i));
+      c1 = fr_add(fr_mul_pow2(c1, inc), ld_fr_stream(P + half + i));
     }
     fr_t q0 = ld_fr_stream(eq + i), q1 = ld_fr_stream(eq + half + i);
     acc[0] = fr_add(acc[0], fr_mul(c0, q0));
     acc[1] = fr_add(acc[1], fr_mul(c1, q1));
     fr_t c2 = fr_sub(fr_dbl(c1), c0), q2 = fr_sub(fr_dbl(q1), q0);
+    acc[2] = fr_add(acc[2], fr_mul(c2, q2));
+  }
+  block_sum_fr<3>(acc, scratch);
+  finalize_block<3>(fin, acc, 0, blockIdx.x, gridDim.x, 3, gridDim.x);
+}
+
+// The bind of round j-1 (sumcheck.rs:247-253, dense_mlpoly.rs:209-216) and the evaluation of round j in ONE pass
+// over the polynomials: thread i owns the four elements i, i+q, i+2q, i+3q of every polynomial (q = a quarter of
+// the length before the bind), folds them to the two elements i, i+q of the bound polynomial, stores those in place
+// and feeds them to round j's sums.  192 B per poly per i instead of 96 + 96 (bind) + 64 + 64 (evaluation).
+__global__ void __launch_bounds__(kThreads)
+    sc_bind_eval_linear_kernel(fr_t* base, size_t stride, int alpha, size_t q, fr_t r, int inc, Finalize fin) {
+  __shared__ fr_t scratch[3 * kThreads / 32];
+  fr_t acc[3] = {fr_zero(), fr_zero(), fr_zero()};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < q; i += (size_t)gridDim.x * blockDim.x) {
+    fr_t c0 = fr_zero(), c1 = fr_zero();
+    for (int k = alpha - 1; k >= 0; k--) {
+      fr_t* P = base + (size_t)k * stride;
+      const fr_t a0 = ld_fr_stream(P + i), a1 = ld_fr_stream(P + q + i);
+      const fr_t a2 = ld_fr_stream(P + 2 * q + i), a3 = ld_fr_stream(P + 3 * q + i);
+      const fr_t n0 = fr_add(a0, fr_mul(r, fr_sub(a2, a0))), n1 = fr_add(a1, fr_mul(r, fr_sub(a3, a1)));
+      st_fr(P + i, n0);
+      st_fr(P + q + i, n1);
+      c0 = fr_add(fr_mul_pow2(c0, inc), n0);
+      c1 = fr_add(fr_mul_pow2(c1, inc), n1);
+    }
+    fr_t* E = base + (size_t)alpha * stride;
+    const fr_t e0 = ld_fr_stream(E + i), e1 = ld_fr_stream(E + q + i);
+    const fr_t e2 = ld_fr_stream(E + 2 * q + i), e3 = ld_fr_stream(E + 3 * q + i);
+    const fr_t q0 = fr_add(e0, fr_mul(r, fr_sub(e2, e0))), q1 = fr_add(e1, fr_mul(r, fr_sub(e3, e1)));
+    st_fr(E + i, q0);
+    st_fr(E + q + i, q1);
+    acc[0] = fr_add(acc[0], fr_mul(c0, q0));
+    acc[1] = fr_add(acc[1], fr_mul(c1, q1));
+    const fr_t c2 = fr_sub(fr_dbl(c1), c0), q2 = fr_sub(fr_dbl(q1), q0);
     acc[2] = fr_add(acc[2], fr_mul(c2, q2));
   }
   block_sum_fr<3>(acc, scratch);
@@ -380,12 +418,8 @@ __global__ void __launch_bounds__(128)
   finalize_last_stage(fin, gridDim.x, NP);
 }
 
-static FrVec linear_weights(const Strategy& S) {
-  FrVec w;
-  int inc = S.kind == STRAT_RANGE ? S.log_m : S.log_m / 2;
-  for (int k = 0; k < S.num_memories(); k++) w.v[k] = fr_from_u64(1ull << (k * inc));  // F::from(1u64 << (i*inc))
-  return w;
-}
+// combine_lookups weights are F::from(1u64 << (i * inc)): inc = log2 of the chunk size (and.rs:45-53, range_check.rs:78-86)
+static int linear_inc(const Strategy& S) { return S.kind == STRAT_RANGE ? S.log_m : S.log_m / 2; }
 
 template <int C>
 static void launch_lt(const fr_t* base, size_t stride, size_t half, const Finalize& fin, int blocks, cudaStream_t st) {
@@ -420,20 +454,30 @@ void launch_sumcheck_eval_arbitrary(const Strategy& S, const fr_t* base, size_t 
     }
   } else {
     blocks = grid_for(half);
-    sc_eval_linear_kernel<<<blocks, kThreads, 0, st>>>(base, stride, S.num_memories(), half, linear_weights(S), fin);
+    sc_eval_linear_kernel<<<blocks, kThreads, 0, st>>>(base, stride, S.num_memories(), half, linear_inc(S), fin);
     LB_LAUNCH_CHECK();
   }
+}
+// bind with r (length 4q -> 2q) then evaluate the round over the bound polynomials, one launch; only the strategies
+// with a linear g have a fused kernel (false: the caller binds and evaluates separately)
+bool launch_sumcheck_bind_eval_arbitrary(const Strategy& S, fr_t* base, size_t stride, size_t q, const fr_t& r,
+                                         const Finalize& fin, cudaStream_t st) {
+  if (S.kind == STRAT_LT || q == 0) return false;
+  // 128 registers: two resident CTAs per SM, one wave
+  sc_bind_eval_linear_kernel<<<grid_for(q, kThreads, kNumSMs * 2), kThreads, 0, st>>>(base, stride, S.num_memories(), q, r, linear_inc(S), fin);
+  LB_LAUNCH_CHECK();
+  return true;
 }
 
 // subtables/mod.rs:186-216: sum_k eq[k] * g(E_1[k], ..., E_alpha[k]) over the whole hypercube
 __global__ void __launch_bounds__(kThreads)
-    claim_linear_kernel(const fr_t* base, size_t stride, int alpha, size_t n, FrVec w, fr_t* partial) {
+    claim_linear_kernel(const fr_t* base, size_t stride, int alpha, size_t n, int inc, fr_t* partial) {
   __shared__ fr_t scratch[kThreads / 32];
   fr_t acc[1] = {fr_zero()};
   const fr_t* eq = base + (size_t)alpha * stride;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    fr_t c = ld_fr_stream(base + i);
-    for (int k = 1; k < alpha; k++) c = fr_add(c, fr_mul(w.v[k], ld_fr_stream(base + (size_t)k * stride + i)));
+    fr_t c = ld_fr_stream(base + (size_t)(alpha - 1) * stride + i);
+    for (int k = alpha - 2; k >= 0; k--) c = fr_add(fr_mul_pow2(c, inc), ld_fr_stream(base + (size_t)k * stride + i));
     acc[0] = fr_add(acc[0], fr_mul(c, ld_fr_stream(eq + i)));
   }
   block_sum_fr<1>(acc, scratch);
@@ -461,7 +505,7 @@ void launch_sumcheck_claim(const Strategy& S, const fr_t* base, size_t stride, s
   if (S.kind == STRAT_LT)
     claim_lt_kernel<<<blocks, kThreads, 0, st>>>(base, stride, S.C, n, partial);
   else
-    claim_linear_kernel<<<blocks, kThreads, 0, st>>>(base, stride, S.num_memories(), n, linear_weights(S), partial);
+    claim_linear_kernel<<<blocks, kThreads, 0, st>>>(base, stride, S.num_memories(), n, linear_inc(S), partial);
   LB_LAUNCH_CHECK();
   reduce_partials_kernel<<<1, kThreads, 0, st>>>(partial, blocks, out);
   LB_LAUNCH_CHECK();

@@ -775,8 +775,20 @@ static SumcheckProof prove_arbitrary(Ctx* c, const Strategy& S, fr_t* base, size
   DBuf<fr_t> tail;
   bool sharded = c->world > 1;
   size_t len = len_loc;
+  // The bind of a round is deferred into the next round's evaluation launch where the strategy has a fused kernel
+  // (one pass over the polynomials per round instead of two); `pending` = the polynomials still have length 2*len
+  static const bool unfused = getenv("LASSO_B200_UNFUSED_PRIMARY") != nullptr;
+  bool pending = false;
+  fr_t r_pending = fr_zero();
+  auto flush_bind = [&]() {
+    if (!pending) return;
+    launch_bind_top(base, stride, npolys, len, r_pending, c->st);
+    g_launches += 1;
+    pending = false;
+  };
   for (;;) {
     if (sharded && len == 1) {  // hand over to the replicated tail
+      flush_bind();
       tail.alloc(c, (size_t)npolys * c->world);
       comm_gather_heads(c, nullptr, base, stride, npolys, nullptr, tail.p);
       base = tail.p;
@@ -788,7 +800,12 @@ static SumcheckProof prove_arbitrary(Ctx* c, const Strategy& S, fr_t* base, size
     size_t half = len / 2;
     {  // sharded: every rank's partial sums go to every process, the hosts add them; else this process only
       Finalize f = c->fin_begin(sharded);
-      launch_sumcheck_eval_arbitrary(S, base, stride, half, f, c->st);
+      if (pending && launch_sumcheck_bind_eval_arbitrary(S, base, stride, half, r_pending, f, c->st)) {
+        pending = false;
+      } else {
+        flush_bind();
+        launch_sumcheck_eval_arbitrary(S, base, stride, half, f, c->st);
+      }
       if (f.pub.ndst)
         c->fin_wait(f, evals.data(), npts);
       else
@@ -799,11 +816,13 @@ static SumcheckProof prove_arbitrary(Ctx* c, const Strategy& S, fr_t* base, size
     unipoly_append(coeffs, transcript);
     fr_t r_j = transcript.challenge_scalar("challenge_nextround");
     r.push_back(r_j);
-    launch_bind_top(base, stride, npolys, half, r_j, c->st);
-    g_launches += 1;
     proof.push_back(unipoly_compress(coeffs));
     len = half;
+    pending = true;
+    r_pending = r_j;
+    if (unfused) flush_bind();
   }
+  flush_bind();
   return proof;
 }
 

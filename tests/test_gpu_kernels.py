@@ -86,6 +86,35 @@ def test_sumcheck_round_arbitrary(ctx, kind, C, log_m, log_r, log_len):
     assert (got == ref).all()
 
 
+@pytest.mark.parametrize("kind,C,log_m,log_r", CASES + [(2, 8, 16, 0), (4, 2, 24, 40), (0, 16, 6, 0)])
+@pytest.mark.parametrize("log_len", [2, 5, 14, 17])
+def test_sumcheck_bind_round_arbitrary(ctx, kind, C, log_m, log_r, log_len):
+    """The bind between two rounds fused with the next round's evaluation (sumcheck.rs:247-253 + 179-237): the bound
+    polynomials and the round's evaluations against the oracle's bind followed by its round evaluation."""
+    import lasso_b200 as lb
+
+    S = lb.Strategy(kind, C, log_m, log_r)
+    if log_len == 17 and S.num_memories > 8:
+        pytest.skip("covered at 2^14")
+    rng = np.random.default_rng(kind * 1000 + C * 10 + log_len)
+    n = 1 << log_len
+    np_ = S.num_memories + 1
+    polys = ol.rand_fr(rng, np_ * n).reshape(np_, n, 4)
+    polys[0][: min(n, 8)] = edge_fr()[: min(n, 8)]
+    for r in [ol.rand_fr(rng, 1)[0], ol.fr_array([0])[0], ol.fr_array([ol.L_FR - 1])[0]]:
+        bound = np.zeros((np_, n // 2, 4), dtype=np.uint64)
+        for k in range(np_):
+            z = polys[k].copy()
+            orc().orc_bind(1, P(z), sz(n), P(np.ascontiguousarray(r)))
+            bound[k] = z[: n // 2]
+        ref = np.zeros((S.sumcheck_poly_degree + 1, 4), dtype=np.uint64)
+        orc().orc_sumcheck_round_arbitrary(kind, sz(C), sz(log_m), sz(log_r), P(np.ascontiguousarray(bound)), sz(n // 2), P(ref))
+        got_polys, got = lb.sumcheck_bind_round_arbitrary(ctx, S, [polys[k] for k in range(np_)], r)
+        assert (got == ref).all()
+        for k in range(np_):
+            assert (got_polys[k] == bound[k]).all()
+
+
 @pytest.mark.parametrize("ncirc,log_len", [(1, 1), (2, 3), (8, 10), (16, 14), (32, 6)])
 def test_sumcheck_round_cubic(ctx, ncirc, log_len):
     import lasso_b200 as lb

@@ -105,6 +105,29 @@ int main() {
     fr_t one = fr_one(), m1 = fr_sub(fr_zero(), one);
     if (!fr_eq(fr_inv(one), one) || !fr_eq(fr_inv(m1), m1)) bad++;
   }
+  // 2c. a * 2^k by shift-and-fold == Montgomery multiplication by F::from(1 << k), every k the weights of
+  // combine_lookups can take, on random elements and on the edges 0, 1, -1, l - 2^j
+  {
+    int pm = 0;
+    std::vector<fr_t> xs = {fr_zero(), fr_one(), fr_sub(fr_zero(), fr_one()), fr_from_u64(1), fr_sub(fr_zero(), fr_from_u64(1))};
+    fr_t x = a;
+    for (int i = 0; i < 3000; i++) {
+      x = fr_add(fr_mul(x, b), fr_from_u64(g()));
+      xs.push_back(x);
+    }
+    for (int j = 0; j < 64; j++) xs.push_back(fr_sub(fr_zero(), fr_from_u64(1ull << j)));
+    for (const fr_t& v : xs)
+      for (int k = 0; k <= 31; k++)
+        if (!fr_eq(fr_mul_pow2(v, k), fr_mul(v, fr_from_u64(1ull << k)))) pm++;
+    // also on raw residues just below l and at 2^252 (Montgomery form is just another residue)
+    fr_t top = {{LB_FR_P0 - 1, LB_FR_P1, LB_FR_P2, LB_FR_P3, 0, 0, 0, LB_FR_P7}}, mid = {{0, 0, 0, 0, 0, 0, 0, 0x10000000u}};
+    for (int k = 0; k <= 31; k++) {
+      if (!fr_eq(fr_mul_pow2(top, k), fr_mul(top, fr_from_u64(1ull << k)))) pm++;
+      if (!fr_eq(fr_mul_pow2(mid, k), fr_mul(mid, fr_from_u64(1ull << k)))) pm++;
+    }
+    if (pm) printf("fr_mul_pow2 mismatches: %d\n", pm);
+    bad += pm;
+  }
   // 3. host Fq64 normalisation == device-code normalisation + ark compression
   fq_t bx = {{0x8f25d51au, 0xc9562d60u, 0x9525a7b2u, 0x692cc760u, 0xfdd6dc5cu, 0xc0a4e231u, 0xcd6e53feu, 0x216936d3u}};
   fq_t by = {{0x66666658u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u}};
