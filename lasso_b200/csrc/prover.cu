@@ -777,7 +777,7 @@ static SumcheckProof prove_arbitrary(Ctx* c, const Strategy& S, fr_t* base, size
   size_t len = len_loc;
   // The bind of a round is deferred into the next round's evaluation launch where the strategy has a fused kernel
   // (one pass over the polynomials per round instead of two); `pending` = the polynomials still have length 2*len
-  static const bool unfused = getenv("LASSO_B200_UNFUSED_PRIMARY") != nullptr;
+  const bool unfused = getenv("LASSO_B200_UNFUSED_PRIMARY") != nullptr;  // read per proof: A/B runs in one process
   bool pending = false;
   fr_t r_pending = fr_zero();
   auto flush_bind = [&]() {
