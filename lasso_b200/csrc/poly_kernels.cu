@@ -204,7 +204,8 @@ __global__ void __launch_bounds__(kThreads)
 // over the polynomials: thread i owns the four elements i, i+q, i+2q, i+3q of every polynomial (q = a quarter of
 // the length before the bind), folds them to the two elements i, i+q of the bound polynomial, stores those in place
 // and feeds them to round j's sums.  192 B per poly per i instead of 96 + 96 (bind) + 64 + 64 (evaluation).
-__global__ void __launch_bounds__(kThreads)
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
     sc_bind_eval_linear_kernel(fr_t* base, size_t stride, int alpha, size_t q, fr_t r, int inc, Finalize fin) {
   __shared__ fr_t scratch[3 * kThreads / 32];
   fr_t acc[3] = {fr_zero(), fr_zero(), fr_zero()};
@@ -463,8 +464,14 @@ void launch_sumcheck_eval_arbitrary(const Strategy& S, const fr_t* base, size_t 
 bool launch_sumcheck_bind_eval_arbitrary(const Strategy& S, fr_t* base, size_t stride, size_t q, const fr_t& r,
                                          const Finalize& fin, cudaStream_t st) {
   if (S.kind == STRAT_LT || q == 0) return false;
-  // 128 registers: two resident CTAs per SM, one wave
-  sc_bind_eval_linear_kernel<<<grid_for(q, kThreads, kNumSMs * 2), kThreads, 0, st>>>(base, stride, S.num_memories(), q, r, linear_inc(S), fin);
+  // resident CTAs per SM the kernel is compiled for: 2 (128 registers) or 3 (80 registers, a few spilled words);
+  // the grid is one wave of those
+  static const int minb = bind_env("LASSO_B200_FUSED_MINB", 2);
+  const int alpha = S.num_memories(), inc = linear_inc(S);
+  if (minb == 3)
+    sc_bind_eval_linear_kernel<3><<<grid_for(q, kThreads, kNumSMs * 3), kThreads, 0, st>>>(base, stride, alpha, q, r, inc, fin);
+  else
+    sc_bind_eval_linear_kernel<2><<<grid_for(q, kThreads, kNumSMs * 2), kThreads, 0, st>>>(base, stride, alpha, q, r, inc, fin);
   LB_LAUNCH_CHECK();
   return true;
 }
