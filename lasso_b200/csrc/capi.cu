@@ -170,7 +170,7 @@ int lasso_sumcheck_bind_round_arbitrary(lasso_ctx* h, int strategy, int C, int l
   memcpy(&rr, r, 32);
   Finalize f = c->fin_begin();
   f.pub.ndst = 0;  // plain device result + copy on this entry point
-  if (!launch_sumcheck_bind_eval_arbitrary(S, d.p, len, len / 4, rr, f, c->st)) {
+  if (!launch_sumcheck_bind_eval_arbitrary(S, d.p, len, len / 4, rr, f, 1, c->st)) {
     launch_bind_top(d.p, len, np, len / 2, rr, c->st);
     launch_sumcheck_eval_arbitrary(S, d.p, len, len / 4, f, c->st);
     g_launches += 1;

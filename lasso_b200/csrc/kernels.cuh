@@ -58,9 +58,10 @@ void launch_eq_evals(const FrVec& r, int ell, fr_t* out, fr_t* scratch, cudaStre
 void launch_sumcheck_eval_arbitrary(const Strategy& S, const fr_t* base, size_t stride, size_t half, const Finalize& fin,
                                     cudaStream_t st);
 // The previous round's bind (with r) fused with this round's evaluation: base holds polynomials of length 4q, bound
-// in place to 2q.  Returns false (nothing launched) when the strategy has no fused kernel.
+// in place to 2q.  Returns false (nothing launched) when the strategy has no fused kernel or q < min_q (0: the
+// default threshold below which a round is latency-bound and two short launches are quicker).
 bool launch_sumcheck_bind_eval_arbitrary(const Strategy& S, fr_t* base, size_t stride, size_t q, const fr_t& r,
-                                         const Finalize& fin, cudaStream_t st);
+                                         const Finalize& fin, size_t min_q, cudaStream_t st);
 int sumcheck_max_blocks();
 
 // ---- K3: batched cubic round evaluation (sumcheck.rs:49-93) ----

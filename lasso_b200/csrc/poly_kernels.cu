@@ -461,9 +461,13 @@ void launch_sumcheck_eval_arbitrary(const Strategy& S, const fr_t* base, size_t 
 }
 // bind with r (length 4q -> 2q) then evaluate the round over the bound polynomials, one launch; only the strategies
 // with a linear g have a fused kernel (false: the caller binds and evaluates separately)
+// Measured (tools/ab_primary.py, XOR C=4): at 2^24 lookups the fused rounds take 5 % off Sumcheck.prove; below
+// q = 2^15 a round is a latency chain and the longer per-thread chain of the fused kernel costs ~0.7 us more than
+// the two short launches it replaces — those rounds stay unfused (min_q = 0: that default; 1: always fuse).
 bool launch_sumcheck_bind_eval_arbitrary(const Strategy& S, fr_t* base, size_t stride, size_t q, const fr_t& r,
-                                         const Finalize& fin, cudaStream_t st) {
-  if (S.kind == STRAT_LT || q == 0) return false;
+                                         const Finalize& fin, size_t min_q, cudaStream_t st) {
+  static const size_t dflt_min_q = (size_t)bind_env("LASSO_B200_FUSED_MIN_Q", 1 << 15);
+  if (S.kind == STRAT_LT || q == 0 || q < (min_q ? min_q : dflt_min_q)) return false;
   // resident CTAs per SM the kernel is compiled for: 2 (128 registers) or 3 (80 registers, a few spilled words);
   // the grid is one wave of those
   static const int minb = bind_env("LASSO_B200_FUSED_MINB", 2);

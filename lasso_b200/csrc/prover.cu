@@ -800,7 +800,7 @@ static SumcheckProof prove_arbitrary(Ctx* c, const Strategy& S, fr_t* base, size
     size_t half = len / 2;
     {  // sharded: every rank's partial sums go to every process, the hosts add them; else this process only
       Finalize f = c->fin_begin(sharded);
-      if (pending && launch_sumcheck_bind_eval_arbitrary(S, base, stride, half, r_pending, f, c->st)) {
+      if (pending && launch_sumcheck_bind_eval_arbitrary(S, base, stride, half, r_pending, f, 0, c->st)) {
         pending = false;
       } else {
         flush_bind();

@@ -12,7 +12,7 @@ import lasso_b200 as lb
 log_s = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 pairs = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 C, log_m = 4, 16
-idx, r, seed = bench.make_inputs(log_s, C, log_m, 1)
+idx, r, seed = bench.make_inputs(log_s, C, log_m, bench.wl.BENCH_SEED)  # s = 2^20: the bench workload
 spans_on = os.environ.get("LASSO_B200_SPANS") == "1"  # the library then synchronises around every span
 ctx = lb.Context(0)
 S = lb.Strategy(lb.XOR, C, log_m)
