@@ -32,6 +32,8 @@ extern "C" {
     pub fn lasso_eq_evals(ctx: *mut lasso_ctx, r: *const u64, ell: c_int, out: *mut u64) -> c_int;
     pub fn lasso_sumcheck_round_arbitrary(ctx: *mut lasso_ctx, strategy: c_int, c: c_int, log_m: c_int, log_r: c_int,
                                           polys: *const *const u64, len: usize, evals_out: *mut u64) -> c_int;
+    pub fn lasso_sumcheck_bind_round_arbitrary(ctx: *mut lasso_ctx, strategy: c_int, c: c_int, log_m: c_int, log_r: c_int,
+                                               polys: *const *mut u64, len: usize, r: *const u64, evals_out: *mut u64) -> c_int;
     pub fn lasso_sumcheck_round_cubic(ctx: *mut lasso_ctx, n_circuits: c_int, a: *const *const u64, b: *const *const u64,
                                       ceq: *const u64, len: usize, e0e2e3_out: *mut u64) -> c_int;
     pub fn lasso_materialize_subtables(ctx: *mut lasso_ctx, strategy: c_int, c: c_int, log_m: c_int, log_r: c_int,
