@@ -99,7 +99,11 @@ def test_sumcheck_bind_round_arbitrary(ctx, kind, C, log_m, log_r, log_len):
     rng = np.random.default_rng(kind * 1000 + C * 10 + log_len)
     n = 1 << log_len
     np_ = S.num_memories + 1
-    polys = ol.rand_fr(rng, np_ * n).reshape(np_, n, 4)
+    if log_len >= 14:  # any residue below l is a field element in memory format: uniform below 2^252, made by numpy
+        polys = rng.integers(0, 1 << 64, size=(np_, n, 4), dtype=np.uint64)
+        polys[:, :, 3] &= np.uint64((1 << 60) - 1)
+    else:
+        polys = ol.rand_fr(rng, np_ * n).reshape(np_, n, 4)
     polys[0][: min(n, 8)] = edge_fr()[: min(n, 8)]
     for r in [ol.rand_fr(rng, 1)[0], ol.fr_array([0])[0], ol.fr_array([ol.L_FR - 1])[0]]:
         bound = np.zeros((np_, n // 2, 4), dtype=np.uint64)
