@@ -15,6 +15,9 @@
 // products and a shift instead of eight products.
 #pragma once
 #include <cstdint>
+#if !defined(__CUDA_ARCH__)
+#include "host_modinv.hpp"
+#endif
 
 #if defined(__CUDACC__)
 #define LB_HD __host__ __device__ __forceinline__
@@ -388,10 +391,9 @@ LB_HD fr_t fr_from_raw_int(const fr_t& raw) { return fr_mul(raw, fr_r2()); }
 
 #if !defined(__CUDA_ARCH__)
 namespace frh {
-// Inversion (u^-1 of every Bulletproofs round, the batching coefficients of a grand-product layer): the whole
-// exponentiation stays on 64-bit limbs; l - 2 = 2^252 + (125 bits) is walked with a fixed 4-bit window
-// (252 squarings + ~32 multiplications).
-inline fr_t inv(const fr_t& A) {
+// Inversion by exponentiation on 64-bit limbs; l - 2 = 2^252 + (125 bits) is walked with a fixed 4-bit window
+// (252 squarings + ~32 multiplications).  The comparator of the binary-GCD inversion below.
+inline fr_t inv_fermat(const fr_t& A) {
   // l - 2 = 2^252 + 0x14def9dea2f79cd65812631a5cf5d3eb
   static const uint64_t E[4] = {0x5812631a5cf5d3ebULL, 0x14def9dea2f79cd6ULL, 0x0ULL, 0x1000000000000000ULL};
   w4 tab[16];
@@ -408,6 +410,17 @@ inline fr_t inv(const fr_t& A) {
     if (d) acc = mul(acc, tab[d]);
   }
   return store(acc);
+}
+// Inversion on the critical path (u^-1 of every Bulletproofs round, the batching coefficients of a grand-product
+// layer): binary extended GCD on the residue (host_modinv.hpp, ~1.8 us against ~7 us for the exponentiation).
+// A = a R; the GCD returns A^-1 = a^-1 R^-1 as a plain residue; one Montgomery product with R^3 gives a^-1 R.
+inline fr_t inv(const fr_t& A) {
+  static const uint64_t kL[4] = {kP0, kP1, 0, kP3};
+  static const modinv::Modulus M = modinv::make_modulus(kL);
+  static const w4 r3 = mul(load(fr_r2()), load(fr_r2()));  // R^2 * R^2 * R^-1
+  w4 y = load(A), x;
+  modinv::inverse(y.v, M, x.v);
+  return store(mul(x, r3));
 }
 }  // namespace frh
 #endif

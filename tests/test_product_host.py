@@ -150,6 +150,67 @@ int main() {
     if (pm) printf("fr_mul_pow2 mismatches: %d\n", pm);
     bad += pm;
   }
+  // 2d. binary-GCD inversion (host_modinv.hpp) == the exponentiation, for both fields: zero, +-1, +-2^j, small values,
+  // non-canonical Fq inputs (q, q + 1, 2^256 - 1) and random elements
+  {
+    int im = 0;
+    auto chk_fr = [&](const fr_t& v) {
+      const fr_t i1 = fr_inv(v), i2 = frh::inv_fermat(v);
+      if (!fr_eq(i1, i2)) im++;
+      if (!fr_is_zero(v) && !fr_eq(fr_mul(v, i1), fr_one())) im++;
+    };
+    chk_fr(fr_zero());
+    chk_fr(fr_one());
+    chk_fr(fr_sub(fr_zero(), fr_one()));
+    for (int j = 0; j < 64; j++) {
+      chk_fr(fr_from_u64(1ull << j));
+      chk_fr(fr_sub(fr_zero(), fr_from_u64(1ull << j)));
+    }
+    for (int j = 0; j < 252; j++) {  // raw residues 2^j (any residue below l is an element in memory format)
+      fr_t t = fr_zero();
+      t.v[j >> 5] = 1u << (j & 31);
+      chk_fr(t);
+    }
+    for (uint64_t k = 1; k < 300; k++) chk_fr(fr_from_u64(k));
+    fr_t x = a;
+    for (int i = 0; i < 20000; i++) {
+      x = fr_add(fr_mul(x, b), fr_from_u64(g()));
+      chk_fr(x);
+    }
+    auto chk_fq = [&](const uint64_t y[4]) {
+      h64::fe Y;
+      memcpy(Y.v, y, 32);
+      const h64::fe i1 = h64::inv(Y), i2 = h64::canonical(h64::inv_fermat(Y));
+      if (memcmp(i1.v, i2.v, 32)) im++;
+    };
+    const uint64_t q[4] = {0xffffffffffffffedULL, 0xffffffffffffffffULL, 0xffffffffffffffffULL, 0x7fffffffffffffffULL};
+    uint64_t y[4] = {0, 0, 0, 0};
+    chk_fq(y);
+    chk_fq(q);
+    memcpy(y, q, 32);
+    y[0] += 1;
+    chk_fq(y);
+    for (int i = 0; i < 4; i++) y[i] = ~0ULL;
+    chk_fq(y);
+    for (int j = 0; j < 256; j++) {
+      uint64_t t[4] = {0, 0, 0, 0};
+      t[j >> 6] = 1ULL << (j & 63);
+      chk_fq(t);
+      t[0] |= 1;
+      chk_fq(t);
+    }
+    for (uint64_t k = 1; k < 300; k++) {
+      uint64_t t[4] = {k, 0, 0, 0};
+      chk_fq(t);
+    }
+    for (int i = 0; i < 20000; i++) {
+      uint64_t t[4] = {g(), g(), g(), g()};
+      if (i & 1) t[3] >>= (i % 64);
+      chk_fq(t);
+    }
+    if (im) printf("modinv mismatches: %d\n", im);
+    bad += im;
+  }
   // 3. host Fq64 normalisation == device-code normalisation + ark compression
   fq_t bx = {{0x8f25d51au, 0xc9562d60u, 0x9525a7b2u, 0x692cc760u, 0xfdd6dc5cu, 0xc0a4e231u, 0xcd6e53feu, 0x216936d3u}};
   fq_t by = {{0x66666658u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u}};
