@@ -355,17 +355,31 @@ __global__ void publish_fr_kernel(const fr_t* src, int count, PubDst pub) {
     pub_store(pub, v, x.v);
   }
 }
-static void reduce_to_host(Ctx* c, fr_t* d_buf, int count, fr_t* h_out) {
+// In two halves so that host work can sit between the launch and the wait; `f.pub.ndst == 0` after _begin: no
+// publication buffers, _end copies synchronously.
+static Finalize reduce_to_host_begin(Ctx* c, fr_t* d_buf, int count) {
   if (!c->h_pub || count > kPubElems) {
     if (c->world > 1) throw std::runtime_error("sharded proof without publication buffers");
-    c->d2h(h_out, d_buf, (size_t)count * sizeof(fr_t));
-    return;
+    Finalize f{};
+    f.pub.ndst = 0;
+    return f;
   }
   Finalize f = c->fin_begin(true);
   publish_fr_kernel<<<1, 128, 0, c->st>>>(d_buf, count, f.pub);
   LB_LAUNCH_CHECK();
   g_launches += 1;
+  return f;
+}
+static void reduce_to_host_end(Ctx* c, const Finalize& f, fr_t* d_buf, int count, fr_t* h_out) {
+  if (f.pub.ndst == 0) {
+    c->d2h(h_out, d_buf, (size_t)count * sizeof(fr_t));
+    return;
+  }
   c->fin_wait(f, h_out, count);
+}
+static void reduce_to_host(Ctx* c, fr_t* d_buf, int count, fr_t* h_out) {
+  const Finalize f = reduce_to_host_begin(c, d_buf, count);
+  reduce_to_host_end(c, f, d_buf, count, h_out);
 }
 // this rank's shard of eq(r[off .. off+ell)) (eq_poly.rs:21-38): eq[i*G + g] = eq_hi[i] * eq_lo[g] where
 // eq_lo is the table of the LAST log2(G) coordinates (they bind the low index bits: r[0] <-> MSB)
@@ -1452,18 +1466,22 @@ std::vector<uint8_t> prove(Ctx* c, const Strategy& S, Dense& dense, const std::v
     }
   }
   ByteWriter w;
+  std::vector<uint8_t> comm_E;
   // ---- comm_derefs (surge.rs:136-140, subtables/mod.rs:177-184, 382-393)
   {
     SpanTimer sp(c, "Subtables.commit");
     unsigned tbits = S.kind == STRAT_LT ? 1 : (S.kind == STRAT_RANGE ? (unsigned)S.log_m : (unsigned)(S.log_m / 2));
-    std::vector<uint8_t> comm = commit_u32(c, g, E_u32.p, nv_d, tbits);
+    comm_E = commit_u32(c, g, E_u32.p, nv_d, tbits);
+    w.vec_pts(comm_E);
+  }
+  auto absorb_comm_E = [&]() {  // ~700 Keccak permutations (2^11 points): done while the device prepares the sumcheck
     transcript.append_message("subtable_evals_commitment", std::string("begin_subtable_evals_commitment"));
     transcript.append_message("comm_poly_row_col_ops_val", std::string("poly_commitment_begin"));
-    for (size_t i = 0; i < comm.size() / 32; i++) transcript.append_point_compressed("poly_commitment_share", comm.data() + 32 * i);
+    for (size_t i = 0; i < comm_E.size() / 32; i++)
+      transcript.append_point_compressed("poly_commitment_share", comm_E.data() + 32 * i);
     transcript.append_message("comm_poly_row_col_ops_val", std::string("poly_commitment_end"));
     transcript.append_message("subtable_evals_commitment", std::string("end_subtable_evals_commitment"));
-    w.vec_pts(comm);
-  }
+  };
   // ---- primary sumcheck (surge.rs:142-172)
   std::vector<fr_t> r_z;
   {
@@ -1473,7 +1491,9 @@ std::vector<uint8_t> prove(Ctx* c, const Strategy& S, Dense& dense, const std::v
     launch_sumcheck_claim(S, Wk.p, s_loc, s_loc, c->d_partial, c->d_small, c->st);  // subtables/mod.rs:186-216
     g_launches += 2;
     fr_t claimed_eval;
-    reduce_to_host(c, c->d_small, 1, &claimed_eval);
+    const Finalize fclaim = reduce_to_host_begin(c, c->d_small, 1);
+    absorb_comm_E();  // transcript order unchanged: the commitment, then the claim
+    reduce_to_host_end(c, fclaim, c->d_small, 1, &claimed_eval);
     transcript.append_scalar("claim_eval_scalar_product", claimed_eval);
     SumcheckProof primary = prove_arbitrary(c, S, Wk.p, s_loc, s_loc, transcript, r_z);
     ser_sumcheck(w, primary);
