@@ -15,7 +15,7 @@ namespace lb {
 // The permutation is the host's largest single cost inside a proof (a 2^20-lookup proof absorbs ~0.7 MB through
 // 4337 permutations: four 2048-scalar `a` vectors, the commitments, every round message and challenge), and it is
 // on the critical path between kernel launches.  On x86-64 the same source (keccak_f1600_body.inc) is compiled a
-// second time for x86-64-v3 (ANDN for chi, RORX for rho, three-operand forms: -40 % time) and chosen at run time.
+// second time for x86-64-v3 (ANDN for chi, RORX for rho, three-operand forms: -35 % on an absorb) and chosen at run time.
 #if defined(__x86_64__) && defined(__GNUC__) && !defined(__CUDA_ARCH__) && !defined(LB_KECCAK_NO_DISPATCH)
 #define LB_KECCAK_DISPATCH 1
 #else
