@@ -93,6 +93,16 @@ class Context:
         h = C.c_void_p()
         _chk(lib().lasso_ctx_create(C.byref(h), int(device)))
         self._h = h
+        self._scratch = {}
+
+    def _buf(self, name, shape, dtype):
+        """Output staging reused across calls (a fresh 4 MiB np.zeros per commit / prove is an mmap + page faults +
+        munmap inside the caller's timed region); contents are overwritten by the library before they are read."""
+        b = self._scratch.get(name)
+        if b is None or b.shape != tuple(np.atleast_1d(shape)) or b.dtype != np.dtype(dtype):
+            b = np.zeros(shape, dtype=dtype)
+            self._scratch[name] = b
+        return b
 
     def close(self):
         if self._h:
@@ -346,7 +356,7 @@ class DensifiedRepresentation:
 
     def commit(self, gens):
         cap = 1 << 22
-        out = np.zeros(cap, dtype=np.uint8)
+        out = self.ctx._buf("commitment", cap, np.uint8)
         n = C.c_size_t(0)
         _chk(lib().lasso_commit(self.ctx._h, self._h, gens._h, _p(out), C.c_size_t(cap), C.byref(n)))
         return bytes(out[: n.value])
@@ -370,8 +380,8 @@ class SparsePolynomialEvaluationProof:
         r = _fr(r).reshape(-1, 4)
         seed = _fr(tape_seed if tape_seed is not None else np.zeros(4, dtype=np.uint64))
         cap = 1 << 22
-        out = np.zeros(cap, dtype=np.uint8)
-        chal = np.zeros((1 << 14, 4), dtype=np.uint64)
+        out = ctx._buf("proof", cap, np.uint8)
+        chal = ctx._buf("challenges", (1 << 14, 4), np.uint64)
         n, nch = C.c_size_t(0), C.c_size_t(0)
         _chk(lib().lasso_prove(ctx._h, strategy.kind, strategy.log_r, dense._h, _p(r), C.c_size_t(r.shape[0]), gens._h,
                                transcript_label, tape_label, _p(seed), _p(out), C.c_size_t(cap), C.byref(n), _p(chal),
