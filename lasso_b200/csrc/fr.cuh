@@ -419,7 +419,7 @@ inline fr_t inv(const fr_t& A) {
   static const modinv::Modulus M = modinv::make_modulus(kL);
   static const w4 r3 = mul(load(fr_r2()), load(fr_r2()));  // R^2 * R^2 * R^-1
   w4 y = load(A), x;
-  modinv::inverse(y.v, M, x.v);
+  if (!modinv::inverse(y.v, M, x.v)) return inv_fermat(A);
   return store(mul(x, r3));
 }
 }  // namespace frh

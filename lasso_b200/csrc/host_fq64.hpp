@@ -69,12 +69,13 @@ inline fe inv_fermat(const fe& z) {  // z^(2^255 - 21): the comparator of inv() 
   fe z2_250_0 = mul(sqr_n(z2_200_0, 50), z2_50_0);
   return mul(sqr_n(z2_250_0, 5), z11);
 }
+inline fe canonical(const fe& a);
 // z^-1 as a canonical residue by binary extended GCD (host_modinv.hpp): ~1.8 us against ~6 us for the exponentiation
 inline fe inv(const fe& z) {
   static const uint64_t kQ[4] = {0xffffffffffffffedULL, 0xffffffffffffffffULL, 0xffffffffffffffffULL, 0x7fffffffffffffffULL};
   static const modinv::Modulus M = modinv::make_modulus(kQ);
   fe r;
-  modinv::inverse(z.v, M, r.v);
+  if (!modinv::inverse(z.v, M, r.v)) return canonical(inv_fermat(z));
   return r;
 }
 inline fe canonical(const fe& a) {

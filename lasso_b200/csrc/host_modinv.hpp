@@ -135,13 +135,17 @@ inline void lincomb_mod(uint64_t r[4], const uint64_t u[4], const uint64_t v[4],
   for (int i = 0; i < 4; i++) r[i] = ge ? s[i] : q[i];
 }
 
-// out = y^-1 mod m as a canonical residue (0 when y == 0 mod m); y is any integer below 2^256, m an odd prime
-inline void inverse(const uint64_t y[4], const Modulus& M, uint64_t out[4]) {
+// out = y^-1 mod m as a canonical residue (0 when y == 0 mod m); y is any integer below 2^256, m an odd prime.
+// len(a) + len(b) shrinks by at least 31 bits per round (Pornin, section 3), so 2*256/31 + 1 = 18 rounds bound the
+// loop; `false` (never seen: the callers then fall back to the exponentiation) if it has not ended after 40.
+inline bool inverse(const uint64_t y[4], const Modulus& M, uint64_t out[4]) {
   uint64_t a[4], b[4], u[4] = {1, 0, 0, 0}, v[4] = {0, 0, 0, 0};
   memcpy(a, y, 32);
   memcpy(b, M.m, 32);
   // invariants: a == u y, b == v y (mod m); a, b >= 0; b odd
+  int rounds = 0;
   while (!is_zero4(a)) {
+    if (++rounds > 40) return false;
     const int la = bitlen4(a), lb_ = bitlen4(b), n = la > lb_ ? la : lb_;
     uint64_t xa, xb;
     if (n <= 64) {
@@ -191,6 +195,7 @@ inline void inverse(const uint64_t y[4], const Modulus& M, uint64_t out[4]) {
   }
   const bool unit = b[0] == 1 && (b[1] | b[2] | b[3]) == 0;
   for (int i = 0; i < 4; i++) out[i] = unit ? v[i] : 0;
+  return true;
 }
 
 }  // namespace modinv
