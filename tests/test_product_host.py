@@ -274,3 +274,26 @@ def test_host_transcript_and_field_code():
         lines = out.stdout.strip().splitlines()
         assert lines[0] == "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
         assert lines[1] == "bad=0" and out.returncode == 0
+
+
+def test_portable_build_of_the_host_code():
+    """The same program with the run-time dispatch compiled out (LB_KECCAK_NO_DISPATCH: what a non-x86 host or a CPU
+    without AVX2 / BMI2 runs): same Merlin vector, same checks."""
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "t.cpp")
+        open(src, "w").write(PROG)
+        exe = os.path.join(d, "t")
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wno-psabi", "-DLB_KECCAK_NO_DISPATCH", "-I", CSRC, src, "-o", exe])
+        out = subprocess.run([exe], capture_output=True, text=True)
+        lines = out.stdout.strip().splitlines()
+        assert lines[0] == "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
+        assert lines[1] == "bad=0" and out.returncode == 0
+
+
+def test_host_microbenchmark_builds():
+    """tools/hostbench/host_bench.cpp (the source of profiles/r02_host_microbench.txt) keeps compiling from the headers."""
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "hb")
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wno-psabi", "-I", CSRC,
+                               os.path.join(ROOT, "tools", "hostbench", "host_bench.cpp"), "-o", exe])
+        assert os.path.exists(exe)
